@@ -1,0 +1,273 @@
+// api.cu — the extern "C" surface declared in include/hairgs_rast.h: argument checks, workspace
+// carving, stage orchestration.  Mirrors the orchestration (not the code) of
+// CudaRasterizer::Rasterizer::{forward,backward,markVisible} rasterizer_impl.cu:141-434.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "hgs_common.cuh"
+
+namespace hgs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return HGS_OK;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return HGS_ERR_CUDA;
+}
+
+// debug mode: synchronise and surface asynchronous kernel faults per stage (auxiliary.h:166-173)
+int stage_check(const char* stage, int debug, cudaStream_t s) {
+    if (!debug) return HGS_OK;
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("[CUDA ERROR] in stage %s: %s", stage, cudaGetErrorString(e));
+        return HGS_ERR_CUDA;
+    }
+    return HGS_OK;
+}
+
+// launchers implemented in the other translation units
+int launch_preprocess_fwd(const hgs_raster_params*, const hgs_raster_inputs*, const GeomLayout&, int32_t*, cudaStream_t);
+int launch_preprocess_bwd(const hgs_raster_params*, const hgs_raster_inputs*, const GeomLayout&, const int32_t*,
+                          const hgs_raster_grads*, cudaStream_t);
+int launch_mark_visible(int, const float*, const float*, uint8_t*, cudaStream_t);
+int launch_view_geom(int, const hgs_raster_params*, const hgs_raster_inputs*, const GeomLayout&, void*, cudaStream_t);
+int launch_emit_keys(int, const GeomLayout&, const uint2*, uint64_t*, uint32_t*, uint32_t, uint32_t, cudaStream_t);
+int launch_sort_pairs(int64_t, int, uint64_t* [2], uint32_t* [2], void*, int*, cudaStream_t);
+int launch_tile_ranges(int64_t, const uint64_t*, uint2*, size_t, cudaStream_t);
+int launch_composite_fwd(int, const ImageLayout&, const uint32_t*, int, int, const GeomLayout&, const float*, float*,
+                         cudaStream_t);
+int launch_composite_bwd(int, const ImageLayout&, const uint32_t*, int, int, const GeomLayout&, const float*,
+                         const float*, const hgs_raster_grads*, cudaStream_t);
+size_t knn_bytes(int P);
+int launch_knn(int P, const float* points, float* out, void* ws, cudaStream_t s);
+
+static int validate(const hgs_raster_params* prm, const hgs_raster_inputs* in, bool forward = true) {
+    if (!prm || !in) { set_error("null params"); return HGS_ERR_INVALID; }
+    if (prm->P < 0 || prm->width <= 0 || prm->height <= 0) { set_error("bad sizes P=%d W=%d H=%d", prm->P, prm->width, prm->height); return HGS_ERR_INVALID; }
+    if (prm->channels < 1 || prm->channels > HGS_MAX_CHANNELS) { set_error("channels must be 1..%d", HGS_MAX_CHANNELS); return HGS_ERR_INVALID; }
+    if (prm->channels != 3 && in->colors_precomp == nullptr) {
+        // rasterizer_impl.cu:242-245
+        set_error("For non-RGB, provide precomputed Gaussian colors!");
+        return HGS_ERR_INVALID;
+    }
+    if ((prm->width + HGS_TILE - 1) / HGS_TILE > 0xffff || (prm->height + HGS_TILE - 1) / HGS_TILE > 0xffff) { set_error("image too large"); return HGS_ERR_INVALID; }
+    if (prm->P > 0) {
+        if (!in->means3D || (forward && !in->opacities) || !in->viewmatrix || !in->projmatrix || !in->background) { set_error("missing required input pointer"); return HGS_ERR_INVALID; }
+        if (!in->colors_precomp && (!in->shs || prm->M <= 0 || !in->cam_pos)) { set_error("need shs (+campos) or colors_precomp"); return HGS_ERR_INVALID; }
+        if (!in->colors_precomp && (prm->D < 0 || prm->D > 3 || (prm->D + 1) * (prm->D + 1) > prm->M)) { set_error("SH degree %d incompatible with M=%d", prm->D, prm->M); return HGS_ERR_INVALID; }
+        if (!in->cov3D_precomp && (!in->scales || !in->rotations)) { set_error("need scales+rotations or cov3D_precomp"); return HGS_ERR_INVALID; }
+    }
+    return HGS_OK;
+}
+
+static inline int end_bit_for(const hgs_raster_params* prm) {
+    const uint32_t gx = (prm->width + HGS_TILE - 1) / HGS_TILE, gy = (prm->height + HGS_TILE - 1) / HGS_TILE;
+    return 32 + tile_id_bits(gx * gy);  // rasterizer_impl.cu:300-308
+}
+
+}  // namespace hgs
+
+using namespace hgs;
+
+extern "C" {
+
+int hgs_abi_version(void) { return HGS_ABI_VERSION; }
+const char* hgs_last_error(void) { return g_err; }
+
+size_t hgs_geom_bytes(int32_t P, int32_t channels) { return carve_geom(nullptr, P, channels).bytes; }
+size_t hgs_image_bytes(int32_t width, int32_t height) { return carve_image(nullptr, width, height).bytes; }
+size_t hgs_binning_bytes(int64_t n) { return carve_binning(nullptr, n).bytes; }
+size_t hgs_sort_bytes(int64_t n) { return carve_sort(nullptr, n).bytes; }
+
+int hgs_forward_stage_a(const hgs_raster_params* prm, const hgs_raster_inputs* in, void* geom_ws, int32_t* radii,
+                        void* stream) {
+    if (int e = validate(prm, in)) return e;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!geom_ws) { set_error("null geometry workspace"); return HGS_ERR_INVALID; }
+    GeomLayout g = carve_geom(geom_ws, prm->P, prm->channels);
+    if (prm->P == 0) return check_cuda(cudaMemsetAsync(g.hdr, 0, g.clear_bytes, s), "memset geom header");
+    if (int e = launch_preprocess_fwd(prm, in, g, radii, s)) return e;
+    return stage_check("preprocess", prm->debug, s);
+}
+
+int hgs_forward_read_num_rendered(const void* geom_ws, int32_t P, uint32_t* n_pinned_host, void* stream) {
+    (void)P;
+    const GeomHeader* h = (const GeomHeader*)geom_ws;
+    return check_cuda(cudaMemcpyAsync(n_pinned_host, &h->num_rendered, 2 * sizeof(uint32_t) + 4, cudaMemcpyDeviceToHost,
+                                      (cudaStream_t)stream), "read num_rendered");
+}
+
+int hgs_forward_stage_b(const hgs_raster_params* prm, const hgs_raster_inputs* in, void* geom_ws, void* binning_ws,
+                        void* image_ws, int64_t N, const int32_t* radii, float* out_color, void* stream) {
+    (void)radii;
+    if (int e = validate(prm, in)) return e;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!geom_ws || !image_ws || (N > 0 && !binning_ws) || !out_color) { set_error("null workspace/output"); return HGS_ERR_INVALID; }
+    if (N < 0 || N > 0x7fffffffll) { set_error("num_rendered out of range"); return HGS_ERR_OVERFLOW; }
+    GeomLayout g = carve_geom(geom_ws, prm->P, prm->channels);
+    ImageLayout im = carve_image(image_ws, prm->width, prm->height);
+    BinningLayout b = carve_binning(binning_ws, N);
+    const uint32_t gx = (prm->width + HGS_TILE - 1) / HGS_TILE, gy = (prm->height + HGS_TILE - 1) / HGS_TILE;
+
+    if (int e = launch_emit_keys(N > 0 ? prm->P : 0, g, g.rects, b.keys[0], b.vals[0], gx, (uint32_t)N, s)) return e;
+    if (int e = stage_check("emit_keys", prm->debug, s)) return e;
+    int res = 0;
+    if (int e = launch_sort_pairs(N, end_bit_for(prm), b.keys, b.vals, b.sort_ws, &res, s)) return e;
+    if (int e = stage_check("sort", prm->debug, s)) return e;
+    if (int e = launch_tile_ranges(N, b.keys[res], im.ranges, (size_t)gx * gy, s)) return e;
+    if (int e = stage_check("tile_ranges", prm->debug, s)) return e;
+    if (int e = launch_composite_fwd(prm->channels, im, b.vals[res], prm->width, prm->height, g, in->background,
+                                     out_color, s)) return e;
+    return stage_check("composite_fwd", prm->debug, s);
+}
+
+int hgs_rasterize_forward(hgs_alloc_fn geom_alloc, void* geom_user, hgs_alloc_fn binning_alloc, void* binning_user,
+                          hgs_alloc_fn image_alloc, void* image_user, const hgs_raster_params* prm,
+                          const hgs_raster_inputs* in, float* out_color, int32_t* radii, void* stream) {
+    if (int e = validate(prm, in)) return e;
+    if (!geom_alloc || !binning_alloc || !image_alloc) { set_error("null allocator"); return HGS_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    void* geom = geom_alloc(geom_user, hgs_geom_bytes(prm->P, prm->channels));
+    void* img = image_alloc(image_user, hgs_image_bytes(prm->width, prm->height));
+    if (!geom || !img) { set_error("allocator returned NULL"); return HGS_ERR_ALLOC; }
+    if (int e = hgs_forward_stage_a(prm, in, geom, radii, s)) return e;
+    // the one blocking read-back of the pass (rasterizer_impl.cu:281)
+    uint32_t host[3] = {0, 0, 0};
+    if (int e = check_cuda(cudaMemcpyAsync(host, geom, sizeof(host), cudaMemcpyDeviceToHost, s), "read num_rendered")) return e;
+    if (int e = check_cuda(cudaStreamSynchronize(s), "sync num_rendered")) return e;
+    if (host[2] || host[0] > 0x7fffffffu) { set_error("instance count overflows int32"); return HGS_ERR_OVERFLOW; }
+    const int64_t N = host[0];
+    void* bin = binning_alloc(binning_user, hgs_binning_bytes(N));
+    if (!bin) { set_error("allocator returned NULL"); return HGS_ERR_ALLOC; }
+    if (int e = hgs_forward_stage_b(prm, in, geom, bin, img, N, radii, out_color, s)) return e;
+    return (int)N;
+}
+
+int hgs_rasterize_backward(const hgs_raster_params* prm, const hgs_raster_inputs* in, int64_t R, const int32_t* radii,
+                           const void* geom_ws, const void* binning_ws, const void* image_ws, const float* dL_dpix,
+                           const hgs_raster_grads* gr, void* stream) {
+    if (int e = validate(prm, in, false)) return e;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!gr || !gr->dL_dmean2D || !gr->dL_dconic || !gr->dL_dopacity || !gr->dL_dcolor || !gr->dL_dmean3D ||
+        !gr->dL_dcov3D || !gr->dL_dscale || !gr->dL_drot || (prm->M > 0 && !gr->dL_dsh)) { set_error("missing gradient output pointer"); return HGS_ERR_INVALID; }
+    if (!geom_ws || !image_ws || !dL_dpix || (R > 0 && !binning_ws)) { set_error("null workspace"); return HGS_ERR_INVALID; }
+    const int P = prm->P;
+    if (P == 0) return HGS_OK;
+    GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels);
+    ImageLayout im = carve_image((void*)image_ws, prm->width, prm->height);
+    BinningLayout b = carve_binning((void*)binning_ws, R);
+    const int res = sort_passes(end_bit_for(prm)) & 1;
+
+    // accumulation targets of the compositor (the only arrays that need clearing)
+    const size_t Pz = (size_t)P;
+    if (gr->dL_dconic == gr->dL_dmean2D + 3 * Pz && gr->dL_dopacity == gr->dL_dconic + 4 * Pz &&
+        gr->dL_dcolor == gr->dL_dopacity + Pz) {
+        // caller packed the four arrays back to back: one memset
+        if (int e = check_cuda(cudaMemsetAsync(gr->dL_dmean2D, 0, Pz * (8 + prm->channels) * 4, s), "memset grads")) return e;
+    } else {
+        if (int e = check_cuda(cudaMemsetAsync(gr->dL_dmean2D, 0, Pz * 3 * 4, s), "memset dL_dmean2D")) return e;
+        if (int e = check_cuda(cudaMemsetAsync(gr->dL_dconic, 0, Pz * 4 * 4, s), "memset dL_dconic")) return e;
+        if (int e = check_cuda(cudaMemsetAsync(gr->dL_dopacity, 0, Pz * 4, s), "memset dL_dopacity")) return e;
+        if (int e = check_cuda(cudaMemsetAsync(gr->dL_dcolor, 0, Pz * prm->channels * 4, s), "memset dL_dcolor")) return e;
+    }
+    if (R > 0) {
+        if (int e = launch_composite_bwd(prm->channels, im, b.vals[res], prm->width, prm->height, g, in->background,
+                                         dL_dpix, gr, s)) return e;
+        if (int e = stage_check("composite_bwd", prm->debug, s)) return e;
+    }
+    if (int e = launch_preprocess_bwd(prm, in, g, radii, gr, s)) return e;
+    return stage_check("preprocess_bwd", prm->debug, s);
+}
+
+int hgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream) {
+    (void)projmatrix;
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) { set_error("bad mark_visible args"); return HGS_ERR_INVALID; }
+    if (P == 0) return HGS_OK;
+    return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+size_t hgs_knn_bytes(int32_t P) { return knn_bytes(P); }
+
+int hgs_dist2_knn3(int32_t P, const float* points, float* mean_dist2, void* workspace, void* stream) {
+    if (P < 0 || (P > 0 && (!points || !mean_dist2 || !workspace))) { set_error("bad knn args"); return HGS_ERR_INVALID; }
+    if (P == 0) return HGS_OK;
+    return launch_knn(P, points, mean_dist2, workspace, (cudaStream_t)stream);
+}
+
+int hgs_sort_pairs(int64_t n, int end_bit, uint64_t* keys_in, uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out,
+                   void* workspace, void* stream) {
+    if (n < 0 || end_bit < 0 || end_bit > 64) { set_error("bad sort args"); return HGS_ERR_INVALID; }
+    if (n == 0) return HGS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint64_t* keys[2] = {keys_in, keys_out};
+    uint32_t* vals[2] = {vals_in, vals_out};
+    int res = 0;
+    if (int e = launch_sort_pairs(n, end_bit, keys, vals, workspace, &res, s)) return e;
+    if (res == 0) {
+        if (int e = check_cuda(cudaMemcpyAsync(keys_out, keys_in, (size_t)n * 8, cudaMemcpyDeviceToDevice, s), "copy keys")) return e;
+        if (int e = check_cuda(cudaMemcpyAsync(vals_out, vals_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, s), "copy vals")) return e;
+    }
+    return HGS_OK;
+}
+
+int64_t hgs_state_view(int what, const hgs_raster_params* prm, const hgs_raster_inputs* in, int64_t N,
+                       const void* geom_ws, const void* binning_ws, const void* image_ws, void* dst, void* stream) {
+    if (!prm || !dst) { set_error("null args"); return HGS_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int P = prm->P;
+    const size_t hw = (size_t)prm->width * prm->height;
+    const size_t tiles = (size_t)((prm->width + HGS_TILE - 1) / HGS_TILE) * ((prm->height + HGS_TILE - 1) / HGS_TILE);
+    auto d2d = [&](const void* src, size_t bytes) -> int64_t {
+        if (bytes == 0) return 0;
+        if (int e = check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s), "state view copy")) return e;
+        return (int64_t)bytes;
+    };
+    switch (what) {
+        case HGS_VIEW_DEPTHS: case HGS_VIEW_MEANS2D: case HGS_VIEW_CONIC_OPACITY: case HGS_VIEW_RGB:
+        case HGS_VIEW_CLAMPED: case HGS_VIEW_COV3D: {
+            if (!geom_ws || !in) { set_error("null geometry workspace"); return HGS_ERR_INVALID; }
+            if (P == 0) return 0;
+            GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels);
+            if (int e = launch_view_geom(what, prm, in, g, dst, s)) return e;
+            static const int per[] = {4, 8, 16, 0, 0, 0, 3};
+            if (what == HGS_VIEW_RGB) return (int64_t)P * prm->channels * 4;
+            if (what == HGS_VIEW_COV3D) return (int64_t)P * 24;
+            return (int64_t)P * per[what];
+        }
+        case HGS_VIEW_TILES_TOUCHED: case HGS_VIEW_POINT_OFFSETS: {
+            if (!geom_ws) { set_error("null geometry workspace"); return HGS_ERR_INVALID; }
+            GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels);
+            return d2d(what == HGS_VIEW_TILES_TOUCHED ? (void*)g.tiles_touched : (void*)g.offsets, (size_t)P * 4);
+        }
+        case HGS_VIEW_KEYS_SORTED: case HGS_VIEW_POINT_LIST: {
+            if (N > 0 && !binning_ws) { set_error("null binning workspace"); return HGS_ERR_INVALID; }
+            BinningLayout b = carve_binning((void*)binning_ws, N);
+            const int res = sort_passes(end_bit_for(prm)) & 1;
+            if (what == HGS_VIEW_KEYS_SORTED) return d2d(b.keys[res], (size_t)N * 8);
+            return d2d(b.vals[res], (size_t)N * 4);
+        }
+        case HGS_VIEW_RANGES: case HGS_VIEW_FINAL_T: case HGS_VIEW_N_CONTRIB: {
+            if (!image_ws) { set_error("null image workspace"); return HGS_ERR_INVALID; }
+            ImageLayout im = carve_image((void*)image_ws, prm->width, prm->height);
+            if (what == HGS_VIEW_RANGES) return d2d(im.ranges, tiles * 8);
+            if (what == HGS_VIEW_FINAL_T) return d2d(im.final_T, hw * 4);
+            return d2d(im.n_contrib, hw * 4);
+        }
+        default: break;
+    }
+    set_error("unknown view %d", what);
+    return HGS_ERR_INVALID;
+}
+
+}  // extern "C"

@@ -1,0 +1,337 @@
+// binning.cu — instance generation, (tile|depth) sort and tile ranges:
+//   emit_keys      : load-balanced key/value emission (replaces duplicateWithKeys rasterizer_impl.cu:70-111:
+//                    there one thread serially writes its whole rect; here a block's instances are dealt
+//                    round-robin to its threads so every store is coalesced)
+//   radix_histogram + onesweep_pass : hand-written stable LSD radix sort, 8-bit digits, one global
+//                    histogram pass + one chained-scan (decoupled look-back) scatter pass per digit, with
+//                    match.any warp-aggregated ranking (replaces cub::DeviceRadixSort::SortPairs
+//                    rasterizer_impl.cu:303-308)
+//   tile_ranges    : identifyTileRanges rasterizer_impl.cu:116-138
+#include "hgs_common.cuh"
+
+namespace hgs {
+
+// ------------------------------------------------------------------------------------------------
+// key emission
+// ------------------------------------------------------------------------------------------------
+// key = (tile_id << 32) | float_bits(depth), value = Gaussian id; a Gaussian's instances occupy
+// slots [offsets[i]-touched, offsets[i]) with tiles enumerated y-outer / x-inner
+// (rasterizer_impl.cu:88-108).
+__global__ void __launch_bounds__(256) emit_keys_kernel(int P, const uint2* __restrict__ rects,
+                                                        const float* __restrict__ depths,
+                                                        const uint32_t* __restrict__ offsets,
+                                                        const uint32_t* __restrict__ touched_arr,
+                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                        uint32_t grid_x, uint32_t capacity) {
+    __shared__ uint32_t s_start[256];  // block-local exclusive start of each Gaussian's run
+    __shared__ uint32_t s_xy[256];     // xmin | ymin << 16
+    __shared__ uint32_t s_w[256];      // rect width in tiles
+    __shared__ uint32_t s_depth[256];
+    __shared__ uint32_t s_base, s_total;
+
+    const int tid = threadIdx.x;
+    const int g0 = blockIdx.x * 256;
+    const int g = g0 + tid;
+    uint32_t touched = 0, incl = 0;
+    if (g < P) {
+        touched = touched_arr[g];
+        incl = offsets[g];
+    }
+    if (tid == 0) s_base = incl - touched;  // == offsets[g0-1]
+    __syncthreads();
+    const uint32_t base = s_base;
+    s_start[tid] = (g < P) ? (incl - touched - base) : 0xffffffffu;
+    if (touched > 0) {
+        const uint2 r = rects[g];
+        s_xy[tid] = r.x;
+        s_w[tid] = (r.y & 0xffffu) - (r.x & 0xffffu);
+        s_depth[tid] = __float_as_uint(depths[g]);
+    }
+    const int last = min(P - g0, 256) - 1;
+    if (tid == last) s_total = incl - base;
+    __syncthreads();
+    const uint32_t total = s_total;
+    for (uint32_t s = tid; s < total; s += 256) {
+        // largest j with s_start[j] <= s
+        int lo = 0, hi = last;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_start[mid] <= s) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t k = s - s_start[lo];
+        const uint32_t w = s_w[lo];
+        const uint32_t xy = s_xy[lo];
+        const uint32_t ky = k / w;
+        const uint32_t kx = k - ky * w;
+        const uint32_t x = (xy & 0xffffu) + kx;
+        const uint32_t y = (xy >> 16) + ky;
+        const uint64_t key = ((uint64_t)(y * grid_x + x) << 32) | (uint64_t)s_depth[lo];
+        const uint32_t slot = base + s;
+        if (slot < capacity) {
+            keys[slot] = key;
+            vals[slot] = (uint32_t)(g0 + lo);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// radix sort
+// ------------------------------------------------------------------------------------------------
+static constexpr uint32_t kStFlagAgg = 1u << 30;
+static constexpr uint32_t kStFlagIncl = 2u << 30;
+static constexpr uint32_t kStValMask = (1u << 30) - 1;
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+// One read of the keys, all digit histograms at once.
+__global__ void __launch_bounds__(256) radix_histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n,
+                                                              int passes, uint32_t* __restrict__ ghist) {
+    __shared__ uint32_t s_hist[kMaxPasses * kRadix];
+    for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t k = keys[i];
+        for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p * kRadix + (uint32_t)((k >> (8 * p)) & 0xffu)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) {
+        const uint32_t v = s_hist[i];
+        if (v) atomicAdd(&ghist[i], v);
+    }
+}
+
+struct OnesweepSmem {
+    union {
+        uint64_t keys[kSortTile];
+        uint32_t vals[kSortTile];
+    } u;
+    uint32_t warp_hist[kSortThreads / 32][kRadix];
+    uint32_t excl[kRadix];   // block-local exclusive digit offsets
+    uint32_t gbase[kRadix];  // global position of local sorted index 0 of each digit (minus excl)
+    uint32_t scan_tmp[kSortThreads / 32];
+    uint32_t tile;
+};
+
+// block-wide exclusive scan of one value per thread (256 threads); returns exclusive prefix
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* tmp /*[8]*/) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += n;
+    }
+    if (lane == 31) tmp[warp] = incl;
+    __syncthreads();
+    uint32_t wex = 0;
+#pragma unroll
+    for (int w = 0; w < kSortThreads / 32; ++w)
+        if ((uint32_t)w < warp) wex += tmp[w];
+    __syncthreads();
+    return wex + incl - v;
+}
+
+__global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(
+    const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
+    uint32_t* __restrict__ vals_out, uint32_t n, int shift, const uint32_t* __restrict__ ghist /*[256]*/,
+    uint32_t* __restrict__ status /*[ntiles*256]*/, uint32_t* __restrict__ ticket) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int w = 0; w < kSortThreads / 32; ++w) sm.warp_hist[w][tid] = 0;
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    const uint32_t base = tile * kSortTile;
+    const uint32_t nvalid = min((uint32_t)kSortTile, n - base);
+
+    // ---- load keys, warp-striped: item r of this lane is element warp*512 + r*32 + lane ----------
+    uint64_t key[kSortItems];
+    const uint32_t wbase = warp * (kSortItems * 32) + lane;
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t li = wbase + r * 32;
+        key[r] = (li < nvalid) ? keys_in[base + li] : ~0ull;
+    }
+
+    // ---- per-warp ranking with match.any ---------------------------------------------------------
+    uint32_t rank[kSortItems];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t* wh = sm.warp_hist[warp];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t d = (uint32_t)(key[r] >> shift) & 0xffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t prev = wh[d];
+        __syncwarp();
+        const uint32_t lrank = __popc(peers & lt_mask);
+        if (lrank == 0) wh[d] = prev + __popc(peers);
+        __syncwarp();
+        rank[r] = prev + lrank;
+    }
+    __syncthreads();
+
+    // ---- digit `tid`: prefix over warps, block total ----------------------------------------------
+    uint32_t block_count = 0;
+#pragma unroll
+    for (int w = 0; w < kSortThreads / 32; ++w) {
+        const uint32_t c = sm.warp_hist[w][tid];
+        sm.warp_hist[w][tid] = block_count;
+        block_count += c;
+    }
+    // publish as early as possible so successors' look-back does not stall on us
+    uint32_t* my_status = status + (size_t)tile * kRadix + tid;
+    if (tile == 0) st_relaxed_u32(my_status, kStFlagIncl | block_count);
+    else st_relaxed_u32(my_status, kStFlagAgg | block_count);
+
+    const uint32_t local_excl = block_excl_scan_256(block_count, sm.scan_tmp);
+    const uint32_t gexcl = block_excl_scan_256(ghist[tid], sm.scan_tmp);
+
+    uint32_t prev_sum = 0;
+    if (tile > 0) {
+        int t = (int)tile - 1;
+        while (true) {
+            const uint32_t* ps = status + (size_t)t * kRadix + tid;
+            uint32_t w = ld_relaxed_u32(ps);
+            while ((w >> 30) == 0) w = ld_relaxed_u32(ps);
+            prev_sum += w & kStValMask;
+            if ((w >> 30) == 2) break;
+            --t;
+        }
+        st_relaxed_u32(my_status, kStFlagIncl | ((prev_sum + block_count) & kStValMask));
+    }
+    sm.excl[tid] = local_excl;
+    sm.gbase[tid] = gexcl + prev_sum - local_excl;
+    __syncthreads();
+
+    // ---- scatter keys into block-sorted order in shared memory, then coalesced to global ----------
+    uint32_t pos[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t d = (uint32_t)(key[r] >> shift) & 0xffu;
+        pos[r] = sm.excl[d] + wh[d] + rank[r];
+        sm.u.keys[pos[r]] = key[r];
+    }
+    __syncthreads();
+    uint32_t gidx[kSortItems];
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint32_t li = tid + k * kSortThreads;
+        gidx[k] = 0xffffffffu;
+        if (li < nvalid) {
+            const uint64_t kk = sm.u.keys[li];
+            const uint32_t d = (uint32_t)(kk >> shift) & 0xffu;
+            gidx[k] = sm.gbase[d] + li;
+            keys_out[gidx[k]] = kk;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t li = wbase + r * 32;
+        if (li < nvalid) sm.u.vals[pos[r]] = vals_in[base + li];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint32_t li = tid + k * kSortThreads;
+        if (li < nvalid) vals_out[gidx[k]] = sm.u.vals[li];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tile ranges
+// ------------------------------------------------------------------------------------------------
+__global__ void tile_ranges_kernel(uint32_t L, const uint64_t* __restrict__ keys, uint2* __restrict__ ranges) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= L) return;
+    const uint32_t cur = (uint32_t)(keys[idx] >> 32);
+    if (idx == 0) {
+        ranges[cur].x = 0;
+    } else {
+        const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+        if (cur != prev) {
+            ranges[prev].y = idx;
+            ranges[cur].x = idx;
+        }
+    }
+    if (idx == L - 1) ranges[cur].y = L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+int launch_emit_keys(int P, const GeomLayout& g, const uint2* rects, uint64_t* keys, uint32_t* vals, uint32_t grid_x,
+                     uint32_t capacity, cudaStream_t s) {
+    if (P <= 0) return HGS_OK;
+    emit_keys_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, rects, g.depths, g.offsets, g.tiles_touched, keys, vals,
+                                                      grid_x, capacity);
+    return check_cuda(cudaGetLastError(), "emit_keys launch");
+}
+
+// Sorts n pairs on key bits [0, end_bit).  keys[0]/vals[0] hold the input; returns in *result_buf
+// which ping-pong buffer (0/1) holds the sorted output.
+int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* sort_ws, int* result_buf,
+                      cudaStream_t s) {
+    // the sorted data always ends in buffer (passes & 1), also for the trivial sizes
+    const int passes = sort_passes(end_bit);
+    if (passes > kMaxPasses) { set_error("end_bit %d too large", end_bit); return HGS_ERR_INVALID; }
+    *result_buf = passes & 1;
+    if (n <= 0) return HGS_OK;
+    if (n == 1 || end_bit <= 0) {
+        if (passes & 1) {
+            if (int e = check_cuda(cudaMemcpyAsync(keys[1], keys[0], (size_t)n * 8, cudaMemcpyDeviceToDevice, s), "copy keys")) return e;
+            if (int e = check_cuda(cudaMemcpyAsync(vals[1], vals[0], (size_t)n * 4, cudaMemcpyDeviceToDevice, s), "copy vals")) return e;
+        }
+        return HGS_OK;
+    }
+    if (n >= (1ll << 30)) {
+        set_error("radix sort supports < 2^30 instances, got %lld", (long long)n);
+        return HGS_ERR_OVERFLOW;
+    }
+    SortLayout L = carve_sort(sort_ws, n);
+    const size_t clear = (size_t)((char*)L.status - (char*)L.hist) + (size_t)passes * L.ntiles * kRadix * 4;
+    if (int e = check_cuda(cudaMemsetAsync(L.hist, 0, clear, s), "memset sort ws")) return e;
+    static int smem_set = 0;
+    if (!smem_set) {
+        if (int e = check_cuda(cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)sizeof(OnesweepSmem)), "onesweep smem attr")) return e;
+        smem_set = 1;
+    }
+    const uint32_t nn = (uint32_t)n;
+    int64_t hb = (n + 256 * 8 - 1) / (256 * 8);
+    const int hblocks = (int)(hb < 148 * 8 ? hb : 148 * 8);
+    radix_histogram_kernel<<<hblocks, 256, 0, s>>>(keys[0], nn, passes, L.hist);
+    if (int e = check_cuda(cudaGetLastError(), "radix_histogram launch")) return e;
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        onesweep_pass_kernel<<<(unsigned)L.ntiles, kSortThreads, sizeof(OnesweepSmem), s>>>(
+            keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], nn, 8 * p, L.hist + p * kRadix,
+            L.status + (size_t)p * L.ntiles * kRadix, L.tickets + p);
+        if (int e = check_cuda(cudaGetLastError(), "onesweep launch")) return e;
+        cur ^= 1;
+    }
+    *result_buf = cur;
+    return HGS_OK;
+}
+
+int launch_tile_ranges(int64_t n, const uint64_t* keys_sorted, uint2* ranges, size_t tiles, cudaStream_t s) {
+    if (int e = check_cuda(cudaMemsetAsync(ranges, 0, tiles * sizeof(uint2), s), "memset ranges")) return e;
+    if (n > 0) {
+        tile_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((uint32_t)n, keys_sorted, ranges);
+        return check_cuda(cudaGetLastError(), "tile_ranges launch");
+    }
+    return HGS_OK;
+}
+
+}  // namespace hgs

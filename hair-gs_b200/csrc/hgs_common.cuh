@@ -1,0 +1,248 @@
+// hgs_common.cuh — shared device helpers, workspace layouts and launch utilities of libhairgs_rast.
+// sm_100a only.  Nothing here is derived from the reference's sources; where an arithmetic order is
+// part of the numerical contract the reference file:line is cited.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/hairgs_rast.h"
+
+#define HGS_TILE_PIX (HGS_TILE * HGS_TILE)
+
+namespace hgs {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing (host)
+// ------------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+int stage_check(const char* stage, int debug, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------
+// Workspace layouts.  All sub-arrays 256-B aligned; the same carve is repeated by forward, backward
+// and the state viewers (the role GeometryState/ImageState/BinningState::fromChunk play in the
+// reference, rasterizer_impl.cu:155-194 — but a different, 32-byte-record layout).
+// ------------------------------------------------------------------------------------------------
+static constexpr size_t kAlign = 256;
+__host__ __device__ inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }
+
+struct GeomHeader {            // first 256 B of the geometry workspace
+    uint32_t num_rendered;     // total instance count N (written by the last preprocess block)
+    uint32_t block_ticket;     // dynamic block id for the in-kernel chained scan
+    uint32_t overflow;         // set when N would exceed 2^31-1
+    uint32_t pad[61];
+};
+
+// One 32-byte record per Gaussian: everything the compositors need besides colour, in one sector.
+struct __align__(16) GaussRecLo { float x, y, conic_a, conic_b; };   // means2D + conic.xy
+struct __align__(16) GaussRecHi { float conic_c, opacity, hx, hy; }; // conic.z + opacity + alpha>=1/255 half extents
+
+static constexpr int kPreprocThreads = 256;
+
+struct GeomLayout {
+    GeomHeader* hdr;
+    unsigned long long* scan_state;  // [ceil(P/256)] chained-scan status words (directly after hdr: one memset clears both)
+    float4* rec;              // [2P] : rec[2i] = GaussRecLo, rec[2i+1] = GaussRecHi
+    float* rgb;               // [P*cstride] colours used by the compositors (SH result or repacked colors_precomp)
+    float* depths;            // [P]
+    uint32_t* tiles_touched;  // [P]
+    uint32_t* offsets;        // [P] inclusive scan of tiles_touched
+    uint8_t* clamped;         // [P] bit c set when SH channel c was clamped at 0
+    uint2* rects;             // [P] tile rect: .x = xmin | ymin<<16, .y = xmax | ymax<<16 (valid when tiles_touched > 0)
+    size_t bytes;
+    size_t clear_bytes;       // hdr + scan_state: what must be zeroed before stage A
+    int cstride;
+};
+
+__host__ __device__ inline int color_stride(int channels) { return channels <= 4 ? 4 : 8; }
+
+__host__ __device__ inline GeomLayout carve_geom(void* base, int P, int channels) {
+    GeomLayout g;
+    char* p = (char*)base;
+    size_t off = 0;
+    size_t Pz = (size_t)(P > 0 ? P : 0);
+    size_t nblk = (Pz + kPreprocThreads - 1) / kPreprocThreads;
+    g.cstride = color_stride(channels);
+    g.hdr = (GeomHeader*)(p + off);            off = align_up(off + sizeof(GeomHeader));
+    g.scan_state = (unsigned long long*)(p + off); off = align_up(off + nblk * 8);
+    g.clear_bytes = off;
+    g.rec = (float4*)(p + off);                off = align_up(off + Pz * 32);
+    g.rgb = (float*)(p + off);                 off = align_up(off + Pz * 4 * g.cstride);
+    g.depths = (float*)(p + off);              off = align_up(off + Pz * 4);
+    g.tiles_touched = (uint32_t*)(p + off);    off = align_up(off + Pz * 4);
+    g.offsets = (uint32_t*)(p + off);          off = align_up(off + Pz * 4);
+    g.clamped = (uint8_t*)(p + off);           off = align_up(off + Pz);
+    g.rects = (uint2*)(p + off);               off = align_up(off + Pz * 8);
+    g.bytes = off;
+    return g;
+}
+
+struct ImageLayout {
+    float* final_T;        // [H*W]
+    uint32_t* n_contrib;   // [H*W]
+    uint2* ranges;         // [tiles]  (the reference over-allocates H*W entries, rasterizer_impl.cu:172-178)
+    size_t bytes;
+};
+
+__host__ __device__ inline ImageLayout carve_image(void* base, int W, int H) {
+    ImageLayout im;
+    char* p = (char*)base;
+    size_t off = 0;
+    size_t hw = (size_t)W * H;
+    size_t tiles = (size_t)((W + HGS_TILE - 1) / HGS_TILE) * ((H + HGS_TILE - 1) / HGS_TILE);
+    im.final_T = (float*)(p + off);      off = align_up(off + hw * 4);
+    im.n_contrib = (uint32_t*)(p + off); off = align_up(off + hw * 4);
+    im.ranges = (uint2*)(p + off);       off = align_up(off + tiles * 8);
+    im.bytes = off;
+    return im;
+}
+
+// Radix sort geometry (binning.cu)
+static constexpr int kSortThreads = 256;
+static constexpr int kSortItems = 16;                       // keys per thread
+static constexpr int kSortTile = kSortThreads * kSortItems; // 4096 keys per block
+static constexpr int kRadixBits = 8;
+static constexpr int kRadix = 1 << kRadixBits;
+static constexpr int kMaxPasses = 8;
+
+struct SortLayout {
+    uint32_t* hist;     // [kMaxPasses * 256] global digit histograms -> exclusive offsets
+    uint32_t* tickets;  // [kMaxPasses] dynamic tile ids
+    uint32_t* status;   // [kMaxPasses * ntiles * 256] decoupled look-back words
+    size_t bytes;
+    size_t ntiles;
+};
+
+__host__ __device__ inline SortLayout carve_sort(void* base, int64_t n) {
+    SortLayout s;
+    char* p = (char*)base;
+    size_t off = 0;
+    s.ntiles = (size_t)((n + kSortTile - 1) / kSortTile);
+    if (s.ntiles == 0) s.ntiles = 1;
+    s.hist = (uint32_t*)(p + off);    off = align_up(off + (size_t)kMaxPasses * kRadix * 4);
+    s.tickets = (uint32_t*)(p + off); off = align_up(off + (size_t)kMaxPasses * 4);
+    s.status = (uint32_t*)(p + off);  off = align_up(off + (size_t)kMaxPasses * s.ntiles * kRadix * 4);
+    s.bytes = off;
+    return s;
+}
+
+struct BinningLayout {
+    uint64_t* keys[2];   // ping-pong key buffers; [0] receives the emitted (unsorted) keys
+    uint32_t* vals[2];   // ping-pong Gaussian ids
+    void* sort_ws;
+    size_t bytes;
+};
+
+__host__ __device__ inline BinningLayout carve_binning(void* base, int64_t n) {
+    BinningLayout b;
+    char* p = (char*)base;
+    size_t off = 0;
+    size_t nz = (size_t)(n > 0 ? n : 0);
+    b.keys[0] = (uint64_t*)(p + off); off = align_up(off + nz * 8);
+    b.keys[1] = (uint64_t*)(p + off); off = align_up(off + nz * 8);
+    b.vals[0] = (uint32_t*)(p + off); off = align_up(off + nz * 4);
+    b.vals[1] = (uint32_t*)(p + off); off = align_up(off + nz * 4);
+    b.sort_ws = (void*)(p + off);
+    SortLayout s = carve_sort(b.sort_ws, n);
+    off = align_up(off + s.bytes);
+    b.bytes = off;
+    return b;
+}
+
+// Number of 8-bit passes for keys whose significant bits are [0, end_bit), and which ping-pong
+// buffer ends up holding the sorted data.
+__host__ __device__ inline int sort_passes(int end_bit) { return (end_bit + kRadixBits - 1) / kRadixBits; }
+
+// Bits needed for tile ids: same rule as the reference's getHigherMsb (rasterizer_impl.cu:35-50),
+// restated as "smallest b with (n >> b) == 0" — identical results for every n >= 1.
+__host__ inline int tile_id_bits(uint32_t n) {
+    int b = 0;
+    while (b < 32 && (n >> b)) ++b;
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device math helpers
+// ------------------------------------------------------------------------------------------------
+// Column-major 3x3 (m[c][r]) with the textbook product order sum_k A[k][r]*B[c][k], k ascending.
+// The evaluation order is part of the bit-exactness contract with the reference build
+// (SURVEY.md §7.3 item 1): products are accumulated left to right so the compiler's FMA
+// contraction sees the same expression trees.
+struct M3 {
+    float m[3][3];
+};
+
+__device__ __forceinline__ M3 m3_mul(const M3& a, const M3& b) {
+    M3 r;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            r.m[c][q] = a.m[0][q] * b.m[c][0] + a.m[1][q] * b.m[c][1] + a.m[2][q] * b.m[c][2];
+    return r;
+}
+
+__device__ __forceinline__ M3 m3_transpose(const M3& a) {
+    M3 r;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) r.m[c][q] = a.m[q][c];
+    return r;
+}
+
+// x' = m0 x + m4 y + m8 z + m12 ... (auxiliary.h:58-77 convention: column-major 4x4)
+__device__ __forceinline__ float3 xform_point_4x3(const float3 p, const float* __restrict__ m) {
+    float3 t;
+    t.x = m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12];
+    t.y = m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13];
+    t.z = m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14];
+    return t;
+}
+__device__ __forceinline__ float4 xform_point_4x4(const float3 p, const float* __restrict__ m) {
+    float4 t;
+    t.x = m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12];
+    t.y = m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13];
+    t.z = m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14];
+    t.w = m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15];
+    return t;
+}
+
+// Pixel coordinate of an NDC coordinate, evaluated in double like the reference (auxiliary.h:41-44).
+__device__ __forceinline__ float ndc_to_pix(float v, int S) { return ((v + 1.0) * S - 1.0) * 0.5; }
+
+// Tile rectangle of a splat (auxiliary.h:46-56): C truncation, clamp to the grid.
+__device__ __forceinline__ void tile_rect(const float2 p, int max_radius, uint2& rmin, uint2& rmax,
+                                          const uint32_t gx, const uint32_t gy) {
+    rmin.x = min(gx, (uint32_t)max((int)0, (int)((p.x - max_radius) / HGS_TILE)));
+    rmin.y = min(gy, (uint32_t)max((int)0, (int)((p.y - max_radius) / HGS_TILE)));
+    rmax.x = min(gx, (uint32_t)max((int)0, (int)((p.x + max_radius + HGS_TILE - 1) / HGS_TILE)));
+    rmax.y = min(gy, (uint32_t)max((int)0, (int)((p.y + max_radius + HGS_TILE - 1) / HGS_TILE)));
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// cp.async helpers (LDGSTS): 16-byte global -> shared copies without register staging.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// streaming 128-bit loads (read-once data: keep it out of L1)
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+}  // namespace hgs

@@ -1,0 +1,773 @@
+// preprocess.cu — per-Gaussian stages of the rasterizer:
+//   preprocess_fwd : frustum cull + cov3D + EWA cov2D + conic + radius + tile rect + SH->RGB
+//                    + in-kernel chained (decoupled look-back) inclusive scan of tiles_touched
+//                    (replaces preprocessCUDA forward.cu:155-256, cub::DeviceScan rasterizer_impl.cu:277
+//                     and checkFrustum's cull, one launch instead of three)
+//   preprocess_bwd : dL/dconic,dL/dmean2D,dL/dcolor -> dL/dmean3D, dL/dcov3D, dL/dsh, dL/dscale, dL/drot
+//                    (replaces computeCov2DCUDA backward_distwar.cu:145-275 + preprocessCUDA :347-397
+//                     + the nine torch::zeros of rasterize_points.cu:151-159: every element written once)
+//   mark_visible   : checkFrustum rasterizer_impl.cu:54-66
+// Arithmetic order follows SURVEY.md App. A op for op: radii / tile rects / depth bits must equal the
+// reference build's bit for bit.
+#include "hgs_common.cuh"
+
+namespace hgs {
+
+__device__ __constant__ float kSH_C0 = 0.28209479177387814f;
+__device__ __constant__ float kSH_C1 = 0.4886025119029199f;
+__device__ __constant__ float kSH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                           -1.0925484305920792f, 0.5462742152960396f};
+__device__ __constant__ float kSH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                           0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                           -0.5900435899266435f};
+
+struct PreArgs {
+    int P, D, M, W, H, channels, cstride;
+    float tan_fovx, tan_fovy, focal_x, focal_y, scale_modifier;
+    uint32_t grid_x, grid_y;
+    const float* means3D;
+    const float* scales;
+    const float* rotations;
+    const float* opacities;
+    const float* shs;
+    const float* cov3D_precomp;
+    const float* colors_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* cam_pos;
+    int32_t* radii;
+    GeomLayout g;
+    uint32_t nblocks;
+};
+
+// Sigma = (S R)^T (S R) from scale and raw (un-normalised) quaternion (forward.cu:118-152).
+__device__ __forceinline__ void cov3d_from_scale_rot(const float3 scale, float mod, const float4 rot, float* cov3D) {
+    M3 S;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) S.m[c][q] = (c == q) ? 1.0f : 0.0f;
+    S.m[0][0] = mod * scale.x;
+    S.m[1][1] = mod * scale.y;
+    S.m[2][2] = mod * scale.z;
+    const float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
+    M3 R;
+    R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z);       R.m[0][2] = 2.f * (x * z + r * y);
+    R.m[1][0] = 2.f * (x * y + r * z);       R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
+    R.m[2][0] = 2.f * (x * z - r * y);       R.m[2][1] = 2.f * (y * z + r * x);       R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+    M3 Mx = m3_mul(S, R);
+    M3 Sigma = m3_mul(m3_transpose(Mx), Mx);
+    cov3D[0] = Sigma.m[0][0];
+    cov3D[1] = Sigma.m[0][1];
+    cov3D[2] = Sigma.m[0][2];
+    cov3D[3] = Sigma.m[1][1];
+    cov3D[4] = Sigma.m[1][2];
+    cov3D[5] = Sigma.m[2][2];
+}
+
+// EWA projection of a 3D covariance (forward.cu:74-113).  Returns (xx, xy, yy) with the 0.3 low-pass.
+// Also hands back T = W*J (needed again by the backward pass).
+__device__ __forceinline__ float3 cov2d_ewa(const float3 mean, float focal_x, float focal_y, float tan_fovx,
+                                            float tan_fovy, const float* cov3D, const float* __restrict__ view,
+                                            M3& T, float3& t_out, float& txtz_out, float& tytz_out) {
+    float3 t = xform_point_4x3(mean, view);
+    const float limx = 1.3f * tan_fovx;
+    const float limy = 1.3f * tan_fovy;
+    const float txtz = t.x / t.z;
+    const float tytz = t.y / t.z;
+    t.x = min(limx, max(-limx, txtz)) * t.z;
+    t.y = min(limy, max(-limy, tytz)) * t.z;
+    txtz_out = txtz;
+    tytz_out = tytz;
+    t_out = t;
+
+    M3 J;
+    J.m[0][0] = focal_x / t.z; J.m[0][1] = 0.0f;          J.m[0][2] = -(focal_x * t.x) / (t.z * t.z);
+    J.m[1][0] = 0.0f;          J.m[1][1] = focal_y / t.z; J.m[1][2] = -(focal_y * t.y) / (t.z * t.z);
+    J.m[2][0] = 0.0f;          J.m[2][1] = 0.0f;          J.m[2][2] = 0.0f;
+    M3 Wm;
+    Wm.m[0][0] = view[0]; Wm.m[0][1] = view[4]; Wm.m[0][2] = view[8];
+    Wm.m[1][0] = view[1]; Wm.m[1][1] = view[5]; Wm.m[1][2] = view[9];
+    Wm.m[2][0] = view[2]; Wm.m[2][1] = view[6]; Wm.m[2][2] = view[10];
+    T = m3_mul(Wm, J);
+    M3 V;
+    V.m[0][0] = cov3D[0]; V.m[0][1] = cov3D[1]; V.m[0][2] = cov3D[2];
+    V.m[1][0] = cov3D[1]; V.m[1][1] = cov3D[3]; V.m[1][2] = cov3D[4];
+    V.m[2][0] = cov3D[2]; V.m[2][1] = cov3D[4]; V.m[2][2] = cov3D[5];
+    M3 cov = m3_mul(m3_mul(m3_transpose(T), m3_transpose(V)), T);
+    cov.m[0][0] += 0.3f;
+    cov.m[1][1] += 0.3f;
+    return make_float3(cov.m[0][0], cov.m[0][1], cov.m[1][1]);
+}
+
+// SH basis evaluation (forward.cu:20-71), one colour channel at a time; sh points at coefficient 0
+// of this Gaussian, layout [k][3].
+__device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ sh, const float3 pos,
+                                            const float3 campos, uint32_t& clamp_bits) {
+    float3 dir = make_float3(pos.x - campos.x, pos.y - campos.y, pos.z - campos.z);
+    const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+    dir.x = dir.x / len;
+    dir.y = dir.y / len;
+    dir.z = dir.z / len;
+    float res[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) res[c] = kSH_C0 * sh[0 * 3 + c];
+    if (deg > 0) {
+        const float x = dir.x, y = dir.y, z = dir.z;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            res[c] = res[c] - kSH_C1 * y * sh[1 * 3 + c] + kSH_C1 * z * sh[2 * 3 + c] - kSH_C1 * x * sh[3 * 3 + c];
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z;
+            const float xy = x * y, yz = y * z, xz = x * z;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                res[c] = res[c] + kSH_C2[0] * xy * sh[4 * 3 + c] + kSH_C2[1] * yz * sh[5 * 3 + c] +
+                         kSH_C2[2] * (2.0f * zz - xx - yy) * sh[6 * 3 + c] + kSH_C2[3] * xz * sh[7 * 3 + c] +
+                         kSH_C2[4] * (xx - yy) * sh[8 * 3 + c];
+            if (deg > 2) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    res[c] = res[c] + kSH_C3[0] * y * (3.0f * xx - yy) * sh[9 * 3 + c] +
+                             kSH_C3[1] * xy * z * sh[10 * 3 + c] +
+                             kSH_C3[2] * y * (4.0f * zz - xx - yy) * sh[11 * 3 + c] +
+                             kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[12 * 3 + c] +
+                             kSH_C3[4] * x * (4.0f * zz - xx - yy) * sh[13 * 3 + c] +
+                             kSH_C3[5] * z * (xx - yy) * sh[14 * 3 + c] +
+                             kSH_C3[6] * x * (xx - 3.0f * yy) * sh[15 * 3 + c];
+            }
+        }
+    }
+    clamp_bits = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        res[c] += 0.5f;
+        if (res[c] < 0) clamp_bits |= (1u << c);
+        res[c] = fmaxf(res[c], 0.0f);
+    }
+    return make_float3(res[0], res[1], res[2]);
+}
+
+// Conservative half extents of the region where alpha = opacity*exp(power) can reach 1/255
+// (outside it the reference's `alpha < 1/255 -> continue`, forward.cu:343-345, always fires).
+// Used only to SKIP work inside the compositors; never changes tiles_touched / keys / outputs.
+__device__ __forceinline__ float2 alpha_extent(float A, float B, float C, float o) {
+    const float inf = __int_as_float(0x7f800000);
+    if (!(o >= 1.0f / 255.0f)) {
+        // o < 1/255 (or NaN): with power <= 0, o*exp(power) <= o < 1/255 -> never blends.
+        // NaN opacity must not be culled (NaN compares false in the reference's skip tests).
+        return (o == o) ? make_float2(-inf, -inf) : make_float2(inf, inf);
+    }
+    const float det = A * C - B * B;
+    if (!(A > 0.0f) || !(C > 0.0f) || !(det > 1e-4f * A * C)) return make_float2(inf, inf);
+    const float t = 2.0f * logf(255.0f * o) * 1.002f + 1e-3f;  // q(d) <= t  <=>  alpha >= 1/255, padded
+    float hx = sqrtf(t * C / det) * 1.001f + 1e-3f;
+    float hy = sqrtf(t * A / det) * 1.001f + 1e-3f;
+    if (!(hx == hx)) hx = inf;
+    if (!(hy == hy)) hy = inf;
+    return make_float2(hx, hy);
+}
+
+static constexpr unsigned long long kFlagAgg = 1ull << 62;
+static constexpr unsigned long long kFlagIncl = 2ull << 62;
+static constexpr unsigned long long kValMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kPreprocThreads) preprocess_fwd_kernel(const PreArgs a) {
+    __shared__ uint32_t s_bid;
+    __shared__ uint32_t s_warp_sum[kPreprocThreads / 32];
+    __shared__ unsigned long long s_block_excl;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) s_bid = atomicAdd(&a.g.hdr->block_ticket, 1u);
+    __syncthreads();
+    const uint32_t bid = s_bid;
+    const int idx = (int)(bid * kPreprocThreads + tid);
+
+    uint32_t touched = 0;
+    int radius_i = 0;
+    if (idx < a.P) {
+        do {
+            const float3 p_orig = make_float3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+            // near-plane cull (auxiliary.h:139-164)
+            const float4 p_hom = xform_point_4x4(p_orig, a.projmatrix);
+            const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+            const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
+            const float3 p_view = xform_point_4x3(p_orig, a.viewmatrix);
+            if (p_view.z <= 0.2f) break;
+
+            float cov3D_local[6];
+            const float* cov3D;
+            if (a.cov3D_precomp != nullptr) {
+                cov3D = a.cov3D_precomp + (size_t)idx * 6;
+            } else {
+                const float3 sc = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
+                const float4 rq = reinterpret_cast<const float4*>(a.rotations)[idx];
+                cov3d_from_scale_rot(sc, a.scale_modifier, rq, cov3D_local);
+                cov3D = cov3D_local;
+            }
+            M3 T;
+            float3 tclamped;
+            float txtz, tytz;
+            const float3 cov = cov2d_ewa(p_orig, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, cov3D, a.viewmatrix,
+                                         T, tclamped, txtz, tytz);
+            const float det = (cov.x * cov.z - cov.y * cov.y);
+            if (det == 0.0f) break;
+            const float det_inv = 1.f / det;
+            const float3 conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
+
+            const float mid = 0.5f * (cov.x + cov.z);
+            const float lambda1 = mid + sqrtf(max(0.1f, mid * mid - det));
+            const float lambda2 = mid - sqrtf(max(0.1f, mid * mid - det));
+            const float my_radius = ceilf(3.f * sqrtf(max(lambda1, lambda2)));
+            const float2 point_image = make_float2(ndc_to_pix(p_proj.x, a.W), ndc_to_pix(p_proj.y, a.H));
+            uint2 rmin, rmax;
+            tile_rect(point_image, (int)my_radius, rmin, rmax, a.grid_x, a.grid_y);
+            if ((rmax.x - rmin.x) * (rmax.y - rmin.y) == 0) break;
+
+            float* rgb_out = a.g.rgb + (size_t)idx * a.cstride;
+            if (a.colors_precomp == nullptr) {
+                uint32_t cb;
+                const float3 c = sh_to_rgb(a.D, a.shs + (size_t)idx * a.M * 3, p_orig,
+                                           make_float3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]), cb);
+                *reinterpret_cast<float4*>(rgb_out) = make_float4(c.x, c.y, c.z, 0.f);
+                a.g.clamped[idx] = (uint8_t)cb;
+            } else {
+                // repack user colours to a 16/32-byte stride so the compositors fetch them with 128-bit loads
+                const float* src = a.colors_precomp + (size_t)idx * a.channels;
+                float tmp[HGS_MAX_CHANNELS];
+#pragma unroll
+                for (int c = 0; c < HGS_MAX_CHANNELS; ++c) tmp[c] = (c < a.channels) ? src[c] : 0.f;
+                reinterpret_cast<float4*>(rgb_out)[0] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+                if (a.cstride > 4) reinterpret_cast<float4*>(rgb_out)[1] = make_float4(tmp[4], tmp[5], tmp[6], tmp[7]);
+            }
+
+            const float opacity = a.opacities[idx];
+            const float2 ext = alpha_extent(conic.x, conic.y, conic.z, opacity);
+            a.g.depths[idx] = p_view.z;
+            radius_i = (int)my_radius;
+            a.g.rec[2 * (size_t)idx] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
+            a.g.rec[2 * (size_t)idx + 1] = make_float4(conic.z, opacity, ext.x, ext.y);
+            touched = (rmax.y - rmin.y) * (rmax.x - rmin.x);
+            a.g.rects[idx] = make_uint2(rmin.x | (rmin.y << 16), rmax.x | (rmax.y << 16));
+        } while (false);
+        if (a.radii) a.radii[idx] = radius_i;
+        a.g.tiles_touched[idx] = touched;
+    }
+
+    // ---- block-wide inclusive scan of `touched` ------------------------------------------------
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    uint32_t incl = touched;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += n;
+    }
+    if (lane == 31) s_warp_sum[warp] = incl;
+    __syncthreads();
+    uint32_t warp_excl = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < kPreprocThreads / 32; ++w) {
+        const uint32_t v = s_warp_sum[w];
+        if ((uint32_t)w < warp) warp_excl += v;
+        block_total += v;
+    }
+
+    // ---- chained scan across blocks (decoupled look-back, warp 0) ------------------------------
+    if (warp == 0) {
+        unsigned long long excl = 0;
+        if (bid == 0) {
+            if (lane == 0) st_relaxed(&a.g.scan_state[0], kFlagIncl | (unsigned long long)block_total);
+        } else {
+            if (lane == 0) st_relaxed(&a.g.scan_state[bid], kFlagAgg | (unsigned long long)block_total);
+            int look = (int)bid - 1;
+            while (true) {
+                const int j = look - (int)lane;
+                unsigned long long w = (j >= 0) ? ld_relaxed(&a.g.scan_state[j]) : kFlagIncl;
+                while (__any_sync(0xffffffffu, (w >> 62) == 0)) {
+                    if ((w >> 62) == 0) w = ld_relaxed(&a.g.scan_state[j]);
+                }
+                const uint32_t incl_mask = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+                unsigned long long v = w & kValMask;
+                if (incl_mask) {
+                    const int first = __ffs(incl_mask) - 1;
+                    if ((int)lane > first) v = 0;
+                }
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                excl += v;
+                if (incl_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) st_relaxed(&a.g.scan_state[bid], kFlagIncl | (excl + block_total));
+        }
+        if (lane == 0) {
+            s_block_excl = excl;
+            if (bid == a.nblocks - 1) {
+                const unsigned long long total = excl + block_total;
+                a.g.hdr->num_rendered = (uint32_t)min(total, (unsigned long long)0xffffffffu);
+                if (total > 0x7fffffffull) a.g.hdr->overflow = 1;
+            }
+        }
+    }
+    __syncthreads();
+    if (idx < a.P) a.g.offsets[idx] = (uint32_t)(s_block_excl + warp_excl + incl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// mark_visible
+// ------------------------------------------------------------------------------------------------
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
+                                    uint8_t* __restrict__ present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float3 p = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+    const float3 v = xform_point_4x3(p, view);
+    present[idx] = (v.z <= 0.2f) ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// preprocess backward
+// ------------------------------------------------------------------------------------------------
+struct PreBwdArgs {
+    int P, D, M, channels;
+    float tan_fovx, tan_fovy, focal_x, focal_y, scale_modifier;
+    const float* means3D;
+    const int32_t* radii;
+    const float* shs;
+    const uint8_t* clamped;
+    const float* scales;
+    const float* rotations;
+    const float* cov3D_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* cam_pos;
+    const float* dL_dmean2D;  // [P,3]
+    const float* dL_dconic;   // [P,4]
+    const float* dL_dcolor;   // [P,channels]
+    float* dL_dmean3D;        // [P,3]
+    float* dL_dcov3D;         // [P,6]
+    float* dL_dsh;            // [P,M,3]
+    float* dL_dscale;         // [P,3]
+    float* dL_drot;           // [P,4]
+};
+
+__device__ __forceinline__ float3 dnormvdv3(const float3 v, const float3 dv) {  // auxiliary.h:107-117
+    const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
+    const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+    float3 r;
+    r.x = ((+sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y - v.z * v.x * dv.z) * invsum32;
+    r.y = (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y - v.z * v.y * dv.z) * invsum32;
+    r.z = (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * invsum32;
+    return r;
+}
+
+__global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreBwdArgs a) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.P) return;
+    const bool has_sh = (a.shs != nullptr) && a.M > 0;
+    const bool has_sr = (a.scales != nullptr);
+
+    if (!(a.radii[idx] > 0)) {
+        // culled: the reference leaves the torch::zeros fill in place (rasterize_points.cu:151-159)
+        a.dL_dmean3D[3 * idx] = 0.f; a.dL_dmean3D[3 * idx + 1] = 0.f; a.dL_dmean3D[3 * idx + 2] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) a.dL_dcov3D[6 * (size_t)idx + i] = 0.f;
+        if (a.dL_dsh) for (int i = 0; i < a.M * 3; ++i) a.dL_dsh[(size_t)idx * a.M * 3 + i] = 0.f;
+        a.dL_dscale[3 * idx] = 0.f; a.dL_dscale[3 * idx + 1] = 0.f; a.dL_dscale[3 * idx + 2] = 0.f;
+        reinterpret_cast<float4*>(a.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+
+    const float3 mean = make_float3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+
+    // ---- 3D covariance: recomputed (bit-identical to the forward) instead of stored ------------
+    float cov3D[6];
+    float3 sc = make_float3(0.f, 0.f, 0.f);
+    float4 rq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.cov3D_precomp != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) cov3D[i] = a.cov3D_precomp[6 * (size_t)idx + i];
+    } else {
+        sc = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
+        rq = reinterpret_cast<const float4*>(a.rotations)[idx];
+        cov3d_from_scale_rot(sc, a.scale_modifier, rq, cov3D);
+    }
+
+    // ---- conic -> cov2D -> cov3D and mean (backward_distwar.cu:145-275) -------------------------
+    const float3 dL_dconic = make_float3(a.dL_dconic[4 * (size_t)idx], a.dL_dconic[4 * (size_t)idx + 1],
+                                         a.dL_dconic[4 * (size_t)idx + 3]);
+    M3 T;
+    float3 t;
+    float txtz, tytz;
+    const float3 cov2D = cov2d_ewa(mean, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, cov3D, a.viewmatrix, T, t,
+                                   txtz, tytz);
+    const float limx = 1.3f * a.tan_fovx;
+    const float limy = 1.3f * a.tan_fovy;
+    const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+    const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+    const float h_x = a.focal_x, h_y = a.focal_y;
+    const float* view = a.viewmatrix;
+    // W[c][r] as in cov2d_ewa
+    const float W00 = view[0], W01 = view[4], W02 = view[8];
+    const float W10 = view[1], W11 = view[5], W12 = view[9];
+    const float W20 = view[2], W21 = view[6], W22 = view[10];
+    float V[3][3];
+    V[0][0] = cov3D[0]; V[0][1] = cov3D[1]; V[0][2] = cov3D[2];
+    V[1][0] = cov3D[1]; V[1][1] = cov3D[3]; V[1][2] = cov3D[4];
+    V[2][0] = cov3D[2]; V[2][1] = cov3D[4]; V[2][2] = cov3D[5];
+
+    const float ca = cov2D.x, cb = cov2D.y, cc = cov2D.z;
+    const float denom = ca * cc - cb * cb;
+    float dL_da = 0, dL_db = 0, dL_dc = 0;
+    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+    float dcov[6];
+    if (denom2inv != 0) {
+        dL_da = denom2inv * (-cc * cc * dL_dconic.x + 2 * cb * cc * dL_dconic.y + (denom - ca * cc) * dL_dconic.z);
+        dL_dc = denom2inv * (-ca * ca * dL_dconic.z + 2 * ca * cb * dL_dconic.y + (denom - ca * cc) * dL_dconic.x);
+        dL_db = denom2inv * 2 * (cb * cc * dL_dconic.x - (denom + 2 * cb * cb) * dL_dconic.y + ca * cb * dL_dconic.z);
+        dcov[0] = (T.m[0][0] * T.m[0][0] * dL_da + T.m[0][0] * T.m[1][0] * dL_db + T.m[1][0] * T.m[1][0] * dL_dc);
+        dcov[3] = (T.m[0][1] * T.m[0][1] * dL_da + T.m[0][1] * T.m[1][1] * dL_db + T.m[1][1] * T.m[1][1] * dL_dc);
+        dcov[5] = (T.m[0][2] * T.m[0][2] * dL_da + T.m[0][2] * T.m[1][2] * dL_db + T.m[1][2] * T.m[1][2] * dL_dc);
+        dcov[1] = 2 * T.m[0][0] * T.m[0][1] * dL_da + (T.m[0][0] * T.m[1][1] + T.m[0][1] * T.m[1][0]) * dL_db +
+                  2 * T.m[1][0] * T.m[1][1] * dL_dc;
+        dcov[2] = 2 * T.m[0][0] * T.m[0][2] * dL_da + (T.m[0][0] * T.m[1][2] + T.m[0][2] * T.m[1][0]) * dL_db +
+                  2 * T.m[1][0] * T.m[1][2] * dL_dc;
+        dcov[4] = 2 * T.m[0][2] * T.m[0][1] * dL_da + (T.m[0][1] * T.m[1][2] + T.m[0][2] * T.m[1][1]) * dL_db +
+                  2 * T.m[1][1] * T.m[1][2] * dL_dc;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) dcov[i] = 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) a.dL_dcov3D[6 * (size_t)idx + i] = dcov[i];
+
+    const float dL_dT00 = 2 * (T.m[0][0] * V[0][0] + T.m[0][1] * V[0][1] + T.m[0][2] * V[0][2]) * dL_da +
+                          (T.m[1][0] * V[0][0] + T.m[1][1] * V[0][1] + T.m[1][2] * V[0][2]) * dL_db;
+    const float dL_dT01 = 2 * (T.m[0][0] * V[1][0] + T.m[0][1] * V[1][1] + T.m[0][2] * V[1][2]) * dL_da +
+                          (T.m[1][0] * V[1][0] + T.m[1][1] * V[1][1] + T.m[1][2] * V[1][2]) * dL_db;
+    const float dL_dT02 = 2 * (T.m[0][0] * V[2][0] + T.m[0][1] * V[2][1] + T.m[0][2] * V[2][2]) * dL_da +
+                          (T.m[1][0] * V[2][0] + T.m[1][1] * V[2][1] + T.m[1][2] * V[2][2]) * dL_db;
+    const float dL_dT10 = 2 * (T.m[1][0] * V[0][0] + T.m[1][1] * V[0][1] + T.m[1][2] * V[0][2]) * dL_dc +
+                          (T.m[0][0] * V[0][0] + T.m[0][1] * V[0][1] + T.m[0][2] * V[0][2]) * dL_db;
+    const float dL_dT11 = 2 * (T.m[1][0] * V[1][0] + T.m[1][1] * V[1][1] + T.m[1][2] * V[1][2]) * dL_dc +
+                          (T.m[0][0] * V[1][0] + T.m[0][1] * V[1][1] + T.m[0][2] * V[1][2]) * dL_db;
+    const float dL_dT12 = 2 * (T.m[1][0] * V[2][0] + T.m[1][1] * V[2][1] + T.m[1][2] * V[2][2]) * dL_dc +
+                          (T.m[0][0] * V[2][0] + T.m[0][1] * V[2][1] + T.m[0][2] * V[2][2]) * dL_db;
+
+    const float dL_dJ00 = W00 * dL_dT00 + W01 * dL_dT01 + W02 * dL_dT02;
+    const float dL_dJ02 = W20 * dL_dT00 + W21 * dL_dT01 + W22 * dL_dT02;
+    const float dL_dJ11 = W10 * dL_dT10 + W11 * dL_dT11 + W12 * dL_dT12;
+    const float dL_dJ12 = W20 * dL_dT10 + W21 * dL_dT11 + W22 * dL_dT12;
+
+    const float tz = 1.f / t.z;
+    const float tz2 = tz * tz;
+    const float tz3 = tz2 * tz;
+    const float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
+    const float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
+    const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 +
+                         (2 * h_y * t.y) * tz3 * dL_dJ12;
+    // transformVec4x3Transpose (auxiliary.h:89-97)
+    float3 dmean;
+    dmean.x = view[0] * dL_dtx + view[1] * dL_dty + view[2] * dL_dtz;
+    dmean.y = view[4] * dL_dtx + view[5] * dL_dty + view[6] * dL_dtz;
+    dmean.z = view[8] * dL_dtx + view[9] * dL_dty + view[10] * dL_dtz;
+
+    // ---- mean2D -> mean3D through the projection (backward_distwar.cu:371-388) ------------------
+    const float* proj = a.projmatrix;
+    const float4 m_hom = xform_point_4x4(mean, proj);
+    const float m_w = 1.0f / (m_hom.w + 0.0000001f);
+    const float g2x = a.dL_dmean2D[3 * (size_t)idx], g2y = a.dL_dmean2D[3 * (size_t)idx + 1];
+    const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
+    const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
+    float3 dproj;
+    dproj.x = (proj[0] * m_w - proj[3] * mul1) * g2x + (proj[1] * m_w - proj[3] * mul2) * g2y;
+    dproj.y = (proj[4] * m_w - proj[7] * mul1) * g2x + (proj[5] * m_w - proj[7] * mul2) * g2y;
+    dproj.z = (proj[8] * m_w - proj[11] * mul1) * g2x + (proj[9] * m_w - proj[11] * mul2) * g2y;
+    dmean.x += dproj.x;
+    dmean.y += dproj.y;
+    dmean.z += dproj.z;
+
+    // ---- colour -> SH and view direction (backward_distwar.cu:21-140) ---------------------------
+    if (has_sh) {
+        const float* sh = a.shs + (size_t)idx * a.M * 3;
+        float* dsh = a.dL_dsh + (size_t)idx * a.M * 3;
+        const float3 campos = make_float3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]);
+        const float3 dir_orig = make_float3(mean.x - campos.x, mean.y - campos.y, mean.z - campos.z);
+        const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+        const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
+        const uint32_t cbits = a.clamped[idx];
+        float dRGB[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            dRGB[c] = a.dL_dcolor[(size_t)idx * a.channels + c];
+            dRGB[c] *= ((cbits >> c) & 1u) ? 0.f : 1.f;
+        }
+        float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
+        int written = 1;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dsh[0 * 3 + c] = kSH_C0 * dRGB[c];
+        if (a.D > 0) {
+            written = 4;
+            const float d1 = -kSH_C1 * y, d2 = kSH_C1 * z, d3 = -kSH_C1 * x;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                dsh[1 * 3 + c] = d1 * dRGB[c];
+                dsh[2 * 3 + c] = d2 * dRGB[c];
+                dsh[3 * 3 + c] = d3 * dRGB[c];
+                dRGBdx[c] = -kSH_C1 * sh[3 * 3 + c];
+                dRGBdy[c] = -kSH_C1 * sh[1 * 3 + c];
+                dRGBdz[c] = kSH_C1 * sh[2 * 3 + c];
+            }
+            if (a.D > 1) {
+                written = 9;
+                const float xx = x * x, yy = y * y, zz = z * z;
+                const float xy = x * y, yz = y * z, xz = x * z;
+                const float d4 = kSH_C2[0] * xy, d5 = kSH_C2[1] * yz, d6 = kSH_C2[2] * (2.f * zz - xx - yy);
+                const float d7 = kSH_C2[3] * xz, d8 = kSH_C2[4] * (xx - yy);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    dsh[4 * 3 + c] = d4 * dRGB[c];
+                    dsh[5 * 3 + c] = d5 * dRGB[c];
+                    dsh[6 * 3 + c] = d6 * dRGB[c];
+                    dsh[7 * 3 + c] = d7 * dRGB[c];
+                    dsh[8 * 3 + c] = d8 * dRGB[c];
+                    dRGBdx[c] += kSH_C2[0] * y * sh[4 * 3 + c] + kSH_C2[2] * 2.f * -x * sh[6 * 3 + c] +
+                                 kSH_C2[3] * z * sh[7 * 3 + c] + kSH_C2[4] * 2.f * x * sh[8 * 3 + c];
+                    dRGBdy[c] += kSH_C2[0] * x * sh[4 * 3 + c] + kSH_C2[1] * z * sh[5 * 3 + c] +
+                                 kSH_C2[2] * 2.f * -y * sh[6 * 3 + c] + kSH_C2[4] * 2.f * -y * sh[8 * 3 + c];
+                    dRGBdz[c] += kSH_C2[1] * y * sh[5 * 3 + c] + kSH_C2[2] * 2.f * 2.f * z * sh[6 * 3 + c] +
+                                 kSH_C2[3] * x * sh[7 * 3 + c];
+                }
+                if (a.D > 2) {
+                    written = 16;
+                    const float d9 = kSH_C3[0] * y * (3.f * xx - yy);
+                    const float d10 = kSH_C3[1] * xy * z;
+                    const float d11 = kSH_C3[2] * y * (4.f * zz - xx - yy);
+                    const float d12 = kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                    const float d13 = kSH_C3[4] * x * (4.f * zz - xx - yy);
+                    const float d14 = kSH_C3[5] * z * (xx - yy);
+                    const float d15 = kSH_C3[6] * x * (xx - 3.f * yy);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        dsh[9 * 3 + c] = d9 * dRGB[c];
+                        dsh[10 * 3 + c] = d10 * dRGB[c];
+                        dsh[11 * 3 + c] = d11 * dRGB[c];
+                        dsh[12 * 3 + c] = d12 * dRGB[c];
+                        dsh[13 * 3 + c] = d13 * dRGB[c];
+                        dsh[14 * 3 + c] = d14 * dRGB[c];
+                        dsh[15 * 3 + c] = d15 * dRGB[c];
+                        dRGBdx[c] += (kSH_C3[0] * sh[9 * 3 + c] * 3.f * 2.f * xy + kSH_C3[1] * sh[10 * 3 + c] * yz +
+                                      kSH_C3[2] * sh[11 * 3 + c] * -2.f * xy + kSH_C3[3] * sh[12 * 3 + c] * -3.f * 2.f * xz +
+                                      kSH_C3[4] * sh[13 * 3 + c] * (-3.f * xx + 4.f * zz - yy) +
+                                      kSH_C3[5] * sh[14 * 3 + c] * 2.f * xz + kSH_C3[6] * sh[15 * 3 + c] * 3.f * (xx - yy));
+                        dRGBdy[c] += (kSH_C3[0] * sh[9 * 3 + c] * 3.f * (xx - yy) + kSH_C3[1] * sh[10 * 3 + c] * xz +
+                                      kSH_C3[2] * sh[11 * 3 + c] * (-3.f * yy + 4.f * zz - xx) +
+                                      kSH_C3[3] * sh[12 * 3 + c] * -3.f * 2.f * yz + kSH_C3[4] * sh[13 * 3 + c] * -2.f * xy +
+                                      kSH_C3[5] * sh[14 * 3 + c] * -2.f * yz + kSH_C3[6] * sh[15 * 3 + c] * -3.f * 2.f * xy);
+                        dRGBdz[c] += (kSH_C3[1] * sh[10 * 3 + c] * xy + kSH_C3[2] * sh[11 * 3 + c] * 4.f * 2.f * yz +
+                                      kSH_C3[3] * sh[12 * 3 + c] * 3.f * (2.f * zz - xx - yy) +
+                                      kSH_C3[4] * sh[13 * 3 + c] * 4.f * 2.f * xz + kSH_C3[5] * sh[14 * 3 + c] * (xx - yy));
+                    }
+                }
+            }
+        }
+        // coefficients above the active degree: defined zeros (reference: memset)
+        for (int k = written; k < a.M; ++k) {
+            dsh[k * 3 + 0] = 0.f; dsh[k * 3 + 1] = 0.f; dsh[k * 3 + 2] = 0.f;
+        }
+        const float3 dL_ddir = make_float3(dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2],
+                                           dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2],
+                                           dRGBdz[0] * dRGB[0] + dRGBdz[1] * dRGB[1] + dRGBdz[2] * dRGB[2]);
+        const float3 dsm = dnormvdv3(dir_orig, dL_ddir);
+        dmean.x += dsm.x;
+        dmean.y += dsm.y;
+        dmean.z += dsm.z;
+    } else if (a.dL_dsh) {
+        for (int i = 0; i < a.M * 3; ++i) a.dL_dsh[(size_t)idx * a.M * 3 + i] = 0.f;
+    }
+    a.dL_dmean3D[3 * idx] = dmean.x;
+    a.dL_dmean3D[3 * idx + 1] = dmean.y;
+    a.dL_dmean3D[3 * idx + 2] = dmean.z;
+
+    // ---- cov3D -> scale, rotation (backward_distwar.cu:279-342) ---------------------------------
+    if (has_sr) {
+        const float r = rq.x, x = rq.y, y = rq.z, z = rq.w;
+        M3 R;
+        R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z);       R.m[0][2] = 2.f * (x * z + r * y);
+        R.m[1][0] = 2.f * (x * y + r * z);       R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
+        R.m[2][0] = 2.f * (x * z - r * y);       R.m[2][1] = 2.f * (y * z + r * x);       R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+        const float3 s = make_float3(a.scale_modifier * sc.x, a.scale_modifier * sc.y, a.scale_modifier * sc.z);
+        M3 S;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) S.m[c][q] = (c == q) ? 1.0f : 0.0f;
+        S.m[0][0] = s.x; S.m[1][1] = s.y; S.m[2][2] = s.z;
+        const M3 Mx = m3_mul(S, R);
+        M3 dSig;
+        dSig.m[0][0] = dcov[0];        dSig.m[0][1] = 0.5f * dcov[1]; dSig.m[0][2] = 0.5f * dcov[2];
+        dSig.m[1][0] = 0.5f * dcov[1]; dSig.m[1][1] = dcov[3];        dSig.m[1][2] = 0.5f * dcov[4];
+        dSig.m[2][0] = 0.5f * dcov[2]; dSig.m[2][1] = 0.5f * dcov[4]; dSig.m[2][2] = dcov[5];
+        // dL_dM = 2 * M * dL_dSigma  (scalar * mat first, glm evaluates left to right)
+        M3 M2;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) M2.m[c][q] = 2.0f * Mx.m[c][q];
+        const M3 dL_dM = m3_mul(M2, dSig);
+        const M3 Rt = m3_transpose(R);
+        M3 dMt = m3_transpose(dL_dM);
+        float3 dscale;
+        dscale.x = Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2];
+        dscale.y = Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2];
+        dscale.z = Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2];
+        a.dL_dscale[3 * idx] = dscale.x;
+        a.dL_dscale[3 * idx + 1] = dscale.y;
+        a.dL_dscale[3 * idx + 2] = dscale.z;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            dMt.m[0][q] *= s.x;
+            dMt.m[1][q] *= s.y;
+            dMt.m[2][q] *= s.z;
+        }
+        float4 dq;
+        dq.x = 2 * z * (dMt.m[0][1] - dMt.m[1][0]) + 2 * y * (dMt.m[2][0] - dMt.m[0][2]) + 2 * x * (dMt.m[1][2] - dMt.m[2][1]);
+        dq.y = 2 * y * (dMt.m[1][0] + dMt.m[0][1]) + 2 * z * (dMt.m[2][0] + dMt.m[0][2]) + 2 * r * (dMt.m[1][2] - dMt.m[2][1]) -
+               4 * x * (dMt.m[2][2] + dMt.m[1][1]);
+        dq.z = 2 * x * (dMt.m[1][0] + dMt.m[0][1]) + 2 * r * (dMt.m[2][0] - dMt.m[0][2]) + 2 * z * (dMt.m[1][2] + dMt.m[2][1]) -
+               4 * y * (dMt.m[2][2] + dMt.m[0][0]);
+        dq.w = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) -
+               4 * z * (dMt.m[1][1] + dMt.m[0][0]);
+        reinterpret_cast<float4*>(a.dL_drot)[idx] = dq;
+    } else {
+        a.dL_dscale[3 * idx] = 0.f; a.dL_dscale[3 * idx + 1] = 0.f; a.dL_dscale[3 * idx + 2] = 0.f;
+        reinterpret_cast<float4*>(a.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// state viewers: expand our packed records into the reference's array layouts (tests only)
+// ------------------------------------------------------------------------------------------------
+__global__ void view_rec_kernel(int P, const float4* __restrict__ rec, const uint32_t* __restrict__ touched,
+                                float2* means2D, float4* conic_opacity) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const bool vis = touched[idx] > 0;
+    const float4 lo = vis ? rec[2 * (size_t)idx] : make_float4(0, 0, 0, 0);
+    const float4 hi = vis ? rec[2 * (size_t)idx + 1] : make_float4(0, 0, 0, 0);
+    if (means2D) means2D[idx] = make_float2(lo.x, lo.y);
+    if (conic_opacity) conic_opacity[idx] = make_float4(lo.z, lo.w, hi.x, hi.y);
+}
+
+__global__ void view_rgb_kernel(int P, int channels, int cstride, const float* __restrict__ rgb,
+                                const uint32_t* __restrict__ touched, float* out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const bool vis = touched[idx] > 0;
+    for (int c = 0; c < channels; ++c) out[(size_t)idx * channels + c] = vis ? rgb[(size_t)idx * cstride + c] : 0.f;
+}
+
+__global__ void view_clamped_kernel(int P, const uint8_t* __restrict__ clamped, const uint32_t* __restrict__ touched,
+                                    uint8_t* out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const uint32_t b = touched[idx] > 0 ? clamped[idx] : 0;
+    out[3 * (size_t)idx + 0] = b & 1;
+    out[3 * (size_t)idx + 1] = (b >> 1) & 1;
+    out[3 * (size_t)idx + 2] = (b >> 2) & 1;
+}
+
+__global__ void view_depths_kernel(int P, const float* __restrict__ depths, const uint32_t* __restrict__ touched,
+                                   float* out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    out[idx] = touched[idx] > 0 ? depths[idx] : 0.f;
+}
+
+__global__ void view_cov3d_kernel(int P, const float* __restrict__ scales, const float* __restrict__ rotations,
+                                  float mod, float* out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float3 sc = make_float3(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]);
+    const float4 rq = reinterpret_cast<const float4*>(rotations)[idx];
+    float c[6];
+    cov3d_from_scale_rot(sc, mod, rq, c);
+    for (int i = 0; i < 6; ++i) out[6 * (size_t)idx + i] = c[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+int launch_preprocess_fwd(const hgs_raster_params* prm, const hgs_raster_inputs* in, const GeomLayout& g,
+                          int32_t* radii, cudaStream_t s) {
+    PreArgs a;
+    a.P = prm->P; a.D = prm->D; a.M = prm->M; a.W = prm->width; a.H = prm->height;
+    a.channels = prm->channels; a.cstride = g.cstride;
+    a.tan_fovx = prm->tan_fovx; a.tan_fovy = prm->tan_fovy;
+    a.focal_y = prm->height / (2.0f * prm->tan_fovy);   // rasterizer_impl.cu:222-223
+    a.focal_x = prm->width / (2.0f * prm->tan_fovx);
+    a.scale_modifier = prm->scale_modifier;
+    a.grid_x = (prm->width + HGS_TILE - 1) / HGS_TILE;
+    a.grid_y = (prm->height + HGS_TILE - 1) / HGS_TILE;
+    a.means3D = in->means3D; a.scales = in->scales; a.rotations = in->rotations; a.opacities = in->opacities;
+    a.shs = in->shs; a.cov3D_precomp = in->cov3D_precomp; a.colors_precomp = in->colors_precomp;
+    a.viewmatrix = in->viewmatrix; a.projmatrix = in->projmatrix; a.cam_pos = in->cam_pos;
+    a.radii = radii; a.g = g;
+    a.nblocks = (prm->P + kPreprocThreads - 1) / kPreprocThreads;
+    if (int e = check_cuda(cudaMemsetAsync(g.hdr, 0, g.clear_bytes, s), "memset geom header")) return e;
+    preprocess_fwd_kernel<<<a.nblocks, kPreprocThreads, 0, s>>>(a);
+    return check_cuda(cudaGetLastError(), "preprocess_fwd launch");
+}
+
+int launch_preprocess_bwd(const hgs_raster_params* prm, const hgs_raster_inputs* in, const GeomLayout& g,
+                          const int32_t* radii, const hgs_raster_grads* gr, cudaStream_t s) {
+    PreBwdArgs a;
+    a.P = prm->P; a.D = prm->D; a.M = prm->M; a.channels = prm->channels;
+    a.tan_fovx = prm->tan_fovx; a.tan_fovy = prm->tan_fovy;
+    a.focal_y = prm->height / (2.0f * prm->tan_fovy);
+    a.focal_x = prm->width / (2.0f * prm->tan_fovx);
+    a.scale_modifier = prm->scale_modifier;
+    a.means3D = in->means3D; a.radii = radii; a.shs = in->shs; a.clamped = g.clamped;
+    a.scales = in->scales; a.rotations = in->rotations; a.cov3D_precomp = in->cov3D_precomp;
+    a.viewmatrix = in->viewmatrix; a.projmatrix = in->projmatrix; a.cam_pos = in->cam_pos;
+    a.dL_dmean2D = gr->dL_dmean2D; a.dL_dconic = gr->dL_dconic; a.dL_dcolor = gr->dL_dcolor;
+    a.dL_dmean3D = gr->dL_dmean3D; a.dL_dcov3D = gr->dL_dcov3D; a.dL_dsh = gr->dL_dsh;
+    a.dL_dscale = gr->dL_dscale; a.dL_drot = gr->dL_drot;
+    preprocess_bwd_kernel<<<(prm->P + 255) / 256, 256, 0, s>>>(a);
+    return check_cuda(cudaGetLastError(), "preprocess_bwd launch");
+}
+
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s) {
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view, present);
+    return check_cuda(cudaGetLastError(), "mark_visible launch");
+}
+
+int launch_view_geom(int what, const hgs_raster_params* prm, const hgs_raster_inputs* in, const GeomLayout& g,
+                     void* dst, cudaStream_t s) {
+    const int P = prm->P;
+    const int nb = (P + 255) / 256;
+    switch (what) {
+        case HGS_VIEW_DEPTHS: view_depths_kernel<<<nb, 256, 0, s>>>(P, g.depths, g.tiles_touched, (float*)dst); break;
+        case HGS_VIEW_MEANS2D: view_rec_kernel<<<nb, 256, 0, s>>>(P, g.rec, g.tiles_touched, (float2*)dst, nullptr); break;
+        case HGS_VIEW_CONIC_OPACITY: view_rec_kernel<<<nb, 256, 0, s>>>(P, g.rec, g.tiles_touched, nullptr, (float4*)dst); break;
+        case HGS_VIEW_RGB: view_rgb_kernel<<<nb, 256, 0, s>>>(P, prm->channels, g.cstride, g.rgb, g.tiles_touched, (float*)dst); break;
+        case HGS_VIEW_CLAMPED: view_clamped_kernel<<<nb, 256, 0, s>>>(P, g.clamped, g.tiles_touched, (uint8_t*)dst); break;
+        case HGS_VIEW_COV3D:
+            if (!in->scales || !in->rotations) { set_error("cov3D view needs scales/rotations"); return HGS_ERR_INVALID; }
+            view_cov3d_kernel<<<nb, 256, 0, s>>>(P, in->scales, in->rotations, prm->scale_modifier, (float*)dst);
+            break;
+        default: set_error("bad geometry view %d", what); return HGS_ERR_INVALID;
+    }
+    return check_cuda(cudaGetLastError(), "view kernel launch");
+}
+
+}  // namespace hgs

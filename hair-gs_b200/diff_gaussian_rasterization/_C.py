@@ -1,0 +1,144 @@
+"""`diff_gaussian_rasterization._C` — same three entry points, argument order and return tuples as the
+reference's pybind module (submodules/diff-gaussian-rasterization/ext.cpp:15-19, signatures
+rasterize_points.h:18-66), implemented over the C ABI of libhairgs_rast.so (sm_100a kernels).
+
+Differences a caller can observe (all documented in DESIGN.md):
+  * geomBuffer / binningBuffer / imgBuffer are opaque uint8 tensors with OUR layout;
+  * colors_precomp may carry 1..8 channels (the reference is fixed at 3); out_color follows;
+  * kernels run on torch's current stream, not the legacy default stream.
+"""
+import ctypes
+
+import torch
+
+from hairgs_b200 import _lib as L
+
+NUM_CHANNELS = 3
+
+
+def _prep(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+          projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered, debug):
+    if means3D.ndimension() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:57-59
+    if not means3D.is_cuda:
+        raise L.HgsError("means3D must be a CUDA tensor: this rasterizer has no CPU path")
+    dev = means3D.device
+    P = means3D.size(0)
+    keep = {}
+    for name, t in (("background", background), ("means3D", means3D), ("colors_precomp", colors),
+                    ("opacities", opacity), ("scales", scales), ("rotations", rotations),
+                    ("cov3D_precomp", cov3D_precomp), ("viewmatrix", viewmatrix), ("projmatrix", projmatrix),
+                    ("shs", sh), ("cam_pos", campos)):
+        keep[name] = L.f32c(t, name, dev)
+    M = 0
+    if sh is not None and sh.numel() != 0:
+        M = sh.size(1)
+    channels = NUM_CHANNELS
+    if keep["colors_precomp"] is not None:
+        channels = keep["colors_precomp"].size(-1) if keep["colors_precomp"].dim() > 1 else 1
+    prm = L.RasterParams(P=P, D=int(degree), M=int(M), width=int(image_width), height=int(image_height),
+                         channels=int(channels), tan_fovx=float(tan_fovx), tan_fovy=float(tan_fovy),
+                         scale_modifier=float(scale_modifier), prefiltered=int(bool(prefiltered)),
+                         debug=int(bool(debug)))
+    inp = L.RasterInputs(**{k: L.ptr(v) for k, v in keep.items()})
+    return dev, prm, inp, keep
+
+
+def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                        viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
+                        prefiltered, debug):
+    """RasterizeGaussiansCUDA (rasterize_points.cu:35-115): returns
+    (num_rendered, out_color[C,H,W], radii[P] int32, geomBuffer, binningBuffer, imgBuffer)."""
+    lib = L.load()
+    dev, prm, inp, keep = _prep(background, means3D, colors, opacity, scales, rotations, scale_modifier,
+                                cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
+                                image_width, sh, degree, campos, prefiltered, debug)
+    P, H, W, C = prm.P, prm.height, prm.width, prm.channels
+    with torch.cuda.device(dev):
+        stream = L.stream_ptr(dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        out_color = torch.empty((C, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        geom = torch.empty((lib.hgs_geom_bytes(P, C),), **u8)
+        img = torch.empty((lib.hgs_image_bytes(W, H),), **u8)
+        if P == 0:
+            # rasterize_points.cu:81 short-circuit: zero outputs, empty scratch
+            out_color.zero_()
+            return 0, out_color, radii, geom, torch.empty((0,), **u8), img
+        L.check(lib.hgs_forward_stage_a(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(), radii.data_ptr(),
+                                        stream), "forward stage A")
+        # the pass's one blocking read-back (rasterizer_impl.cu:281)
+        hdr = geom[:12].view(torch.int32).cpu()
+        if int(hdr[2]) != 0 or int(hdr[0]) < 0:
+            raise L.HgsError("instance count overflows int32")
+        N = int(hdr[0])
+        binning = torch.empty((lib.hgs_binning_bytes(N),), **u8)
+        L.check(lib.hgs_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
+                                        binning.data_ptr() if N > 0 else None, img.data_ptr(), N, radii.data_ptr(),
+                                        out_color.data_ptr(), stream), "forward stage B")
+    del keep
+    return N, out_color, radii, geom, binning, img
+
+
+def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
+                                 cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh,
+                                 degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug):
+    """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:117-196): returns (dL_dmeans2D[P,3],
+    dL_dcolors[P,C], dL_dopacity[P,1], dL_dmeans3D[P,3], dL_dcov3D[P,6], dL_dsh[P,M,3], dL_dscales[P,3],
+    dL_drotations[P,4])."""
+    lib = L.load()
+    H, W = dL_dout_color.size(1), dL_dout_color.size(2)
+    dev, prm, inp, keep = _prep(background, means3D, colors, None, scales, rotations, scale_modifier, cov3D_precomp,
+                                viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, sh, degree, campos, False, debug)
+    P, M, C = prm.P, prm.M, dL_dout_color.size(0)
+    prm.channels = C
+    f32 = dict(dtype=torch.float32, device=dev)
+    if P == 0:
+        return (torch.zeros((0, 3), **f32), torch.zeros((0, C), **f32), torch.zeros((0, 1), **f32),
+                torch.zeros((0, 3), **f32), torch.zeros((0, 6), **f32), torch.zeros((0, M, 3), **f32),
+                torch.zeros((0, 3), **f32), torch.zeros((0, 4), **f32))
+    with torch.cuda.device(dev):
+        dpix = L.f32c(dL_dout_color, "dL_dout_color", dev)
+        # one allocation for the compositor's accumulation targets (cleared with a single memset inside
+        # the library), one for the arrays preprocess_bwd writes exactly once
+        acc = torch.empty((P * (3 + 4 + 1 + C),), **f32)
+        dL_dmeans2D = acc[:3 * P].view(P, 3)
+        dL_dconic = acc[3 * P:7 * P].view(P, 4)
+        dL_dopacity = acc[7 * P:8 * P].view(P, 1)
+        dL_dcolors = acc[8 * P:].view(P, C)
+        rest = torch.empty((P * (3 + 6 + 3 * M + 3 + 4),), **f32)
+        o = 0
+        dL_drotations = rest[o:o + 4 * P].view(P, 4); o += 4 * P   # first: keeps float4 stores 16-B aligned
+        dL_dmeans3D = rest[o:o + 3 * P].view(P, 3); o += 3 * P
+        dL_dcov3D = rest[o:o + 6 * P].view(P, 6); o += 6 * P
+        dL_dscales = rest[o:o + 3 * P].view(P, 3); o += 3 * P
+        dL_dsh = rest[o:o + 3 * M * P].view(P, M, 3)
+        grads = L.RasterGrads(dL_dmean2D=dL_dmeans2D.data_ptr(), dL_dconic=dL_dconic.data_ptr(),
+                              dL_dopacity=dL_dopacity.data_ptr(), dL_dcolor=dL_dcolors.data_ptr(),
+                              dL_dmean3D=dL_dmeans3D.data_ptr(), dL_dcov3D=dL_dcov3D.data_ptr(),
+                              dL_dsh=L.ptr(dL_dsh), dL_dscale=dL_dscales.data_ptr(),
+                              dL_drot=dL_drotations.data_ptr())
+        L.check(lib.hgs_rasterize_backward(ctypes.byref(prm), ctypes.byref(inp), int(R), L.ptr(radii),
+                                           geomBuffer.data_ptr(), L.ptr(binningBuffer), imageBuffer.data_ptr(),
+                                           dpix.data_ptr(), ctypes.byref(grads), L.stream_ptr(dev)),
+                "backward")
+    del keep
+    return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    """markVisible (rasterize_points.cu:198-217): bool[P], True where view-space z > 0.2."""
+    lib = L.load()
+    if not means3D.is_cuda:
+        raise L.HgsError("means3D must be a CUDA tensor: this rasterizer has no CPU path")
+    dev = means3D.device
+    P = means3D.size(0)
+    present = torch.zeros((P,), dtype=torch.bool, device=dev)
+    if P != 0:
+        m = L.f32c(means3D, "means3D", dev)
+        v = L.f32c(viewmatrix, "viewmatrix", dev)
+        p = L.f32c(projmatrix, "projmatrix", dev)
+        with torch.cuda.device(dev):
+            L.check(lib.hgs_mark_visible(P, m.data_ptr(), v.data_ptr(), p.data_ptr(), present.data_ptr(),
+                                         L.stream_ptr(dev)), "mark_visible")
+    return present

@@ -1,0 +1,175 @@
+/*
+ * hairgs_rast.h — C ABI of the B200-native differentiable Gaussian rasterizer that drops in
+ * behind Hair-GS's render path (libhairgs_rast.so, sm_100a only, no CPU fallback).
+ *
+ * Every entry point takes plain pointers / sizes / a cudaStream_t (as void*), returns an int
+ * status (>= 0 ok, < 0 error; text via hgs_last_error()).  No torch types cross this boundary.
+ * All pointers are DEVICE pointers unless the name ends in _host.  "Absent" optional inputs are
+ * passed as NULL exactly like the reference (rasterize_points.cu:84-87, forward.cu:205,241).
+ *
+ * Reference interface each entry point replaces (paths relative to
+ * submodules/diff-gaussian-rasterization/ and submodules/simple-knn/ of yimin-pan/hair-gs):
+ *
+ *   hgs_rasterize_forward   <- CudaRasterizer::Rasterizer::forward   cuda_rasterizer/rasterizer.h:33-58
+ *                              (impl rasterizer_impl.cu:198-336), bound by RasterizeGaussiansCUDA
+ *                              rasterize_points.cu:35-115
+ *   hgs_rasterize_backward  <- CudaRasterizer::Rasterizer::backward  cuda_rasterizer/rasterizer.h:60-85
+ *                              (impl rasterizer_impl.cu:340-434), bound by
+ *                              RasterizeGaussiansBackwardCUDA rasterize_points.cu:117-196
+ *   hgs_mark_visible        <- CudaRasterizer::Rasterizer::markVisible cuda_rasterizer/rasterizer.h:24-31
+ *                              (impl rasterizer_impl.cu:141-153), bound by markVisible
+ *                              rasterize_points.cu:198-217
+ *   hgs_dist2_knn3          <- SimpleKNN::knn simple_knn.h:17 (impl simple_knn.cu:186-222), bound by
+ *                              distCUDA2 spatial.cu:15-26
+ *   hgs_*_bytes / hgs_forward_stage_* / hgs_state_view
+ *                           <- GeometryState/ImageState/BinningState::fromChunk + required<T>()
+ *                              rasterizer_impl.cu:155-194, rasterizer_impl.h:22-71 (internal ABI of
+ *                              the reference; ours is laid out differently)
+ */
+#ifndef HAIRGS_RAST_H_
+#define HAIRGS_RAST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGS_ABI_VERSION 1
+#define HGS_TILE 16            /* BLOCK_X == BLOCK_Y == 16, cuda_rasterizer/config.h:16-17 */
+#define HGS_MAX_CHANNELS 8     /* colour channels per pass: 3 (reference) .. 8 (fused RGB+mask+orientation) */
+
+/* status codes */
+#define HGS_OK 0
+#define HGS_ERR_INVALID (-1)     /* bad argument (mirrors AT_ERROR / std::runtime_error of the reference) */
+#define HGS_ERR_CUDA (-2)        /* a CUDA call or (debug mode) a kernel failed */
+#define HGS_ERR_ALLOC (-3)       /* an allocator callback returned NULL / too small */
+#define HGS_ERR_OVERFLOW (-4)    /* instance count exceeds 2^31-1 (reference: int num_rendered) */
+
+/* Allocator callback: the C form of the reference's std::function<char*(size_t)> resize functors
+ * (rasterize_points.cu:27-33).  Must return a device pointer to >= bytes bytes, 256-B aligned. */
+typedef void* (*hgs_alloc_fn)(void* user, size_t bytes);
+
+/* Scalar parameters of one rasterization call (rasterizer.h:33-58 scalar arguments). */
+typedef struct hgs_raster_params {
+    int32_t P;              /* number of Gaussians */
+    int32_t D;              /* active SH degree 0..3 */
+    int32_t M;              /* SH coefficients per channel in the shs tensor, 0 if absent */
+    int32_t width, height;  /* image size in pixels */
+    int32_t channels;       /* colour channels; 3 unless colors_precomp carries more (<= HGS_MAX_CHANNELS) */
+    float tan_fovx, tan_fovy;
+    float scale_modifier;
+    int32_t prefiltered;    /* reference traps when a prefiltered point is culled; we report HGS_ERR_INVALID lazily via debug */
+    int32_t debug;          /* synchronise + check after every stage (auxiliary.h:166-173) */
+} hgs_raster_params;
+
+/* Device pointers of the per-Gaussian inputs (rasterizer.h:33-58 pointer arguments). */
+typedef struct hgs_raster_inputs {
+    const float* background;     /* [channels] */
+    const float* means3D;        /* [P,3] */
+    const float* shs;            /* [P,M,3] or NULL */
+    const float* colors_precomp; /* [P,channels] or NULL */
+    const float* opacities;      /* [P] */
+    const float* scales;         /* [P,3] or NULL */
+    const float* rotations;      /* [P,4] (w,x,y,z) or NULL */
+    const float* cov3D_precomp;  /* [P,6] or NULL */
+    const float* viewmatrix;     /* [16] column-major W2C */
+    const float* projmatrix;     /* [16] column-major P*W2C */
+    const float* cam_pos;        /* [3] */
+} hgs_raster_inputs;
+
+/* Gradient outputs (rasterizer.h:60-85).  Every element of every non-NULL array is written
+ * (zeros for culled Gaussians): callers need NOT pre-zero anything. */
+typedef struct hgs_raster_grads {
+    float* dL_dmean2D;   /* [P,3]  (z always 0) */
+    float* dL_dconic;    /* [P,4]  scratch: (xx, xy, unused, yy) as the reference's [P,2,2] */
+    float* dL_dopacity;  /* [P] */
+    float* dL_dcolor;    /* [P,channels] */
+    float* dL_dmean3D;   /* [P,3] */
+    float* dL_dcov3D;    /* [P,6] */
+    float* dL_dsh;       /* [P,M,3] or NULL when M == 0 */
+    float* dL_dscale;    /* [P,3] */
+    float* dL_drot;      /* [P,4] */
+} hgs_raster_grads;
+
+int hgs_abi_version(void);
+const char* hgs_last_error(void);
+
+/* Workspace sizes in bytes (required<T>() of the reference).  binning: N = num_rendered. */
+size_t hgs_geom_bytes(int32_t P, int32_t channels);
+size_t hgs_image_bytes(int32_t width, int32_t height);
+size_t hgs_binning_bytes(int64_t num_rendered);
+
+/* Whole forward pass, reference call shape: allocates through the three callbacks, blocks once on
+ * the instance count exactly like rasterizer_impl.cu:281, returns num_rendered (>= 0) or an error.
+ * out_color [channels,H,W] and radii [P] (may be NULL) are fully written. */
+int hgs_rasterize_forward(hgs_alloc_fn geom_alloc, void* geom_user,
+                          hgs_alloc_fn binning_alloc, void* binning_user,
+                          hgs_alloc_fn image_alloc, void* image_user,
+                          const hgs_raster_params* prm, const hgs_raster_inputs* in,
+                          float* out_color, int32_t* radii, void* stream);
+
+/* The same pass in three stream-ordered stages, for callers that own their workspaces and want to
+ * overlap the instance-count read-back (no allocation, no implicit synchronisation):
+ *   A  preprocess + tile-count scan; leaves num_rendered in the geometry workspace
+ *   (read it with hgs_forward_read_num_rendered: async copy into pinned host memory)
+ *   B  key emission + (tile|depth) radix sort + tile ranges + compositing. */
+int hgs_forward_stage_a(const hgs_raster_params* prm, const hgs_raster_inputs* in,
+                        void* geom_ws, int32_t* radii, void* stream);
+int hgs_forward_read_num_rendered(const void* geom_ws, int32_t P, uint32_t* n_pinned_host, void* stream);
+int hgs_forward_stage_b(const hgs_raster_params* prm, const hgs_raster_inputs* in,
+                        void* geom_ws, void* binning_ws, void* image_ws, int64_t num_rendered,
+                        const int32_t* radii, float* out_color, void* stream);
+
+/* Backward pass.  R = num_rendered returned by the forward; workspaces are the forward's. */
+int hgs_rasterize_backward(const hgs_raster_params* prm, const hgs_raster_inputs* in,
+                           int64_t R, const int32_t* radii,
+                           const void* geom_ws, const void* binning_ws, const void* image_ws,
+                           const float* dL_dpix, const hgs_raster_grads* grads, void* stream);
+
+/* Frustum test only (checkFrustum, rasterizer_impl.cu:54-66): present[i] = view-space z > 0.2. */
+int hgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present, void* stream);
+
+/* Mean squared distance to the 3 nearest neighbours of every point (distCUDA2).
+ * workspace: hgs_knn_bytes(P) bytes of device scratch. */
+size_t hgs_knn_bytes(int32_t P);
+int hgs_dist2_knn3(int32_t P, const float* points, float* mean_dist2, void* workspace, void* stream);
+
+/* Introspection of the opaque workspaces, for parity tests against the reference's
+ * geomBuffer/binningBuffer/imgBuffer carve-up.  `what` selects a sub-array; the call copies it
+ * (device to device, stream-ordered) into dst in the REFERENCE's element layout.
+ * Returns the number of bytes written, or < 0. */
+enum hgs_view {
+    HGS_VIEW_DEPTHS = 0,        /* float[P] */
+    HGS_VIEW_MEANS2D = 1,       /* float2[P] */
+    HGS_VIEW_CONIC_OPACITY = 2, /* float4[P] */
+    HGS_VIEW_RGB = 3,           /* float[P*channels] */
+    HGS_VIEW_TILES_TOUCHED = 4, /* uint32[P] */
+    HGS_VIEW_POINT_OFFSETS = 5, /* uint32[P] inclusive scan */
+    HGS_VIEW_CLAMPED = 6,       /* uint8[P*3] (bool per channel) */
+    HGS_VIEW_KEYS_SORTED = 7,   /* uint64[N] */
+    HGS_VIEW_POINT_LIST = 8,    /* uint32[N] sorted Gaussian ids */
+    HGS_VIEW_RANGES = 9,        /* uint2[tiles] */
+    HGS_VIEW_FINAL_T = 10,      /* float[H*W] */
+    HGS_VIEW_N_CONTRIB = 11,    /* uint32[H*W] */
+    HGS_VIEW_KEYS_UNSORTED = 12,/* uint64[N]; only valid between stage emission and sort (debug builds keep a copy) */
+    HGS_VIEW_COV3D = 13         /* float[P*6]; recomputed on demand */
+};
+int64_t hgs_state_view(int what, const hgs_raster_params* prm, const hgs_raster_inputs* in,
+                       int64_t num_rendered, const void* geom_ws, const void* binning_ws,
+                       const void* image_ws, void* dst, void* stream);
+
+/* Stand-alone stable LSD radix sort of (u64 key, u32 value) pairs on bits [0, end_bit): the
+ * hand-written onesweep that replaces cub::DeviceRadixSort::SortPairs (rasterizer_impl.cu:303-308).
+ * Exposed for parity tests and ncu captures.  workspace: hgs_sort_bytes(n). Sorted output is left in
+ * keys_out/vals_out (both in/out pairs are clobbered). */
+size_t hgs_sort_bytes(int64_t n);
+int hgs_sort_pairs(int64_t n, int end_bit, uint64_t* keys_in, uint32_t* vals_in,
+                   uint64_t* keys_out, uint32_t* vals_out, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAIRGS_RAST_H_ */
