@@ -29,6 +29,12 @@ def build(verbose=False):
         print(f"[oracle/_ref] reference not present at {REF}; using prebuilt files if any")
         return False
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    # This image's default CXX (/opt/gcc wrapper) links libstdc++ STATICALLY into shared objects; the
+    # reference prints integers through std::cout in BACKWARD::render (backward_distwar.cu:1203-1205) and a
+    # private, uninitialised libstdc++ copy segfaults there.  Use the distro compiler (dynamic libstdc++).
+    if os.path.exists("/usr/bin/g++"):
+        os.environ["CXX"] = "/usr/bin/g++"
+        os.environ["CC"] = "/usr/bin/gcc"
     from torch.utils.cpp_extension import load
     ok = True
     for name, srcs, inc in (

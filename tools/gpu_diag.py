@@ -91,6 +91,18 @@ def main():
     print(torch.cuda.get_device_name(0))
     assert refload.ref_dgr() is not None, "oracle/_ref not built"
     small = "--small" in sys.argv
+    import simple_knn._C as knn_ours
+    K = refload.ref_knn()
+    for n in (1, 2, 3, 4, 1000, 100000):
+        pts = torch.randn(n, 3, device=dev) * torch.tensor([1.0, 0.2, 3.0], device=dev) + 2.0
+        a, b = knn_ours.distCUDA2(pts), K.distCUDA2(pts)
+        torch.cuda.synchronize()
+        fin = torch.isfinite(b)
+        print(f"knn n={n}: bit-mismatch={common.bits_equal(a, b)} max-rel={(((a - b).abs() / b.abs().clamp_min(1e-30))[fin].max().item() if fin.any() else 0):.3e}"
+              f" inf ours={int((~torch.isfinite(a)).sum())} ref={int((~fin).sum())}")
+    t_ref = timeit(lambda: K.distCUDA2(pts))
+    t_our = timeit(lambda: knn_ours.distCUDA2(pts))
+    print(f"knn 100k ms: ref={t_ref:.3f} ours={t_our:.3f}")
     run_case("blobs sh3", common.blob_inputs(20000 if small else 300000, 512, 512, dev))
     run_case("blobs big splats", common.blob_inputs(5000, 256, 200, dev, scale_mul=8.0, seed=3))
     run_case("strands rgb", common.strand_inputs(200 if small else 2000, 100, 1024, 1024, dev))
