@@ -1,0 +1,519 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the Hair-GS render path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg5|cfg1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): training views/s of fwd+bwd rasterization.  A *step* is one camera view per GPU rendered
+the way Hair-GS trains on it (train.py:146-155, loss/losses.py:341-346): every colour set of the workload
+(cfg3: SH-RGB, mask, strand orientation) is rasterized forward and backward, the Gaussian-parameter gradients are
+accumulated into one flat fp32 bucket, and with N > 1 GPUs the bucket is all-reduced over NCCL (views shard over
+ranks, one process per GPU, no other data-path collective: weak scaling).
+
+  value  — device-resident: Gaussian inputs, cameras and dL/dimage already in HBM, the `_C` entry points of the
+           drop-in called directly (through the C ABI of libhairgs_rast.so).
+  e2e    — the public API a Hair-GS user calls: render(camera, model, bg) + autograd, with the view's camera and
+           target images copied host->device from pinned memory and the loss read back device->host every step.
+  roofline / stages — per-kernel device times from CUDA events recorded by the library on its launch stream.
+  cpu_baseline — the CPU port (oracle/, OpenMP C) on a bounded sample of the same workload, host cores stated.
+
+`--impl reference` runs the same harness on the UNMODIFIED reference rasterizer (oracle/_ref: the reference's own
+CUDA sources compiled for sm_100a; the reference has no CPU implementation of this path), falling back to the CPU
+port when that build is absent.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "hair-gs_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: (kind, S/P, V, W, H, views, colour sets, sh_degree, M)
+    "cfg1": dict(kind="strands", S=500, V=101, W=512, H=512, views=1, sets=("sh", "mask", "orientation"), D=0, M=1,
+                 desc="50k strand segments, 1 view 512x512"),
+    "cfg2": dict(kind="blobs", P=300000, W=512, H=512, views=16, sets=("sh",), D=3, M=16,
+                 desc="Stage I GaussianModel: 300k Gaussians, SH degree 3, 16 views 512x512"),
+    "cfg3": dict(kind="strands", S=10000, V=100, W=1024, H=1024, views=16, sets=("sh", "mask", "orientation"), D=0, M=1,
+                 desc="Stage III HairGaussianModel: 990k strand-aligned Gaussians (10k strands x 99 segments), "
+                      "1024x1024, RGB + mask + orientation"),
+    "cfg5": dict(kind="strands", S=40000, V=101, W=2048, H=2048, views=4, sets=("sh",), D=0, M=1,
+                 desc="stress: 4M strand-aligned Gaussians at 2048x2048"),
+}
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=48)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-views", type=int, default=2)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------
+def build_workload(cfg, dev):
+    import torch
+    from hairgs_b200 import models, scenes
+    if cfg["kind"] == "strands":
+        scene = scenes.strand_scene(cfg["S"], cfg["V"], seed=0, sh_coeffs=cfg["M"]).to(dev)
+        model = models.StrandModel(scene, sh_degree=cfg["D"]).to(dev)
+    else:
+        scene = scenes.blob_scene(cfg["P"], seed=0, sh_coeffs=cfg["M"]).to(dev)
+        model = models.BlobModel(scene, sh_degree=cfg["D"]).to(dev)
+    cams = scenes.orbit_cameras(max(cfg["views"], 2), cfg["W"], cfg["H"], device=dev)[:cfg["views"]]
+    return model, cams
+
+
+def colour_override(model, which):
+    if which == "sh":
+        return None
+    if which == "mask":
+        return model.get_mask.repeat(1, 3)
+    return model.get_orientation
+
+
+class Harness:
+    """Everything both arms share; `backend` is the `_C`-shaped extension module under test."""
+
+    def __init__(self, cfg, dev, backend, world, rank):
+        import torch
+        self.torch, self.cfg, self.dev, self.C, self.world, self.rank = torch, cfg, dev, backend, world, rank
+        self.model, self.cams = build_workload(cfg, dev)
+        from hairgs_b200 import multiview
+        self.my_views, _ = multiview.shard_views(len(self.cams), world, rank)
+        self.bg = torch.zeros(3, device=dev)
+        H, W = cfg["H"], cfg["W"]
+        g = torch.Generator(device="cpu").manual_seed(1234)
+        # synthetic targets per view (pinned host memory): rgb[3], mask[1], orientation[3]
+        self.targets_host = [torch.rand(7, H, W, generator=g).pin_memory() for _ in self.my_views]
+        # device-resident inputs of the `value` loop
+        with torch.no_grad():
+            m = self.model
+            self.inputs = dict(means3D=m.get_xyz.contiguous(), opacity=m.get_opacity.contiguous(),
+                               scales=m.get_scaling.contiguous(), rotations=m.get_rotation.contiguous(),
+                               sh=m.get_features.contiguous())
+            self.colours = {s: (None if s == "sh" else colour_override(m, s).contiguous()) for s in cfg["sets"]}
+        self.dL = {s: torch.randn(3, H, W, generator=g).to(dev) / (H * W) for s in cfg["sets"]}
+        P, M = self.inputs["means3D"].shape[0], self.inputs["sh"].shape[1]
+        self.P, self.M = P, M
+        # flat gradient bucket: means3D 3, scales 3, rotations 4, opacity 1, sh 3M, + 3 per override colour set
+        shapes = {"means3D": (P, 3), "scales": (P, 3), "rotations": (P, 4), "opacity": (P, 1), "sh": (P, M, 3)}
+        for s in cfg["sets"]:
+            if s != "sh":
+                shapes["colour_" + s] = (P, 3)
+        self.bucket = multiview.GradBucket(shapes, dev)
+        self.empty = torch.Tensor([])
+        self.last_N = 0
+
+    # ---- device-resident step: direct _C calls ------------------------------------------------------
+    def step_resident(self, it):
+        torch, C, cfg, i = self.torch, self.C, self.cfg, self.inputs
+        cam = self.cams[self.my_views[it % len(self.my_views)]]
+        b = self.bucket.zero_()
+        for s in cfg["sets"]:
+            col = self.colours[s]
+            sh = i["sh"] if col is None else self.empty
+            colors = self.empty if col is None else col
+            N, color, radii, geom, binning, img = C.rasterize_gaussians(
+                self.bg, i["means3D"], colors, i["opacity"], i["scales"], i["rotations"], 1.0, self.empty,
+                cam.world_view_transform, cam.full_proj_transform, cam.tanfovx, cam.tanfovy, cfg["H"], cfg["W"], sh,
+                cfg["D"], cam.camera_center, False, False)
+            g2d, gcol, gop, gm3, gcov, gsh, gsc, grot = C.rasterize_gaussians_backward(
+                self.bg, i["means3D"], radii, colors, i["scales"], i["rotations"], 1.0, self.empty,
+                cam.world_view_transform, cam.full_proj_transform, cam.tanfovx, cam.tanfovy, self.dL[s], sh, cfg["D"],
+                cam.camera_center, geom, N, binning, img, False)
+            b.accumulate("means3D", gm3).accumulate("scales", gsc).accumulate("rotations", grot).accumulate("opacity", gop)
+            if col is None:
+                b.accumulate("sh", gsh)
+            else:
+                b.accumulate("colour_" + s, gcol)
+            self.last_N = N
+        b.all_reduce()  # one collective per step; no-op on a single rank
+
+    # ---- end-to-end step: render() + autograd, host<->device copies inside --------------------------
+    def setup_e2e(self):
+        torch = self.torch
+        import diff_gaussian_rasterization as dgr
+        dgr._RasterizeGaussians.backend = self.C
+        from gaussian_renderer import render
+        self.render = render
+        self.params = [p for p in self.model.parameters()]
+        n = sum(p.numel() for p in self.params)
+        self.flat_grad = torch.zeros(n, device=self.dev)
+        o = 0
+        for p in self.params:
+            p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        H, W = self.cfg["H"], self.cfg["W"]
+        self.tgt_dev = [torch.empty(7, H, W, device=self.dev) for _ in range(2)]
+        self.cam_host = []
+        for v in self.my_views:
+            c = self.cams[v]
+            self.cam_host.append(torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1),
+                                            c.camera_center.reshape(-1)]).cpu().pin_memory())
+        self.cam_dev = [torch.empty(35, device=self.dev) for _ in range(2)]
+        self.copy_done = [torch.cuda.Event() for _ in range(2)]
+        self.slot_free = [torch.cuda.Event() for _ in range(2)]
+        self.loss_host = torch.zeros(1).pin_memory()
+        self.h2d_bytes = 7 * H * W * 4 + 35 * 4
+        self.d2h_bytes = 4
+        self._prefetched = -1
+
+    def _prefetch(self, it):
+        """stage view `it` into slot it%2 on the copy stream (double-buffered data loader)."""
+        torch = self.torch
+        slot, k = it % 2, it % len(self.my_views)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.slot_free[slot])
+            self.tgt_dev[slot].copy_(self.targets_host[k], non_blocking=True)
+            self.cam_dev[slot].copy_(self.cam_host[k], non_blocking=True)
+            self.copy_done[slot].record(self.copy_stream)
+        self._prefetched = it
+
+    def step_e2e(self, it):
+        torch, cfg = self.torch, self.cfg
+        from hairgs_b200.scenes import Camera
+        if self._prefetched < it:
+            self._prefetch(it)
+        slot = it % 2
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self.copy_done[slot])
+        if self._prefetched < it + 1:
+            self._prefetch(it + 1)  # next view's copies overlap this view's kernels
+        base = self.cams[self.my_views[it % len(self.my_views)]]
+        cd = self.cam_dev[slot]
+        cam = Camera(base.image_width, base.image_height, base.FoVx, base.FoVy, cd[0:16].view(4, 4), cd[16:32].view(4, 4),
+                     cd[32:35])
+        tgt = self.tgt_dev[slot]
+        self.flat_grad.zero_()
+        m = self.model
+        loss = None
+        for s in cfg["sets"]:
+            out = self.render(cam, m, self.bg, override_color=colour_override(m, s))["render"]
+            if s == "sh":
+                term = (out - tgt[0:3]).abs().mean()
+            elif s == "mask":
+                term = 0.01 * (out[0:1] - tgt[3:4]).abs().mean()  # lambda_mask, arguments/__init__.py:86
+            else:
+                term = (out - tgt[4:7]).abs().mean()
+            loss = term if loss is None else loss + term
+        loss.backward()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_grad)
+        self.slot_free[slot].record(cur)
+        self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+
+def timed_loop(torch, step_fn, steps, warmup, world, dev, flush=None):
+    """W untimed + exactly K timed steps; barrier + synchronize on both sides; device time via CUDA events;
+    returns the max over ranks of the elapsed milliseconds."""
+    for it in range(warmup):
+        step_fn(it)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(dev)
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for it in range(warmup, warmup + steps):
+            step_fn(it)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+    else:
+        evs = []
+        for it in range(warmup, warmup + steps):
+            flush.zero_()  # evict L2 between timed iterations (outside the event brackets)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_fn(it)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize(dev)
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+    if world > 1:
+        torch.distributed.barrier()
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU port (oracle) timing — bounded sample
+# ---------------------------------------------------------------------------------------------------
+def cpu_port_views_per_s(cfg, n_views):
+    import numpy as np
+    import torch
+    from oracle import pyoracle
+    model, cams = build_workload(cfg, "cpu")
+    with torch.no_grad():
+        base = dict(background=np.zeros(3, np.float32), means3D=model.get_xyz.numpy(), opacity=model.get_opacity.numpy(),
+                    scales=model.get_scaling.numpy(), rotations=model.get_rotation.numpy(), cov3D_precomp=None,
+                    scale_modifier=1.0, image_height=cfg["H"], image_width=cfg["W"], degree=cfg["D"])
+        cols = {s: (None if s == "sh" else colour_override(model, s).numpy()) for s in cfg["sets"]}
+        sh = model.get_features.numpy()
+    rng = np.random.default_rng(0)
+    dL = rng.standard_normal((3, cfg["H"], cfg["W"])).astype(np.float32)
+    t0 = time.perf_counter()
+    for v in range(n_views):
+        cam = cams[v % len(cams)]
+        for s in cfg["sets"]:
+            d = dict(base, viewmatrix=cam.world_view_transform.numpy(), projmatrix=cam.full_proj_transform.numpy(),
+                     campos=cam.camera_center.numpy(), tan_fovx=cam.tanfovx, tan_fovy=cam.tanfovy,
+                     sh=sh if cols[s] is None else None, colors=cols[s])
+            f = pyoracle.Forward(d)
+            f.backward(dL)
+            f.close()
+    dt = time.perf_counter() - t0
+    return n_views / dt, pyoracle.num_threads(), dt
+
+
+# ---------------------------------------------------------------------------------------------------
+def algorithmic_bytes(stage, P, N, HW, T, M, D, sh_mode, C=3):
+    """SURVEY.md §8(d) compulsory traffic per launch of each stage."""
+    if stage == "preprocess_fwd":
+        return P * (44 + (12 * (D + 1) ** 2 if sh_mode else 12) + 8) + P * (28 + 12)
+    if stage == "emit_keys":
+        return 20 * P + 12 * N
+    if stage == "sort_histogram":
+        return 8 * N
+    if stage == "sort_onesweep":
+        return 24 * N  # one pass: read + write of (u64 key, u32 value)
+    if stage == "tile_ranges":
+        return 8 * N + 8 * T
+    if stage == "composite_fwd":
+        return 40 * N + 20 * HW
+    if stage == "composite_bwd":
+        return 40 * N + 20 * HW + 36 * N
+    if stage == "preprocess_bwd":
+        return P * (96 + 40) + (P * (12 * (D + 1) ** 2 + 15) + P * 12 * M if sh_mode else 0)
+    return 0
+
+
+def main():
+    args = parse_args()
+    cfg = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import torch
+    config = {"workload": f"{args.workload}: {cfg['desc']}", "views": cfg["views"], "colour_sets": list(cfg["sets"]),
+              "resolution": [cfg["W"], cfg["H"]], "sharding": f"views round-robin over {world} rank(s)"}
+    base_line = {"metric": "train views/s (fwd+bwd rasterize incl. grad accumulation" +
+                           (", NCCL all-reduce" if world > 1 else "") + ")", "unit": "views/s", "n_gpus": world,
+                 "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config}
+
+    use_ref_gpu = False
+    if args.impl == "reference":
+        if rank != 0:
+            return 0  # the reference is single-GPU (utils/general.py:116): rank 0 alone measures it
+        world = 1
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import refload
+        use_ref_gpu = torch.cuda.is_available() and refload.ref_dgr() is not None
+        if not use_ref_gpu:
+            # CPU port of the path on all host cores, bounded sample per step
+            vps, cores, dt = cpu_port_views_per_s(cfg, max(1, min(args.steps, args.cpu_sample_views)))
+            line = dict(base_line, impl="reference", value=vps, n_gpus=1, ms_per_step=1000.0 / vps,
+                        cpu_baseline={"value": vps, "unit": "views/s", "cores": cores, "kind": "port",
+                                      "sample": f"{args.cpu_sample_views} view(s) of {args.workload}, all colour sets, fwd+bwd"},
+                        e2e={"value": vps, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                        gpu_launches=0)
+            print(json.dumps(line))
+            return 0
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+
+    if args.impl == "reference":
+        import refload
+        backend = refload.ref_dgr()
+    else:
+        import diff_gaussian_rasterization._C as backend
+    from hairgs_b200 import _lib as L
+    lib = L.load()
+
+    h = Harness(cfg, dev, backend, world, rank)
+    P, M, D = h.P, h.M, cfg["D"]
+    HW = cfg["W"] * cfg["H"]
+    T = ((cfg["W"] + 15) // 16) * ((cfg["H"] + 15) // 16)
+
+    # working-set estimate of one step -> L2 policy
+    sets = len(cfg["sets"])
+    h.step_resident(0)
+    torch.cuda.synchronize(dev)
+    N = h.last_N
+    ws = P * (56 + 12 * (M - 1)) + sets * (P * 69 + N * 24 + HW * 44 + P * 4 * (11 + 19 + 3 * M)) + h.bucket.flat.numel() * 4
+    flush = None
+    if ws < 2 * L2_BYTES:
+        flush = torch.empty(2 * L2_BYTES // 4, device=dev)
+        config["l2"] = f"explicit flush: {2 * L2_BYTES >> 20} MiB written between timed steps (working set {ws >> 20} MiB)"
+    else:
+        config["l2"] = f"no flush: per-step working set ~{ws >> 20} MiB > 126 MiB L2, views rotate every step"
+    config["P"], config["num_rendered"] = P, N
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    import ctypes
+    ms_res = timed_loop(torch, h.step_resident, args.steps, args.warmup, world, dev, flush)
+    # kernels of libhairgs_rast.so launched per step (the library counts its own launches)
+    launches = (ctypes.c_int64 * 10)()
+    lib.hgs_profile_collect(None, launches)  # reset
+    h.step_resident(0)
+    launches = (ctypes.c_int64 * 10)()
+    lib.hgs_profile_collect(None, launches)
+    launches_per_step = int(sum(launches))
+
+    h.setup_e2e()
+    ms_e2e = timed_loop(torch, h.step_e2e, args.steps, args.warmup, world, dev, flush)
+    clk = clocks.stop() if rank == 0 else None
+    import diff_gaussian_rasterization as dgr
+    dgr._RasterizeGaussians.backend = dgr._C
+
+    views = world * args.steps
+    value = views / (ms_res / 1000.0)
+    e2e_value = views / (ms_e2e / 1000.0)
+
+    # ---- per-stage device times (CUDA events recorded by the library on its launch stream) ----------
+    stages = {}
+    roofline = None
+    if args.impl == "ours":
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else (6650.0, "fallback 6.65 TB/s")
+        lib.hgs_profile_enable(1)
+        prof_steps = min(args.steps, 8)
+        for it in range(prof_steps):
+            h.step_resident(it)
+        ms = (ctypes.c_double * 10)()
+        cnt = (ctypes.c_int64 * 10)()
+        lib.hgs_profile_collect(ms, cnt)
+        lib.hgs_profile_enable(0)
+        total = sum(ms)
+        for sidx in range(10):
+            if cnt[sidx] == 0:
+                continue
+            name = lib.hgs_stage_name(sidx).decode()
+            per_launch_ms = ms[sidx] / cnt[sidx]
+            ab = algorithmic_bytes(name, P, N, HW, T, M, D, True)
+            stages[name] = {"ms_per_launch": round(per_launch_ms, 5), "launches_per_step": cnt[sidx] / prof_steps,
+                            "share": round(ms[sidx] / total, 4) if total else None,
+                            "achieved_GBps": round(ab / per_launch_ms / 1e6, 1) if per_launch_ms > 0 and ab else None,
+                            "frac_of_hbm_peak": round(ab / per_launch_ms / 1e6 / peak, 4) if per_launch_ms > 0 and ab else None}
+        dom = max(stages, key=lambda k: stages[k]["ms_per_launch"] * stages[k]["launches_per_step"])
+        ab = algorithmic_bytes(dom, P, N, HW, T, M, D, True)
+        ach = ab / stages[dom]["ms_per_launch"] / 1e6
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": ab,
+                    "note": "compositors are issue/latency-bound (serial transmittance chain), see DESIGN.md; "
+                            "HBM-bound stages are listed under 'stages'"}
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return 0
+
+    line = dict(base_line, value=round(value, 2), ms_per_step=round(ms_res / args.steps, 4),
+                e2e={"value": round(e2e_value, 2), "unit": "views/s", "h2d_bytes_per_step": h.h2d_bytes,
+                     "d2h_bytes_per_step": h.d2h_bytes, "ms_per_step": round(ms_e2e / args.steps, 4),
+                     "api": "gaussian_renderer.render() + autograd, targets/camera prefetched from pinned host memory"},
+                gpu_launches=launches_per_step * args.steps, clocks=clk)
+    line["n_gpus"] = world
+    if args.impl == "reference":
+        line["impl"] = "reference"
+        line["cpu_baseline"] = {"value": round(value, 2), "unit": "views/s", "cores": 0, "kind": "reference",
+                                "sample": "the reference has no CPU implementation of this path: this is its own CUDA "
+                                          "rasterizer (oracle/_ref, sm_100a build, BW_IMPLEMENTATION=1 "
+                                          "BALANCE_THRESHOLD=8 as train.py:278) on the same GPU, full workload"}
+        line["gpu_launches"] = 0
+    else:
+        line["roofline"] = roofline
+        line["stages"] = stages
+        if not args.no_cpu_baseline and world == 1:
+            vps, cores, dt = cpu_port_views_per_s(cfg, args.cpu_sample_views)
+            line["cpu_baseline"] = {"value": round(vps, 4), "unit": "views/s", "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_sample_views} view(s) of {args.workload} (all colour sets, "
+                                              f"fwd+bwd) through the OpenMP C port in oracle/, {dt:.1f} s"}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

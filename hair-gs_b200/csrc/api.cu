@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 #include "hgs_common.cuh"
 
 namespace hgs {
@@ -33,6 +34,28 @@ int stage_check(const char* stage, int debug, cudaStream_t s) {
         return HGS_ERR_CUDA;
     }
     return HGS_OK;
+}
+
+// ---- stage profiler -------------------------------------------------------------------------------
+static bool g_prof_on = false;
+static int64_t g_launches[HGS_STAGE_COUNT] = {0};
+struct ProfRec { int stage; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+
+StageScope::StageScope(int stage_id, cudaStream_t s) : stage(stage_id), stream(s), stop(nullptr) {
+    g_launches[stage]++;
+    if (g_prof_on) {
+        ProfRec r;
+        r.stage = stage;
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, stream);
+        stop = r.b;
+        g_prof.push_back(r);
+    }
+}
+StageScope::~StageScope() {
+    if (stop) cudaEventRecord(stop, stream);
 }
 
 // launchers implemented in the other translation units
@@ -80,6 +103,34 @@ static inline int end_bit_for(const hgs_raster_params* prm) {
 using namespace hgs;
 
 extern "C" {
+
+int hgs_profile_enable(int on) {
+    g_prof_on = on != 0;
+    return HGS_OK;
+}
+
+int hgs_profile_collect(double* ms, int64_t* launches) {
+    if (int e = check_cuda(cudaDeviceSynchronize(), "profile sync")) return e;
+    for (auto& r : g_prof) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && ms) ms[r.stage] += (double)t;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    for (int i = 0; i < HGS_STAGE_COUNT; ++i) {
+        if (launches) launches[i] += g_launches[i];
+        g_launches[i] = 0;
+    }
+    return HGS_OK;
+}
+
+const char* hgs_stage_name(int stage) {
+    static const char* names[HGS_STAGE_COUNT] = {"preprocess_fwd", "emit_keys", "sort_histogram", "sort_onesweep",
+                                                  "tile_ranges", "composite_fwd", "composite_bwd", "preprocess_bwd",
+                                                  "knn", "other"};
+    return (stage >= 0 && stage < HGS_STAGE_COUNT) ? names[stage] : "?";
+}
 
 int hgs_abi_version(void) { return HGS_ABI_VERSION; }
 const char* hgs_last_error(void) { return g_err; }

@@ -274,6 +274,7 @@ __global__ void tile_ranges_kernel(uint32_t L, const uint64_t* __restrict__ keys
 int launch_emit_keys(int P, const GeomLayout& g, const uint2* rects, uint64_t* keys, uint32_t* vals, uint32_t grid_x,
                      uint32_t capacity, cudaStream_t s) {
     if (P <= 0) return HGS_OK;
+    StageScope prof(HGS_STAGE_EMIT_KEYS, s);
     emit_keys_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, rects, g.depths, g.offsets, g.tiles_touched, keys, vals,
                                                       grid_x, capacity);
     return check_cuda(cudaGetLastError(), "emit_keys launch");
@@ -311,10 +312,14 @@ int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[
     const uint32_t nn = (uint32_t)n;
     int64_t hb = (n + 256 * 8 - 1) / (256 * 8);
     const int hblocks = (int)(hb < 148 * 8 ? hb : 148 * 8);
-    radix_histogram_kernel<<<hblocks, 256, 0, s>>>(keys[0], nn, passes, L.hist);
+    {
+        StageScope prof(HGS_STAGE_SORT_HISTOGRAM, s);
+        radix_histogram_kernel<<<hblocks, 256, 0, s>>>(keys[0], nn, passes, L.hist);
+    }
     if (int e = check_cuda(cudaGetLastError(), "radix_histogram launch")) return e;
     int cur = 0;
     for (int p = 0; p < passes; ++p) {
+        StageScope prof(HGS_STAGE_SORT_ONESWEEP, s);
         onesweep_pass_kernel<<<(unsigned)L.ntiles, kSortThreads, sizeof(OnesweepSmem), s>>>(
             keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], nn, 8 * p, L.hist + p * kRadix,
             L.status + (size_t)p * L.ntiles * kRadix, L.tickets + p);
@@ -328,6 +333,7 @@ int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[
 int launch_tile_ranges(int64_t n, const uint64_t* keys_sorted, uint2* ranges, size_t tiles, cudaStream_t s) {
     if (int e = check_cuda(cudaMemsetAsync(ranges, 0, tiles * sizeof(uint2), s), "memset ranges")) return e;
     if (n > 0) {
+        StageScope prof(HGS_STAGE_TILE_RANGES, s);
         tile_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((uint32_t)n, keys_sorted, ranges);
         return check_cuda(cudaGetLastError(), "tile_ranges launch");
     }

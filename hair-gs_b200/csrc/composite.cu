@@ -397,6 +397,7 @@ static int launch_fwd_c(const ImageLayout& im, const uint32_t* point_list, int W
                         const float* bg, float* out_color, cudaStream_t s) {
     dim3 grid((W + HGS_TILE - 1) / HGS_TILE, (H + HGS_TILE - 1) / HGS_TILE);
     constexpr int CS = (C <= 4) ? 4 : 8;
+    StageScope prof(HGS_STAGE_COMPOSITE_FWD, s);
     composite_fwd_kernel<C, CS><<<grid, 256, 0, s>>>(im.ranges, point_list, W, H, g.rec, g.rgb, bg, im.final_T,
                                                       im.n_contrib, out_color);
     return check_cuda(cudaGetLastError(), "composite_fwd launch");
@@ -423,6 +424,7 @@ static int launch_bwd_c(const ImageLayout& im, const uint32_t* point_list, int W
                         const float* bg, const float* dL_dpix, const hgs_raster_grads* gr, cudaStream_t s) {
     dim3 grid((W + HGS_TILE - 1) / HGS_TILE, (H + HGS_TILE - 1) / HGS_TILE);
     constexpr int CS = (C <= 4) ? 4 : 8;
+    StageScope prof(HGS_STAGE_COMPOSITE_BWD, s);
     composite_bwd_kernel<C, CS><<<grid, 256, 0, s>>>(im.ranges, point_list, W, H, bg, g.rec, g.rgb, im.final_T,
                                                       im.n_contrib, dL_dpix, gr->dL_dmean2D, gr->dL_dconic,
                                                       gr->dL_dopacity, gr->dL_dcolor);

@@ -19,6 +19,19 @@ int check_cuda(cudaError_t e, const char* what);
 int stage_check(const char* stage, int debug, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------
+// Stage profiler: counts every kernel launch of the library and, when enabled through
+// hgs_profile_enable(), brackets each launch with CUDA events on the launching stream
+// (bench.py's roofline numbers come from here; see hgs_profile_collect in api.cu).
+// ------------------------------------------------------------------------------------------------
+struct StageScope {
+    int stage;
+    cudaStream_t stream;
+    cudaEvent_t stop;
+    StageScope(int stage_id, cudaStream_t s);
+    ~StageScope();
+};
+
+// ------------------------------------------------------------------------------------------------
 // Workspace layouts.  All sub-arrays 256-B aligned; the same carve is repeated by forward, backward
 // and the state viewers (the role GeometryState/ImageState/BinningState::fromChunk play in the
 // reference, rasterizer_impl.cu:155-194 — but a different, 32-byte-record layout).

@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(128) knn_search_kernel(int P, const float4* __
 
 int launch_knn(int P, const float* points, float* out, void* ws, cudaStream_t s) {
     KnnLayout k = carve_knn(ws, P);
+    StageScope prof(HGS_STAGE_KNN, s);
     knn_init_bounds<<<1, 32, 0, s>>>(k.bounds);
     const int nb = (P + 255) / 256;
     knn_bounds_kernel<<<min(nb, 148 * 4), 256, 0, s>>>(P, points, k.bounds);

@@ -724,6 +724,7 @@ int launch_preprocess_fwd(const hgs_raster_params* prm, const hgs_raster_inputs*
     a.radii = radii; a.g = g;
     a.nblocks = (prm->P + kPreprocThreads - 1) / kPreprocThreads;
     if (int e = check_cuda(cudaMemsetAsync(g.hdr, 0, g.clear_bytes, s), "memset geom header")) return e;
+    StageScope prof(HGS_STAGE_PREPROCESS_FWD, s);
     preprocess_fwd_kernel<<<a.nblocks, kPreprocThreads, 0, s>>>(a);
     return check_cuda(cudaGetLastError(), "preprocess_fwd launch");
 }
@@ -742,11 +743,13 @@ int launch_preprocess_bwd(const hgs_raster_params* prm, const hgs_raster_inputs*
     a.dL_dmean2D = gr->dL_dmean2D; a.dL_dconic = gr->dL_dconic; a.dL_dcolor = gr->dL_dcolor;
     a.dL_dmean3D = gr->dL_dmean3D; a.dL_dcov3D = gr->dL_dcov3D; a.dL_dsh = gr->dL_dsh;
     a.dL_dscale = gr->dL_dscale; a.dL_drot = gr->dL_drot;
+    StageScope prof(HGS_STAGE_PREPROCESS_BWD, s);
     preprocess_bwd_kernel<<<(prm->P + 255) / 256, 256, 0, s>>>(a);
     return check_cuda(cudaGetLastError(), "preprocess_bwd launch");
 }
 
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s) {
+    StageScope prof(HGS_STAGE_OTHER, s);
     mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view, present);
     return check_cuda(cudaGetLastError(), "mark_visible launch");
 }

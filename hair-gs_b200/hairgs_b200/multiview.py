@@ -1,0 +1,74 @@
+"""View-sharded data parallelism for the render path.
+
+The path shards naturally over camera views: every rank holds a full replica of the Gaussian parameters, renders
+the views dealt to it, accumulates their parameter gradients IN PLACE into one flat fp32 bucket and the bucket is
+summed across ranks with a single all-reduce per optimiser step (NCCL over NVLink on the B200 box, gloo in the CPU
+tests).  There is no other data-path collective.  The reference has no distributed code at all
+(utils/general.py:116 pins cuda:0), so this is new surface, kept deliberately small.
+"""
+from collections import OrderedDict
+
+import torch
+import torch.distributed as dist
+
+
+def shard_views(n_views, world_size, rank):
+    """View i goes to rank i mod world_size (round-robin).  Every rank gets at least one view so that
+    collectives stay matched when n_views < world_size (the extra ranks repeat a view with zero weight)."""
+    if not (0 <= rank < world_size):
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    mine = list(range(rank, n_views, world_size))
+    weights = [1.0] * len(mine)
+    if not mine:
+        mine, weights = [rank % max(n_views, 1)], [0.0]
+    return mine, weights
+
+
+def steps_per_epoch(n_views, world_size):
+    """Number of lock-step iterations needed to cover all views: ceil(n_views / world_size)."""
+    return (n_views + world_size - 1) // world_size
+
+
+class GradBucket:
+    """One flat fp32 tensor with named views; gradients are accumulated into the views in place and the whole
+    bucket is all-reduced at once."""
+
+    def __init__(self, shapes, device):
+        self.slices = OrderedDict()
+        n = 0
+        for name, shape in shapes.items():
+            numel = 1
+            for s in shape:
+                numel *= int(s)
+            self.slices[name] = (n, numel, tuple(shape))
+            n += numel
+        self.flat = torch.zeros(n, dtype=torch.float32, device=device)
+
+    def view(self, name):
+        o, n, shape = self.slices[name]
+        return self.flat[o:o + n].view(shape)
+
+    def zero_(self):
+        self.flat.zero_()
+        return self
+
+    def accumulate(self, name, grad, weight=1.0):
+        v = self.view(name)
+        if weight == 1.0:
+            v.add_(grad.reshape(v.shape))
+        elif weight != 0.0:
+            v.add_(grad.reshape(v.shape), alpha=weight)
+        return self
+
+    def attach_to(self, params):
+        """Point p.grad of every parameter at its slice so autograd accumulates straight into the bucket."""
+        for name, p in params.items():
+            p.grad = self.view(name)
+
+    def all_reduce(self, group=None, average_over=None):
+        """Sum over ranks (one collective for every parameter); optionally divide by the number of views."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        if average_over:
+            self.flat.div_(float(average_over))
+        return self

@@ -226,8 +226,10 @@ def matrix_to_quaternion(matrix):
 
 
 def rotation_from_x_axis(v2, eps=1e-7):
-    """Rotation taking +x onto normalize(v2): R = I + K + K^2/(1 + x.d) (utils/transform.py:69-86)."""
-    v2 = v2 / torch.norm(v2, dim=1, keepdim=True)
+    """Rotation taking +x onto normalize(v2): R = I + K + K^2/(1 + x.d) (utils/transform.py:69-86).
+    The norm is floored at 1e-30 so collapsed segments give R = I instead of NaN (the reference filters them
+    out with a boolean mask before calling; callers here select with torch.where, which needs finite values)."""
+    v2 = v2 / torch.norm(v2, dim=1, keepdim=True).clamp_min(1e-30)
     v1 = torch.zeros_like(v2)
     v1[:, 0] = 1.0
     dot = torch.clamp(torch.sum(v1 * v2, dim=1), -1 + eps, 1 - eps)
@@ -243,25 +245,43 @@ def rotation_from_x_axis(v2, eps=1e-7):
     return eye + K + torch.bmm(K, K) / (1 + dot)[:, None, None]
 
 
-def strand_gaussians(endpoints, endpoint_pairs, width):
-    """HairGaussianModel.get_xyz / get_scaling / get_rotation / get_orientation
-    (scene/hair_gaussian_model.py:134-201): returns (means3D[P,3], scales[P,3], rotations[P,4], orientation[P,3])."""
-    pairs = endpoints[endpoint_pairs]  # [P,2,3]
-    diff = pairs[:, 1] - pairs[:, 0]
-    means = torch.mean(pairs, dim=1)
-    dist = torch.norm(diff, p=2, dim=1, keepdim=True)
+def strand_xyz(endpoints, endpoint_pairs):
+    """HairGaussianModel.get_xyz (scene/hair_gaussian_model.py:167-172): segment centres."""
+    return torch.mean(endpoints[endpoint_pairs], dim=1)
+
+
+def strand_scaling(endpoints, endpoint_pairs, width):
+    """get_scaling (:134-145): sigma_x = max(|e1-e0|/2 * k, 1e-7), sigma_yz = exp(width)."""
+    pairs = endpoints[endpoint_pairs]
+    dist = torch.norm(pairs[:, 1] - pairs[:, 0], p=2, dim=1, keepdim=True)
     scale_x = torch.clamp(dist / 2 * DIST_TO_SCALE, min=MIN_VAL)
-    scale_yz = torch.exp(width.repeat(1, 2))
-    scales = torch.cat((scale_x, scale_yz), dim=1)
-    valid = dist.squeeze(1) > MIN_VAL
-    rot = torch.zeros(diff.shape[0], 4, dtype=diff.dtype, device=diff.device)
-    rot[:, 0] = 1.0
-    if bool(valid.any()):
-        q = matrix_to_quaternion(rotation_from_x_axis(diff[valid]))
-        rot = rot.clone()
-        rot[valid] = q
-    orient = torch.zeros_like(diff)
-    orient[:, 0] = 1.0
-    ok = dist.squeeze(1) >= MIN_VAL
-    orient = torch.where(ok[:, None], diff / dist.clamp_min(1e-30), orient)
-    return means, scales, rot, orient
+    return torch.cat((scale_x, torch.exp(width.repeat(1, 2))), dim=1)
+
+
+def strand_rotation(endpoints, endpoint_pairs):
+    """get_rotation (:147-165): quaternion (w,x,y,z) rotating +x onto the segment; identity when collapsed;
+    NOT re-normalised (neither does the reference, :164, nor the rasterizer, forward.cu:127).
+    Sync-free: the reference's boolean-mask indexing is replaced by torch.where."""
+    pairs = endpoints[endpoint_pairs]
+    v2 = pairs[:, 1] - pairs[:, 0]
+    valid = torch.norm(v2, p=2, dim=1) > MIN_VAL
+    q = matrix_to_quaternion(rotation_from_x_axis(v2))
+    ident = torch.zeros_like(q)
+    ident[:, 0] = 1.0
+    return torch.where(valid[:, None], q, ident)
+
+
+def strand_orientation(endpoints, endpoint_pairs):
+    """get_orientation (:188-201): unit segment direction, +x when collapsed."""
+    pairs = endpoints[endpoint_pairs]
+    d = pairs[:, 1] - pairs[:, 0]
+    norm = torch.norm(d, p=2, dim=1, keepdim=True)
+    xaxis = torch.zeros_like(d)
+    xaxis[:, 0] = 1.0
+    return torch.where(norm >= MIN_VAL, d / norm.clamp_min(1e-30), xaxis)
+
+
+def strand_gaussians(endpoints, endpoint_pairs, width):
+    """All four derived quantities: (means3D[P,3], scales[P,3], rotations[P,4], orientation[P,3])."""
+    return (strand_xyz(endpoints, endpoint_pairs), strand_scaling(endpoints, endpoint_pairs, width),
+            strand_rotation(endpoints, endpoint_pairs), strand_orientation(endpoints, endpoint_pairs))

@@ -169,6 +169,28 @@ size_t hgs_sort_bytes(int64_t n);
 int hgs_sort_pairs(int64_t n, int end_bit, uint64_t* keys_in, uint32_t* vals_in,
                    uint64_t* keys_out, uint32_t* vals_out, void* workspace, void* stream);
 
+/* Per-stage device timing and launch counting (no reference counterpart; the reference only has the
+ * debug-mode synchronisation of auxiliary.h:166-173).  hgs_profile_enable(1) makes every kernel launch of the
+ * library bracket itself with CUDA events on its stream; hgs_profile_collect synchronises the device, adds
+ * the elapsed milliseconds per stage into ms[HGS_STAGE_COUNT], the launches per stage into
+ * launches[HGS_STAGE_COUNT], and resets.  Launch counts are kept even when timing is disabled. */
+enum hgs_stage {
+    HGS_STAGE_PREPROCESS_FWD = 0,
+    HGS_STAGE_EMIT_KEYS = 1,
+    HGS_STAGE_SORT_HISTOGRAM = 2,
+    HGS_STAGE_SORT_ONESWEEP = 3,
+    HGS_STAGE_TILE_RANGES = 4,
+    HGS_STAGE_COMPOSITE_FWD = 5,
+    HGS_STAGE_COMPOSITE_BWD = 6,
+    HGS_STAGE_PREPROCESS_BWD = 7,
+    HGS_STAGE_KNN = 8,
+    HGS_STAGE_OTHER = 9,
+    HGS_STAGE_COUNT = 10
+};
+int hgs_profile_enable(int on);
+int hgs_profile_collect(double* ms, int64_t* launches);
+const char* hgs_stage_name(int stage);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,95 @@
+"""N>1 host logic on CPU: two gloo ranks shard views round-robin, accumulate per-view gradients (produced by the
+CPU oracle — the CUDA rasterizer needs a GPU) into the flat bucket and all-reduce once; the result must equal the
+single-process sum of per-view gradients ('parity for the batch against the sum of per-view oracle
+gradients')."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import common
+from hairgs_b200 import multiview, scenes
+
+N_VIEWS = 3
+NAMES = ("dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dsh")
+
+
+def _view_grads(view):
+    from oracle import pyoracle
+    d = common.blob_inputs(400, 64, 48, "cpu", seed=5, view=view, n_views=N_VIEWS + 1, sh_degree=1, M=4)
+    f = pyoracle.Forward({k: (v.numpy() if torch.is_tensor(v) else v) for k, v in d.items()})
+    dL = np.random.default_rng(view).standard_normal(f.color.shape).astype(np.float32)
+    g = f.backward(dL)
+    f.close()
+    return {k: torch.tensor(g[k]) for k in NAMES}
+
+
+def _shapes():
+    return {"dL_dmeans3D": (400, 3), "dL_dscales": (400, 3), "dL_drotations": (400, 4), "dL_dopacity": (400, 1),
+            "dL_dsh": (400, 4, 3)}
+
+
+def _worker(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        bucket = multiview.GradBucket(_shapes(), "cpu")
+        views, weights = multiview.shard_views(N_VIEWS, world, rank)
+        for v, w in zip(views, weights):
+            for k, g in _view_grads(v).items():
+                bucket.accumulate(k, g, w)
+        bucket.all_reduce()
+        if rank == 0:
+            torch.save(bucket.flat.clone(), out_path)
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_two_rank_bucket_allreduce_equals_sum_of_views(tmp_path, world):
+    out = str(tmp_path / "flat.pt")
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    got = torch.load(out)
+    ref = multiview.GradBucket(_shapes(), "cpu")
+    for v in range(N_VIEWS):
+        for k, g in _view_grads(v).items():
+            ref.accumulate(k, g)
+    assert torch.allclose(got, ref.flat, rtol=1e-5, atol=1e-6)
+
+
+def test_shard_views_round_robin():
+    for n in (1, 3, 16, 64):
+        for w in (1, 2, 4, 8):
+            seen = []
+            for r in range(w):
+                v, wt = multiview.shard_views(n, w, r)
+                assert len(v) >= 1 and len(v) == len(wt)
+                seen += [x for x, y in zip(v, wt) if y > 0]
+            assert sorted(seen) == list(range(n))
+            assert multiview.steps_per_epoch(n, w) == -(-n // w)
+    with pytest.raises(ValueError):
+        multiview.shard_views(4, 2, 2)
+
+
+def test_bucket_attach_accumulates_autograd_in_place():
+    params = {"a": torch.nn.Parameter(torch.randn(5, 3)), "b": torch.nn.Parameter(torch.randn(7))}
+    bucket = multiview.GradBucket({k: p.shape for k, p in params.items()}, "cpu")
+    bucket.attach_to(params)
+    (params["a"].sum() * 2 + (params["b"] ** 2).sum()).backward()
+    assert torch.allclose(bucket.view("a"), torch.full((5, 3), 2.0))
+    assert torch.allclose(bucket.view("b"), 2 * params["b"].detach())
+    assert bucket.flat.data_ptr() == params["a"].grad.data_ptr()
