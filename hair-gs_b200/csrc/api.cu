@@ -66,10 +66,10 @@ int launch_mark_visible(int, const float*, const float*, uint8_t*, cudaStream_t)
 int launch_view_geom(int, const hgs_raster_params*, const hgs_raster_inputs*, const GeomLayout&, void*, cudaStream_t);
 int launch_emit_keys(int, const GeomLayout&, const uint2*, uint64_t*, uint32_t*, uint32_t, uint32_t, cudaStream_t);
 int launch_sort_pairs(int64_t, int, uint64_t* [2], uint32_t* [2], void*, int*, cudaStream_t);
-int launch_tile_ranges(int64_t, const uint64_t*, uint2*, size_t, cudaStream_t);
-int launch_composite_fwd(int, const ImageLayout&, const uint32_t*, int, int, const GeomLayout&, const float*, float*,
-                         cudaStream_t);
-int launch_composite_bwd(int, const ImageLayout&, const uint32_t*, int, int, const GeomLayout&, const float*,
+int launch_finalize_sorted(int, int64_t, const uint64_t*, const uint32_t*, const GeomLayout&, const BinningLayout&, uint2*,
+                           size_t, cudaStream_t);
+int launch_composite_fwd(int, const ImageLayout&, const BinningLayout&, int, int, const float*, float*, cudaStream_t);
+int launch_composite_bwd(int, const ImageLayout&, const BinningLayout&, const uint32_t*, int, int, const float*,
                          const float*, const hgs_raster_grads*, cudaStream_t);
 size_t knn_bytes(int P);
 int launch_knn(int P, const float* points, float* out, void* ws, cudaStream_t s);
@@ -137,7 +137,7 @@ const char* hgs_last_error(void) { return g_err; }
 
 size_t hgs_geom_bytes(int32_t P, int32_t channels) { return carve_geom(nullptr, P, channels).bytes; }
 size_t hgs_image_bytes(int32_t width, int32_t height) { return carve_image(nullptr, width, height).bytes; }
-size_t hgs_binning_bytes(int64_t n) { return carve_binning(nullptr, n).bytes; }
+size_t hgs_binning_bytes(int64_t n, int32_t channels) { return carve_binning(nullptr, n, channels).bytes; }
 size_t hgs_sort_bytes(int64_t n) { return carve_sort(nullptr, n).bytes; }
 
 int hgs_forward_stage_a(const hgs_raster_params* prm, const hgs_raster_inputs* in, void* geom_ws, int32_t* radii,
@@ -167,7 +167,7 @@ int hgs_forward_stage_b(const hgs_raster_params* prm, const hgs_raster_inputs* i
     if (N < 0 || N > 0x7fffffffll) { set_error("num_rendered out of range"); return HGS_ERR_OVERFLOW; }
     GeomLayout g = carve_geom(geom_ws, prm->P, prm->channels);
     ImageLayout im = carve_image(image_ws, prm->width, prm->height);
-    BinningLayout b = carve_binning(binning_ws, N);
+    BinningLayout b = carve_binning(binning_ws, N, prm->channels);
     const uint32_t gx = (prm->width + HGS_TILE - 1) / HGS_TILE, gy = (prm->height + HGS_TILE - 1) / HGS_TILE;
 
     if (int e = launch_emit_keys(N > 0 ? prm->P : 0, g, g.rects, b.keys[0], b.vals[0], gx, (uint32_t)N, s)) return e;
@@ -175,10 +175,9 @@ int hgs_forward_stage_b(const hgs_raster_params* prm, const hgs_raster_inputs* i
     int res = 0;
     if (int e = launch_sort_pairs(N, end_bit_for(prm), b.keys, b.vals, b.sort_ws, &res, s)) return e;
     if (int e = stage_check("sort", prm->debug, s)) return e;
-    if (int e = launch_tile_ranges(N, b.keys[res], im.ranges, (size_t)gx * gy, s)) return e;
-    if (int e = stage_check("tile_ranges", prm->debug, s)) return e;
-    if (int e = launch_composite_fwd(prm->channels, im, b.vals[res], prm->width, prm->height, g, in->background,
-                                     out_color, s)) return e;
+    if (int e = launch_finalize_sorted(prm->channels, N, b.keys[res], b.vals[res], g, b, im.ranges, (size_t)gx * gy, s)) return e;
+    if (int e = stage_check("finalize_sorted", prm->debug, s)) return e;
+    if (int e = launch_composite_fwd(prm->channels, im, b, prm->width, prm->height, in->background, out_color, s)) return e;
     return stage_check("composite_fwd", prm->debug, s);
 }
 
@@ -198,7 +197,7 @@ int hgs_rasterize_forward(hgs_alloc_fn geom_alloc, void* geom_user, hgs_alloc_fn
     if (int e = check_cuda(cudaStreamSynchronize(s), "sync num_rendered")) return e;
     if (host[2] || host[0] > 0x7fffffffu) { set_error("instance count overflows int32"); return HGS_ERR_OVERFLOW; }
     const int64_t N = host[0];
-    void* bin = binning_alloc(binning_user, hgs_binning_bytes(N));
+    void* bin = binning_alloc(binning_user, hgs_binning_bytes(N, prm->channels));
     if (!bin) { set_error("allocator returned NULL"); return HGS_ERR_ALLOC; }
     if (int e = hgs_forward_stage_b(prm, in, geom, bin, img, N, radii, out_color, s)) return e;
     return (int)N;
@@ -216,7 +215,7 @@ int hgs_rasterize_backward(const hgs_raster_params* prm, const hgs_raster_inputs
     if (P == 0) return HGS_OK;
     GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels);
     ImageLayout im = carve_image((void*)image_ws, prm->width, prm->height);
-    BinningLayout b = carve_binning((void*)binning_ws, R);
+    BinningLayout b = carve_binning((void*)binning_ws, R, prm->channels);
     const int res = sort_passes(end_bit_for(prm)) & 1;
 
     // accumulation targets of the compositor (the only arrays that need clearing)
@@ -232,7 +231,7 @@ int hgs_rasterize_backward(const hgs_raster_params* prm, const hgs_raster_inputs
         if (int e = check_cuda(cudaMemsetAsync(gr->dL_dcolor, 0, Pz * prm->channels * 4, s), "memset dL_dcolor")) return e;
     }
     if (R > 0) {
-        if (int e = launch_composite_bwd(prm->channels, im, b.vals[res], prm->width, prm->height, g, in->background,
+        if (int e = launch_composite_bwd(prm->channels, im, b, b.vals[res], prm->width, prm->height, in->background,
                                          dL_dpix, gr, s)) return e;
         if (int e = stage_check("composite_bwd", prm->debug, s)) return e;
     }
@@ -303,7 +302,7 @@ int64_t hgs_state_view(int what, const hgs_raster_params* prm, const hgs_raster_
         }
         case HGS_VIEW_KEYS_SORTED: case HGS_VIEW_POINT_LIST: {
             if (N > 0 && !binning_ws) { set_error("null binning workspace"); return HGS_ERR_INVALID; }
-            BinningLayout b = carve_binning((void*)binning_ws, N);
+            BinningLayout b = carve_binning((void*)binning_ws, N, prm->channels);
             const int res = sort_passes(end_bit_for(prm)) & 1;
             if (what == HGS_VIEW_KEYS_SORTED) return d2d(b.keys[res], (size_t)N * 8);
             return d2d(b.vals[res], (size_t)N * 4);

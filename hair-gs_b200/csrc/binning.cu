@@ -6,7 +6,7 @@
 //                    histogram pass + one chained-scan (decoupled look-back) scatter pass per digit, with
 //                    match.any warp-aggregated ranking (replaces cub::DeviceRadixSort::SortPairs
 //                    rasterizer_impl.cu:303-308)
-//   tile_ranges    : identifyTileRanges rasterizer_impl.cu:116-138
+//   (tile ranges are produced by finalize_sorted in composite_warp.cu)
 #include "hgs_common.cuh"
 
 namespace hgs {
@@ -250,25 +250,6 @@ __global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
-// tile ranges
-// ------------------------------------------------------------------------------------------------
-__global__ void tile_ranges_kernel(uint32_t L, const uint64_t* __restrict__ keys, uint2* __restrict__ ranges) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= L) return;
-    const uint32_t cur = (uint32_t)(keys[idx] >> 32);
-    if (idx == 0) {
-        ranges[cur].x = 0;
-    } else {
-        const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
-        if (cur != prev) {
-            ranges[prev].y = idx;
-            ranges[cur].x = idx;
-        }
-    }
-    if (idx == L - 1) ranges[cur].y = L;
-}
-
-// ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
 int launch_emit_keys(int P, const GeomLayout& g, const uint2* rects, uint64_t* keys, uint32_t* vals, uint32_t grid_x,
@@ -327,16 +308,6 @@ int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[
         cur ^= 1;
     }
     *result_buf = cur;
-    return HGS_OK;
-}
-
-int launch_tile_ranges(int64_t n, const uint64_t* keys_sorted, uint2* ranges, size_t tiles, cudaStream_t s) {
-    if (int e = check_cuda(cudaMemsetAsync(ranges, 0, tiles * sizeof(uint2), s), "memset ranges")) return e;
-    if (n > 0) {
-        StageScope prof(HGS_STAGE_TILE_RANGES, s);
-        tile_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((uint32_t)n, keys_sorted, ranges);
-        return check_cuda(cudaGetLastError(), "tile_ranges launch");
-    }
     return HGS_OK;
 }
 

@@ -1,0 +1,483 @@
+// composite_warp.cu — per-tile alpha compositing, forward and backward, warp-independent edition.
+//   composite_fwd<C> replaces renderCUDA            forward.cu:261-374
+//   composite_bwd<C> replaces renderCUDABW_*        backward_distwar.cu:450-1014 (all three variants)
+//   finalize_sorted  replaces identifyTileRanges    rasterizer_impl.cu:116-138 and additionally packs the
+//                    per-instance records in sorted order
+// Blending arithmetic follows SURVEY.md App. A exactly (same expressions, IEEE expf/div, no fast-math)
+// so that pixels, final_T and n_contrib agree with the reference build bit for bit.
+//
+// B200-first structure (what differs from the reference; motivated by profiles/r1_composite_v0.md):
+//  * after the sort, one streaming kernel writes every instance's record (means2D, conic, opacity, cull extent,
+//    colour) in SORTED order: the compositors then read their tile list with perfectly coalesced 128-bit loads
+//    instead of three dependent gathers per instance, forward AND backward;
+//  * a CTA still covers one 16x16 tile, but its 8 warps never synchronise with each other: each warp owns an
+//    8x4 pixel block and walks the tile list by itself in chunks of 32 instances (one per lane), prefetching
+//    the next chunk into registers.  No __syncthreads in the hot loop -> no barrier stalls, and early
+//    termination is per 32 pixels instead of per 256;
+//  * per chunk every lane tests ITS instance's alpha>=1/255 extent against the warp's pixel block; a ballot
+//    gives the candidates, which are broadcast through a 1.5 KB per-warp shared-memory slab.  Skipped instances
+//    are exactly those for which every pixel of the warp would take the reference's `continue`
+//    (power>0 or alpha<1/255), so outputs are unchanged; list positions still advance;
+//  * backward: gradients of a (warp, instance) pair are reduced with a transposing shuffle tree
+//    (V + 5 shuffles instead of 5 V), then 6+C lanes issue one red.global.add each.
+#include "hgs_common.cuh"
+
+namespace hgs {
+
+// ------------------------------------------------------------------------------------------------
+// finalize: tile ranges + sorted-order packing
+// ------------------------------------------------------------------------------------------------
+template <int CS>
+__global__ void __launch_bounds__(256) finalize_sorted_kernel(uint32_t L, const uint64_t* __restrict__ keys,
+                                                              const uint32_t* __restrict__ point_list,
+                                                              const float4* __restrict__ rec,
+                                                              const float* __restrict__ rgb, uint2* __restrict__ ranges,
+                                                              float4* __restrict__ pk_lo, float4* __restrict__ pk_hi,
+                                                              float4* __restrict__ pk_col) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= L) return;
+    const uint32_t id = point_list[idx];
+    const float4 lo = rec[2 * (size_t)id];
+    const float4 hi = rec[2 * (size_t)id + 1];
+    const float4 c0 = *reinterpret_cast<const float4*>(rgb + (size_t)id * CS);
+    pk_lo[idx] = lo;
+    pk_hi[idx] = hi;
+    pk_col[(size_t)idx * (CS / 4)] = c0;
+    if (CS > 4) pk_col[(size_t)idx * (CS / 4) + 1] = *reinterpret_cast<const float4*>(rgb + (size_t)id * CS + 4);
+    // tile ranges (rasterizer_impl.cu:116-138)
+    const uint32_t cur = (uint32_t)(keys[idx] >> 32);
+    if (idx == 0) {
+        ranges[cur].x = 0;
+    } else {
+        const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+        if (cur != prev) {
+            ranges[prev].y = idx;
+            ranges[cur].x = idx;
+        }
+    }
+    if (idx == L - 1) ranges[cur].y = L;
+}
+
+template <int C, int CS>
+__global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restrict__ ranges, int W, int H,
+                                                            const float4* __restrict__ pk_lo,
+                                                            const float4* __restrict__ pk_hi,
+                                                            const float4* __restrict__ pk_col,
+                                                            const float* __restrict__ bg_color,
+                                                            float* __restrict__ final_T,
+                                                            uint32_t* __restrict__ n_contrib,
+                                                            float* __restrict__ out_color) {
+    __shared__ float4 s_lo[8][32];
+    __shared__ float4 s_hi[8][32];
+    __shared__ float4 s_col[8][32 * (CS / 4)];
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t horizontal_blocks = (W + HGS_TILE - 1) / HGS_TILE;
+    const uint32_t X0 = blockIdx.x * HGS_TILE, Y0 = blockIdx.y * HGS_TILE;
+    const uint32_t bx = X0 + (warp & 1) * 8, by = Y0 + (warp >> 1) * 4;
+    const uint32_t px = bx + (lane & 7), py = by + (lane >> 3);
+    const uint32_t pix_id = W * py + px;
+    const float2 pixf = make_float2((float)px, (float)py);
+    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+    bool done = !inside;
+    const float wx0 = (float)bx, wx1 = (float)(bx + 7), wy0 = (float)by, wy1 = (float)(by + 3);
+
+    const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
+    const int total = (int)(range.y - range.x);
+    const int nchunks = (total + 31) >> 5;
+
+    float T = 1.0f;
+    uint32_t last_contributor = 0;
+    float Cacc[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) Cacc[ch] = 0.f;
+
+    if (!__all_sync(0xffffffffu, done) && nchunks > 0) {
+        float4 nlo = make_float4(0, 0, 0, 0), nhi = make_float4(0, 0, 0, 0), nc0 = make_float4(0, 0, 0, 0),
+               nc1 = make_float4(0, 0, 0, 0);
+        if ((int)lane < total) {
+            const size_t i = (size_t)range.x + lane;
+            nlo = pk_lo[i];
+            nhi = pk_hi[i];
+            nc0 = pk_col[i * (CS / 4)];
+            if (CS > 4) nc1 = pk_col[i * (CS / 4) + 1];
+        }
+        for (int c = 0; c < nchunks; ++c) {
+            const float4 lo = nlo, hi = nhi, c0 = nc0, c1 = nc1;
+            const bool have = c * 32 + (int)lane < total;
+            if (c + 1 < nchunks) {  // prefetch the next chunk while this one is blended
+                const int p = (c + 1) * 32 + (int)lane;
+                if (p < total) {
+                    const size_t i = (size_t)range.x + p;
+                    nlo = pk_lo[i];
+                    nhi = pk_hi[i];
+                    nc0 = pk_col[i * (CS / 4)];
+                    if (CS > 4) nc1 = pk_col[i * (CS / 4) + 1];
+                }
+            }
+            // culled only when a comparison is TRUE, so NaNs keep the instance (the reference would evaluate it)
+            const bool cand = have && !(lo.x - hi.z > wx1 || lo.x + hi.z < wx0 || lo.y - hi.w > wy1 || lo.y + hi.w < wy0);
+            uint32_t bits = __ballot_sync(0xffffffffu, cand);
+            if (bits) {
+                if (cand) {
+                    s_lo[warp][lane] = lo;
+                    s_hi[warp][lane] = hi;
+                    s_col[warp][lane * (CS / 4)] = c0;
+                    if (CS > 4) s_col[warp][lane * (CS / 4) + 1] = c1;
+                }
+                __syncwarp();
+                const uint32_t pos_base = (uint32_t)(c * 32) + 1u;
+                while (bits) {
+                    const int j = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if (done) continue;
+                    const float4 glo = s_lo[warp][j];
+                    const float4 ghi = s_hi[warp][j];
+                    const float2 d = make_float2(glo.x - pixf.x, glo.y - pixf.y);
+                    const float power = -0.5f * (glo.z * d.x * d.x + ghi.x * d.y * d.y) - glo.w * d.x * d.y;
+                    if (power > 0.0f) continue;
+                    const float alpha = min(0.99f, ghi.y * exp(power));
+                    if (alpha < 1.0f / 255.0f) continue;
+                    const float test_T = T * (1 - alpha);
+                    if (test_T < 0.0001f) {
+                        done = true;
+                        continue;
+                    }
+                    const float* col = reinterpret_cast<const float*>(&s_col[warp][j * (CS / 4)]);
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) Cacc[ch] += col[ch] * alpha * T;
+                    T = test_T;
+                    last_contributor = pos_base + (uint32_t)j;
+                }
+                __syncwarp();
+                if (__all_sync(0xffffffffu, done)) break;
+            }
+        }
+    }
+
+    if (inside) {
+        final_T[pix_id] = T;
+        n_contrib[pix_id] = last_contributor;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) out_color[(size_t)ch * H * W + pix_id] = Cacc[ch] + T * bg_color[ch];
+    }
+}
+
+// Sum V per-lane values across the warp with a transposing tree: after the call, lane l holds the
+// warp total of value index (l >> 2) & (VP-1) where VP = next pow2 >= V (VP <= 8 -> index l>>2).
+template <int VP>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[VP], uint32_t lane) {
+    static_assert(VP == 8 || VP == 16, "VP");
+    // level 0 (xor 16): keep lower half of the indices if bit4 clear, upper half otherwise
+    if (VP == 16) {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float send = up ? v[k] : v[k + 8];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+            v[k] = (up ? v[k + 8] : v[k]) + recv;
+        }
+        // now 8 live values: indices (bit4 ? 8 : 0) + k ; continue with xor 8, 4, 2 on 8 -> 1
+        {
+            const bool u2 = lane & 8;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float send = u2 ? v[k] : v[k + 4];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+                v[k] = (u2 ? v[k + 4] : v[k]) + recv;
+            }
+        }
+        {
+            const bool u3 = lane & 4;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float send = u3 ? v[k] : v[k + 2];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+                v[k] = (u3 ? v[k + 2] : v[k]) + recv;
+            }
+        }
+        {
+            const bool u4 = lane & 2;
+            const float send = u4 ? v[0] : v[1];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+            v[0] = (u4 ? v[1] : v[0]) + recv;
+        }
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+        return v[0];  // lane l holds index: bit4*8 + bit3*4 + bit2*2 + bit1  == (l >> 1) & 15
+    } else {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float send = up ? v[k] : v[k + 4];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+            v[k] = (up ? v[k + 4] : v[k]) + recv;
+        }
+        {
+            const bool u2 = lane & 8;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float send = u2 ? v[k] : v[k + 2];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+                v[k] = (u2 ? v[k + 2] : v[k]) + recv;
+            }
+        }
+        {
+            const bool u3 = lane & 4;
+            const float send = u3 ? v[0] : v[1];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+            v[0] = (u3 ? v[1] : v[0]) + recv;
+        }
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+        return v[0];  // lane l holds index (l >> 2) & 7
+    }
+}
+
+
+template <int C, int CS>
+__global__ void __launch_bounds__(256) composite_bwd_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
+    const float* __restrict__ bg_color, const float4* __restrict__ pk_lo, const float4* __restrict__ pk_hi,
+    const float4* __restrict__ pk_col, const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
+    const float* __restrict__ dL_dpixels, float* __restrict__ dL_dmean2D /*[P,3]*/,
+    float* __restrict__ dL_dconic /*[P,4]*/, float* __restrict__ dL_dopacity /*[P]*/,
+    float* __restrict__ dL_dcolors /*[P,C]*/) {
+    __shared__ float4 s_lo[8][32];
+    __shared__ float4 s_hi[8][32];
+    __shared__ float4 s_col[8][32 * (CS / 4)];
+    __shared__ uint32_t s_id[8][32];
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t horizontal_blocks = (W + HGS_TILE - 1) / HGS_TILE;
+    const uint32_t X0 = blockIdx.x * HGS_TILE, Y0 = blockIdx.y * HGS_TILE;
+    const uint32_t bx = X0 + (warp & 1) * 8, by = Y0 + (warp >> 1) * 4;
+    const uint32_t px = bx + (lane & 7), py = by + (lane >> 3);
+    const uint32_t pix_id = W * py + px;
+    const float2 pixf = make_float2((float)px, (float)py);
+    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+    const float wx0 = (float)bx, wx1 = (float)(bx + 7), wy0 = (float)by, wy1 = (float)(by + 3);
+
+    const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
+
+    const float T_final = inside ? final_Ts[pix_id] : 0;
+    float T = T_final;
+    const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
+
+    // nothing at list position >= max over the warp of last_contributor can contribute to these 32 pixels
+    int total = last_contributor;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) total = max(total, __shfl_xor_sync(0xffffffffu, total, o));
+    if (total == 0) return;
+    const int nchunks = (total + 31) >> 5;
+
+    float accum_rec[C], dL_dpixel[C], last_color[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+        accum_rec[ch] = 0.f;
+        last_color[ch] = 0.f;
+        dL_dpixel[ch] = inside ? dL_dpixels[(size_t)ch * H * W + pix_id] : 0.f;
+    }
+    float last_alpha = 0.f;
+    float bg_dot_dpixel = 0;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) bg_dot_dpixel += bg_color[ch] * dL_dpixel[ch];
+    const float ddelx_dx = 0.5 * W;
+    const float ddely_dy = 0.5 * H;
+
+    // back to front: lane l of chunk c holds list position total-1-(c*32+l)
+    float4 nlo = make_float4(0, 0, 0, 0), nhi = make_float4(0, 0, 0, 0), nc0 = make_float4(0, 0, 0, 0),
+           nc1 = make_float4(0, 0, 0, 0);
+    uint32_t nid = 0;
+    {
+        const int pos = total - 1 - (int)lane;
+        if (pos >= 0) {
+            const size_t i = (size_t)range.x + pos;
+            nlo = pk_lo[i];
+            nhi = pk_hi[i];
+            nc0 = pk_col[i * (CS / 4)];
+            if (CS > 4) nc1 = pk_col[i * (CS / 4) + 1];
+            nid = point_list[i];
+        }
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        const float4 lo = nlo, hi = nhi, c0 = nc0, c1 = nc1;
+        const uint32_t id = nid;
+        const int pos_first = total - 1 - c * 32;  // list position held by lane 0
+        const bool have = pos_first - (int)lane >= 0;
+        if (c + 1 < nchunks) {
+            const int pos = pos_first - 32 - (int)lane;
+            if (pos >= 0) {
+                const size_t i = (size_t)range.x + pos;
+                nlo = pk_lo[i];
+                nhi = pk_hi[i];
+                nc0 = pk_col[i * (CS / 4)];
+                if (CS > 4) nc1 = pk_col[i * (CS / 4) + 1];
+                nid = point_list[i];
+            }
+        }
+        const bool cand = have && !(lo.x - hi.z > wx1 || lo.x + hi.z < wx0 || lo.y - hi.w > wy1 || lo.y + hi.w < wy0);
+        uint32_t bits = __ballot_sync(0xffffffffu, cand);
+        if (!bits) continue;
+        if (cand) {
+            s_lo[warp][lane] = lo;
+            s_hi[warp][lane] = hi;
+            s_col[warp][lane * (CS / 4)] = c0;
+            if (CS > 4) s_col[warp][lane * (CS / 4) + 1] = c1;
+            s_id[warp][lane] = id;
+        }
+        __syncwarp();
+        while (bits) {
+            const int j = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int pos = pos_first - j;
+            bool valid = pos < last_contributor;  // false for outside pixels (last_contributor == 0)
+            const float4 glo = s_lo[warp][j];
+            const float4 ghi = s_hi[warp][j];
+            const float2 d = make_float2(glo.x - pixf.x, glo.y - pixf.y);
+            const float power = -0.5f * (glo.z * d.x * d.x + ghi.x * d.y * d.y) - glo.w * d.x * d.y;
+            if (power > 0.0f) valid = false;
+            const float G = exp(power);
+            const float alpha = min(0.99f, ghi.y * G);
+            if (alpha < 1.0f / 255.0f) valid = false;
+            if (!__any_sync(0xffffffffu, valid)) continue;
+
+            constexpr int V = 6 + C;
+            constexpr int VP = (V <= 8) ? 8 : 16;
+            float v[VP];
+#pragma unroll
+            for (int k = 0; k < VP; ++k) v[k] = 0.f;
+            if (valid) {
+                T = T / (1.f - alpha);
+                const float dchannel_dcolor = alpha * T;
+                float dL_dalpha = 0.0f;
+                const float* col = reinterpret_cast<const float*>(&s_col[warp][j * (CS / 4)]);
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    const float cc = col[ch];
+                    accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+                    last_color[ch] = cc;
+                    const float dL_dchannel = dL_dpixel[ch];
+                    dL_dalpha += (cc - accum_rec[ch]) * dL_dchannel;
+                    v[6 + ch] = dchannel_dcolor * dL_dchannel;
+                }
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                const float dL_dG = ghi.y * dL_dalpha;
+                const float gdx = G * d.x;
+                const float gdy = G * d.y;
+                const float dG_ddelx = -gdx * glo.z - gdy * glo.w;
+                const float dG_ddely = -gdy * ghi.x - gdx * glo.w;
+                v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                v[1] = dL_dG * dG_ddely * ddely_dy;
+                v[2] = -0.5f * gdx * d.x * dL_dG;
+                v[3] = -0.5f * gdx * d.y * dL_dG;
+                v[4] = -0.5f * gdy * d.y * dL_dG;
+                v[5] = G * dL_dalpha;
+            }
+            const float red = warp_transpose_reduce<VP>(v, lane);
+            const uint32_t gid = s_id[warp][j];
+            const int k = (VP == 8) ? (int)(lane >> 2) : (int)(lane >> 1);
+            const bool writer = (VP == 8) ? ((lane & 3) == 0) : ((lane & 1) == 0);
+            if (writer && k < V) {
+                float* dst;
+                switch (k) {
+                    case 0: dst = dL_dmean2D + 3 * (size_t)gid; break;
+                    case 1: dst = dL_dmean2D + 3 * (size_t)gid + 1; break;
+                    case 2: dst = dL_dconic + 4 * (size_t)gid; break;
+                    case 3: dst = dL_dconic + 4 * (size_t)gid + 1; break;
+                    case 4: dst = dL_dconic + 4 * (size_t)gid + 3; break;
+                    case 5: dst = dL_dopacity + gid; break;
+                    default: dst = dL_dcolors + (size_t)gid * C + (k - 6); break;
+                }
+                atomicAdd(dst, red);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+struct PackedView {
+    float4* lo;
+    float4* hi;
+    float4* col;
+};
+
+static PackedView packed_view(const BinningLayout& b) { return PackedView{b.pk_lo, b.pk_hi, b.pk_col}; }
+
+int launch_finalize_sorted(int channels, int64_t n, const uint64_t* keys_sorted, const uint32_t* point_list,
+                           const GeomLayout& g, const BinningLayout& b, uint2* ranges, size_t tiles, cudaStream_t s) {
+    if (int e = check_cuda(cudaMemsetAsync(ranges, 0, tiles * sizeof(uint2), s), "memset ranges")) return e;
+    if (n <= 0) return HGS_OK;
+    StageScope prof(HGS_STAGE_TILE_RANGES, s);
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (color_stride(channels) == 4)
+        finalize_sorted_kernel<4><<<nb, 256, 0, s>>>((uint32_t)n, keys_sorted, point_list, g.rec, g.rgb, ranges, b.pk_lo,
+                                                     b.pk_hi, b.pk_col);
+    else
+        finalize_sorted_kernel<8><<<nb, 256, 0, s>>>((uint32_t)n, keys_sorted, point_list, g.rec, g.rgb, ranges, b.pk_lo,
+                                                     b.pk_hi, b.pk_col);
+    return check_cuda(cudaGetLastError(), "finalize_sorted launch");
+}
+
+template <int C>
+static int launch_fwd_c(const ImageLayout& im, const BinningLayout& b, int W, int H, const float* bg, float* out_color,
+                        cudaStream_t s) {
+    dim3 grid((W + HGS_TILE - 1) / HGS_TILE, (H + HGS_TILE - 1) / HGS_TILE);
+    constexpr int CS = (C <= 4) ? 4 : 8;
+    const PackedView p = packed_view(b);
+    StageScope prof(HGS_STAGE_COMPOSITE_FWD, s);
+    composite_fwd_kernel<C, CS><<<grid, 256, 0, s>>>(im.ranges, W, H, p.lo, p.hi, p.col, bg, im.final_T, im.n_contrib,
+                                                      out_color);
+    return check_cuda(cudaGetLastError(), "composite_fwd launch");
+}
+
+int launch_composite_fwd(int channels, const ImageLayout& im, const BinningLayout& b, int W, int H, const float* bg,
+                         float* out_color, cudaStream_t s) {
+    switch (channels) {
+        case 1: return launch_fwd_c<1>(im, b, W, H, bg, out_color, s);
+        case 2: return launch_fwd_c<2>(im, b, W, H, bg, out_color, s);
+        case 3: return launch_fwd_c<3>(im, b, W, H, bg, out_color, s);
+        case 4: return launch_fwd_c<4>(im, b, W, H, bg, out_color, s);
+        case 5: return launch_fwd_c<5>(im, b, W, H, bg, out_color, s);
+        case 6: return launch_fwd_c<6>(im, b, W, H, bg, out_color, s);
+        case 7: return launch_fwd_c<7>(im, b, W, H, bg, out_color, s);
+        case 8: return launch_fwd_c<8>(im, b, W, H, bg, out_color, s);
+    }
+    set_error("unsupported channel count %d", channels);
+    return HGS_ERR_INVALID;
+}
+
+template <int C>
+static int launch_bwd_c(const ImageLayout& im, const BinningLayout& b, const uint32_t* point_list, int W, int H,
+                        const float* bg, const float* dL_dpix, const hgs_raster_grads* gr, cudaStream_t s) {
+    dim3 grid((W + HGS_TILE - 1) / HGS_TILE, (H + HGS_TILE - 1) / HGS_TILE);
+    constexpr int CS = (C <= 4) ? 4 : 8;
+    const PackedView p = packed_view(b);
+    StageScope prof(HGS_STAGE_COMPOSITE_BWD, s);
+    composite_bwd_kernel<C, CS><<<grid, 256, 0, s>>>(im.ranges, point_list, W, H, bg, p.lo, p.hi, p.col, im.final_T,
+                                                      im.n_contrib, dL_dpix, gr->dL_dmean2D, gr->dL_dconic,
+                                                      gr->dL_dopacity, gr->dL_dcolor);
+    return check_cuda(cudaGetLastError(), "composite_bwd launch");
+}
+
+int launch_composite_bwd(int channels, const ImageLayout& im, const BinningLayout& b, const uint32_t* point_list, int W,
+                         int H, const float* bg, const float* dL_dpix, const hgs_raster_grads* gr, cudaStream_t s) {
+    switch (channels) {
+        case 1: return launch_bwd_c<1>(im, b, point_list, W, H, bg, dL_dpix, gr, s);
+        case 2: return launch_bwd_c<2>(im, b, point_list, W, H, bg, dL_dpix, gr, s);
+        case 3: return launch_bwd_c<3>(im, b, point_list, W, H, bg, dL_dpix, gr, s);
+        case 4: return launch_bwd_c<4>(im, b, point_list, W, H, bg, dL_dpix, gr, s);
+        case 5: return launch_bwd_c<5>(im, b, point_list, W, H, bg, dL_dpix, gr, s);
+        case 6: return launch_bwd_c<6>(im, b, point_list, W, H, bg, dL_dpix, gr, s);
+        case 7: return launch_bwd_c<7>(im, b, point_list, W, H, bg, dL_dpix, gr, s);
+        case 8: return launch_bwd_c<8>(im, b, point_list, W, H, bg, dL_dpix, gr, s);
+    }
+    set_error("unsupported channel count %d", channels);
+    return HGS_ERR_INVALID;
+}
+
+}  // namespace hgs

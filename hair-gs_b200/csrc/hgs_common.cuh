@@ -142,11 +142,14 @@ __host__ __device__ inline SortLayout carve_sort(void* base, int64_t n) {
 struct BinningLayout {
     uint64_t* keys[2];   // ping-pong key buffers; [0] receives the emitted (unsorted) keys
     uint32_t* vals[2];   // ping-pong Gaussian ids
+    float4* pk_lo;       // [N] sorted-order copies of the Gaussian records (x, y, conic.x, conic.y)
+    float4* pk_hi;       // [N] (conic.z, opacity, hx, hy)
+    float4* pk_col;      // [N * cstride/4] colours in sorted order
     void* sort_ws;
     size_t bytes;
 };
 
-__host__ __device__ inline BinningLayout carve_binning(void* base, int64_t n) {
+__host__ __device__ inline BinningLayout carve_binning(void* base, int64_t n, int channels) {
     BinningLayout b;
     char* p = (char*)base;
     size_t off = 0;
@@ -155,6 +158,9 @@ __host__ __device__ inline BinningLayout carve_binning(void* base, int64_t n) {
     b.keys[1] = (uint64_t*)(p + off); off = align_up(off + nz * 8);
     b.vals[0] = (uint32_t*)(p + off); off = align_up(off + nz * 4);
     b.vals[1] = (uint32_t*)(p + off); off = align_up(off + nz * 4);
+    b.pk_lo = (float4*)(p + off);     off = align_up(off + nz * 16);
+    b.pk_hi = (float4*)(p + off);     off = align_up(off + nz * 16);
+    b.pk_col = (float4*)(p + off);    off = align_up(off + nz * 4 * color_stride(channels));
     b.sort_ws = (void*)(p + off);
     SortLayout s = carve_sort(b.sort_ws, n);
     off = align_up(off + s.bytes);

@@ -72,7 +72,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         if int(hdr[2]) != 0 or int(hdr[0]) < 0:
             raise L.HgsError("instance count overflows int32")
         N = int(hdr[0])
-        binning = torch.empty((lib.hgs_binning_bytes(N),), **u8)
+        binning = torch.empty((lib.hgs_binning_bytes(N, C),), **u8)
         L.check(lib.hgs_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
                                         binning.data_ptr() if N > 0 else None, img.data_ptr(), N, radii.data_ptr(),
                                         out_color.data_ptr(), stream), "forward stage B")

@@ -58,7 +58,7 @@ def load():
     lib.hgs_image_bytes.restype = c_size_t
     lib.hgs_image_bytes.argtypes = [c_int32, c_int32]
     lib.hgs_binning_bytes.restype = c_size_t
-    lib.hgs_binning_bytes.argtypes = [c_int64]
+    lib.hgs_binning_bytes.argtypes = [c_int64, c_int32]
     lib.hgs_sort_bytes.restype = c_size_t
     lib.hgs_sort_bytes.argtypes = [c_int64]
     lib.hgs_knn_bytes.restype = c_size_t
@@ -85,6 +85,12 @@ def load():
     lib.hgs_state_view.restype = c_int64
     lib.hgs_state_view.argtypes = [c_int, P(RasterParams), P(RasterInputs), c_int64, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p]
+    lib.hgs_profile_enable.restype = c_int
+    lib.hgs_profile_enable.argtypes = [c_int]
+    lib.hgs_profile_collect.restype = c_int
+    lib.hgs_profile_collect.argtypes = [c_void_p, c_void_p]
+    lib.hgs_stage_name.restype = c_char_p
+    lib.hgs_stage_name.argtypes = [c_int]
     if lib.hgs_abi_version() != 1:
         raise ImportError("libhairgs_rast.so ABI version mismatch; rebuild")
     _lib = lib

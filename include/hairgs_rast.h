@@ -99,7 +99,7 @@ const char* hgs_last_error(void);
 /* Workspace sizes in bytes (required<T>() of the reference).  binning: N = num_rendered. */
 size_t hgs_geom_bytes(int32_t P, int32_t channels);
 size_t hgs_image_bytes(int32_t width, int32_t height);
-size_t hgs_binning_bytes(int64_t num_rendered);
+size_t hgs_binning_bytes(int64_t num_rendered, int32_t channels);
 
 /* Whole forward pass, reference call shape: allocates through the three callbacks, blocks once on
  * the instance count exactly like rasterizer_impl.cu:281, returns num_rendered (>= 0) or an error.

@@ -40,8 +40,8 @@ def test_workspace_size_queries():
     a, b = lib.hgs_geom_bytes(1000, 3), lib.hgs_geom_bytes(2000, 3)
     assert b > a and lib.hgs_geom_bytes(1000, 7) > a
     assert lib.hgs_image_bytes(1024, 1024) >= 1024 * 1024 * 8 + 4096 * 8
-    assert lib.hgs_binning_bytes(1 << 20) >= (1 << 20) * 24
-    assert lib.hgs_binning_bytes(0) >= 0 and lib.hgs_sort_bytes(10) > 0 and lib.hgs_knn_bytes(100) > 0
+    assert lib.hgs_binning_bytes(1 << 20, 3) >= (1 << 20) * 72
+    assert lib.hgs_binning_bytes(0, 3) >= 0 and lib.hgs_sort_bytes(10) > 0 and lib.hgs_knn_bytes(100) > 0
 
 
 def test_argument_validation_without_gpu():
