@@ -67,10 +67,11 @@ int launch_view_geom(int, const hgs_raster_params*, const hgs_raster_inputs*, co
 int launch_emit_keys(int, const GeomLayout&, const uint2*, uint64_t*, uint32_t*, uint32_t, uint32_t, cudaStream_t);
 int launch_sort_pairs(int64_t, int, uint64_t* [2], uint32_t* [2], void*, int*, cudaStream_t);
 int launch_finalize_sorted(int, int64_t, const uint64_t*, const uint32_t*, const GeomLayout&, const BinningLayout&, uint2*,
-                           size_t, cudaStream_t);
+                           uint32_t*, size_t, cudaStream_t);
 int launch_composite_fwd(int, const ImageLayout&, const BinningLayout&, int, int, const float*, float*, cudaStream_t);
 int launch_composite_bwd(int, const ImageLayout&, const BinningLayout&, const uint32_t*, int, int, const float*,
                          const float*, const hgs_raster_grads*, cudaStream_t);
+int set_fwd_stats(void* dev_ptr);
 size_t knn_bytes(int P);
 int launch_knn(int P, const float* points, float* out, void* ws, cudaStream_t s);
 
@@ -103,6 +104,8 @@ static inline int end_bit_for(const hgs_raster_params* prm) {
 using namespace hgs;
 
 extern "C" {
+
+int hgs_debug_set_stats(void* dev_ptr) { return set_fwd_stats(dev_ptr); }
 
 int hgs_profile_enable(int on) {
     g_prof_on = on != 0;
@@ -175,7 +178,7 @@ int hgs_forward_stage_b(const hgs_raster_params* prm, const hgs_raster_inputs* i
     int res = 0;
     if (int e = launch_sort_pairs(N, end_bit_for(prm), b.keys, b.vals, b.sort_ws, &res, s)) return e;
     if (int e = stage_check("sort", prm->debug, s)) return e;
-    if (int e = launch_finalize_sorted(prm->channels, N, b.keys[res], b.vals[res], g, b, im.ranges, (size_t)gx * gy, s)) return e;
+    if (int e = launch_finalize_sorted(prm->channels, N, b.keys[res], b.vals[res], g, b, im.ranges, im.tile_order, (size_t)gx * gy, s)) return e;
     if (int e = stage_check("finalize_sorted", prm->debug, s)) return e;
     if (int e = launch_composite_fwd(prm->channels, im, b, prm->width, prm->height, in->background, out_color, s)) return e;
     return stage_check("composite_fwd", prm->debug, s);

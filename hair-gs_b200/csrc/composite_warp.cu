@@ -24,6 +24,14 @@
 
 namespace hgs {
 
+// optional per-(tile,warp) work statistics of the forward compositor (debug; set through hgs_debug_set_stats)
+__device__ uint4* g_fwd_stats = nullptr;
+
+int set_fwd_stats(void* dev_ptr) {
+    uint4* p = (uint4*)dev_ptr;
+    return check_cuda(cudaMemcpyToSymbol(g_fwd_stats, &p, sizeof(p)), "set stats pointer");
+}
+
 // ------------------------------------------------------------------------------------------------
 // finalize: tile ranges + sorted-order packing
 // ------------------------------------------------------------------------------------------------
@@ -58,8 +66,39 @@ __global__ void __launch_bounds__(256) finalize_sorted_kernel(uint32_t L, const 
     if (idx == L - 1) ranges[cur].y = L;
 }
 
+// Longest-list-first processing order of the tiles (bucketed by floor(log2(length))): the block scheduler hands
+// out CTAs in index order, so the few tiles with thousands of instances start first and the tail of the grid is
+// made of cheap tiles (profiles/r1_composite.md: SM active cycles min/avg/max 112k/319k/575k without it).
+__global__ void __launch_bounds__(1024) tile_order_kernel(uint32_t tiles, const uint2* __restrict__ ranges,
+                                                          uint32_t* __restrict__ order) {
+    __shared__ uint32_t s_count[33];
+    __shared__ uint32_t s_offset[33];
+    if (threadIdx.x < 33) s_count[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < tiles; t += blockDim.x) {
+        const uint2 r = ranges[t];
+        const uint32_t len = r.y - r.x;
+        atomicAdd(&s_count[len ? __clz(len) : 32], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int b = 0; b < 33; ++b) {
+            s_offset[b] = run;
+            run += s_count[b];
+        }
+    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < tiles; t += blockDim.x) {
+        const uint2 r = ranges[t];
+        const uint32_t len = r.y - r.x;
+        order[atomicAdd(&s_offset[len ? __clz(len) : 32], 1u)] = t;
+    }
+}
+
 template <int C, int CS>
-__global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restrict__ ranges, int W, int H,
+__global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restrict__ ranges,
+                                                            const uint32_t* __restrict__ tile_order, int W, int H,
                                                             const float4* __restrict__ pk_lo,
                                                             const float4* __restrict__ pk_hi,
                                                             const float4* __restrict__ pk_col,
@@ -73,7 +112,8 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restr
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t horizontal_blocks = (W + HGS_TILE - 1) / HGS_TILE;
-    const uint32_t X0 = blockIdx.x * HGS_TILE, Y0 = blockIdx.y * HGS_TILE;
+    const uint32_t tile = tile_order[blockIdx.x];
+    const uint32_t X0 = (tile % horizontal_blocks) * HGS_TILE, Y0 = (tile / horizontal_blocks) * HGS_TILE;
     const uint32_t bx = X0 + (warp & 1) * 8, by = Y0 + (warp >> 1) * 4;
     const uint32_t px = bx + (lane & 7), py = by + (lane >> 3);
     const uint32_t pix_id = W * py + px;
@@ -82,7 +122,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restr
     bool done = !inside;
     const float wx0 = (float)bx, wx1 = (float)(bx + 7), wy0 = (float)by, wy1 = (float)(by + 3);
 
-    const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
+    const uint2 range = ranges[tile];
     const int total = (int)(range.y - range.x);
     const int nchunks = (total + 31) >> 5;
 
@@ -91,6 +131,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restr
     float Cacc[C];
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) Cacc[ch] = 0.f;
+    uint32_t st_chunks = 0, st_cand = 0, st_blend = 0;
 
     if (!__all_sync(0xffffffffu, done) && nchunks > 0) {
         float4 nlo = make_float4(0, 0, 0, 0), nhi = make_float4(0, 0, 0, 0), nc0 = make_float4(0, 0, 0, 0),
@@ -118,6 +159,8 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restr
             // culled only when a comparison is TRUE, so NaNs keep the instance (the reference would evaluate it)
             const bool cand = have && !(lo.x - hi.z > wx1 || lo.x + hi.z < wx0 || lo.y - hi.w > wy1 || lo.y + hi.w < wy0);
             uint32_t bits = __ballot_sync(0xffffffffu, cand);
+            st_chunks++;
+            st_cand += __popc(bits);
             if (bits) {
                 if (cand) {
                     s_lo[warp][lane] = lo;
@@ -148,6 +191,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restr
                     for (int ch = 0; ch < C; ++ch) Cacc[ch] += col[ch] * alpha * T;
                     T = test_T;
                     last_contributor = pos_base + (uint32_t)j;
+                    st_blend++;
                 }
                 __syncwarp();
                 if (__all_sync(0xffffffffu, done)) break;
@@ -160,6 +204,12 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restr
         n_contrib[pix_id] = last_contributor;
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) out_color[(size_t)ch * H * W + pix_id] = Cacc[ch] + T * bg_color[ch];
+    }
+    if (g_fwd_stats != nullptr) {
+        st_blend = __reduce_add_sync(0xffffffffu, st_blend);
+        const uint32_t ndone = __popc(__ballot_sync(0xffffffffu, done && inside));
+        if (lane == 0)
+            g_fwd_stats[tile * 8 + warp] = make_uint4(st_chunks, st_cand, st_blend, ndone | ((uint32_t)nchunks << 8));
     }
 }
 
@@ -234,22 +284,49 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[VP], uint32_t 
 }
 
 
+// Backward compositor.  Per warp (8x4 pixels), back to front over the tile list:
+//   1. chunks of 32 instances are culled against the warp's pixel block exactly like the forward; surviving
+//      instances are COMPACTED into a small per-warp queue (shared memory ring), list order preserved;
+//   2. whenever 8 candidates are queued:
+//      phase 1 (lanes = pixels): the per-pixel recurrence of backward_distwar.cu:855-1014 runs over the 8 candidates
+//               in order; each contributing pixel parks (G, dL/dalpha, alpha*T) for (candidate, pixel) in a slab;
+//      phase 2 (lanes = candidate x pixel-quarter): every lane sums ITS candidate's nine gradient terms over the
+//               contributing pixels of its quarter in registers, two shuffle levels fold the four quarters, and
+//               one lane per candidate issues the red.global.adds.
+//      Compared with reducing every candidate across the 32 pixel lanes (16 shuffles + ~50 ALU ops each), this
+//      cuts the instruction count per candidate roughly in half and the atomics per warp 4x
+//      (profiles/r1_composite.md).
+template <int CS>
+struct BwdWarpSmem {
+    static constexpr int QN = 64;  // candidate queue capacity (32 new + < 8 left over), power of two
+    static constexpr int GR = 8;   // candidates per group
+    float4 q_lo[QN];
+    float4 q_hi[QN];
+    float4 q_col[QN * (CS / 4)];
+    uint2 q_ip[QN];                // (Gaussian id, list position)
+    float4 slab[GR * 33];          // [candidate][pixel] (G, dL/dalpha, alpha*T, -), row stride 33 -> conflict-free
+    float4 dpix[32 * (CS / 4)];    // dL/dpixel of the warp's 32 pixels
+    uint32_t vmask[GR];            // which pixels contributed to each candidate
+};
+
 template <int C, int CS>
 __global__ void __launch_bounds__(256) composite_bwd_kernel(
-    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
+    const uint32_t* __restrict__ point_list, int W, int H,
     const float* __restrict__ bg_color, const float4* __restrict__ pk_lo, const float4* __restrict__ pk_hi,
     const float4* __restrict__ pk_col, const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
     const float* __restrict__ dL_dpixels, float* __restrict__ dL_dmean2D /*[P,3]*/,
     float* __restrict__ dL_dconic /*[P,4]*/, float* __restrict__ dL_dopacity /*[P]*/,
     float* __restrict__ dL_dcolors /*[P,C]*/) {
-    __shared__ float4 s_lo[8][32];
-    __shared__ float4 s_hi[8][32];
-    __shared__ float4 s_col[8][32 * (CS / 4)];
-    __shared__ uint32_t s_id[8][32];
-
+    using WS = BwdWarpSmem<CS>;
+    constexpr int QN = WS::QN, GR = WS::GR;
+    extern __shared__ __align__(16) unsigned char bwd_smem_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WS& ws = reinterpret_cast<WS*>(bwd_smem_raw)[warp];
+
     const uint32_t horizontal_blocks = (W + HGS_TILE - 1) / HGS_TILE;
-    const uint32_t X0 = blockIdx.x * HGS_TILE, Y0 = blockIdx.y * HGS_TILE;
+    const uint32_t tile = tile_order[blockIdx.x];
+    const uint32_t X0 = (tile % horizontal_blocks) * HGS_TILE, Y0 = (tile / horizontal_blocks) * HGS_TILE;
     const uint32_t bx = X0 + (warp & 1) * 8, by = Y0 + (warp >> 1) * 4;
     const uint32_t px = bx + (lane & 7), py = by + (lane >> 3);
     const uint32_t pix_id = W * py + px;
@@ -257,7 +334,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
     const float wx0 = (float)bx, wx1 = (float)(bx + 7), wy0 = (float)by, wy1 = (float)(by + 3);
 
-    const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
+    const uint2 range = ranges[tile];
 
     const float T_final = inside ? final_Ts[pix_id] : 0;
     float T = T_final;
@@ -277,12 +354,109 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
         last_color[ch] = 0.f;
         dL_dpixel[ch] = inside ? dL_dpixels[(size_t)ch * H * W + pix_id] : 0.f;
     }
+    {
+        float tmp[8];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) tmp[ch] = ch < C ? dL_dpixel[ch] : 0.f;
+        ws.dpix[lane * (CS / 4)] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+        if (CS > 4) ws.dpix[lane * (CS / 4) + 1] = make_float4(tmp[4], tmp[5], tmp[6], tmp[7]);
+    }
     float last_alpha = 0.f;
     float bg_dot_dpixel = 0;
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) bg_dot_dpixel += bg_color[ch] * dL_dpixel[ch];
     const float ddelx_dx = 0.5 * W;
     const float ddely_dy = 0.5 * H;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    // phase-2 role of this lane
+    const uint32_t my_g = lane & 7, my_q = lane >> 3;
+
+    uint32_t qhead = 0, qcount = 0;
+
+    auto process_group = [&](const uint32_t n) {
+        // ---- phase 1: lanes = pixels, candidates in list order ------------------------------------------
+        for (uint32_t g = 0; g < n; ++g) {
+            const uint32_t slot = (qhead + g) & (QN - 1);
+            const float4 glo = ws.q_lo[slot];
+            const float4 ghi = ws.q_hi[slot];
+            const int pos = (int)ws.q_ip[slot].y;
+            bool valid = pos < last_contributor;  // false for outside pixels (last_contributor == 0)
+            const float2 d = make_float2(glo.x - pixf.x, glo.y - pixf.y);
+            const float power = -0.5f * (glo.z * d.x * d.x + ghi.x * d.y * d.y) - glo.w * d.x * d.y;
+            if (power > 0.0f) valid = false;
+            const float G = exp(power);
+            const float alpha = min(0.99f, ghi.y * G);
+            if (alpha < 1.0f / 255.0f) valid = false;
+            const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0) ws.vmask[g] = vm;
+            if (valid) {
+                T = T / (1.f - alpha);
+                const float dchannel_dcolor = alpha * T;
+                float dL_dalpha = 0.0f;
+                const float* col = reinterpret_cast<const float*>(&ws.q_col[slot * (CS / 4)]);
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    const float cc = col[ch];
+                    accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+                    last_color[ch] = cc;
+                    dL_dalpha += (cc - accum_rec[ch]) * dL_dpixel[ch];
+                }
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                ws.slab[g * 33 + lane] = make_float4(G, dL_dalpha, dchannel_dcolor, 0.f);
+            }
+        }
+        __syncwarp();
+        // ---- phase 2: lanes = (candidate my_g, pixel quarter my_q) ---------------------------------------
+        float acc[6 + C];
+#pragma unroll
+        for (int k = 0; k < 6 + C; ++k) acc[k] = 0.f;
+        uint32_t my_vm = 0;
+        const uint32_t slot = (qhead + my_g) & (QN - 1);
+        if (my_g < n) {
+            my_vm = ws.vmask[my_g];
+            uint32_t m = (my_vm >> (my_q * 8)) & 0xffu;
+            if (m) {
+                const float4 glo = ws.q_lo[slot];
+                const float4 ghi = ws.q_hi[slot];
+                while (m) {
+                    const uint32_t p = my_q * 8 + (uint32_t)__ffs(m) - 1u;
+                    m &= m - 1;
+                    const float4 r = ws.slab[my_g * 33 + p];  // (G, dL_dalpha, alpha*T)
+                    const float dx = glo.x - (wx0 + (float)(p & 7)), dy = glo.y - (wy0 + (float)(p >> 3));
+                    const float dL_dG = ghi.y * r.y;
+                    const float gdx = r.x * dx, gdy = r.x * dy;
+                    acc[0] += dL_dG * (-gdx * glo.z - gdy * glo.w);
+                    acc[1] += dL_dG * (-gdy * ghi.x - gdx * glo.w);
+                    acc[2] += gdx * dx * dL_dG;
+                    acc[3] += gdx * dy * dL_dG;
+                    acc[4] += gdy * dy * dL_dG;
+                    acc[5] += r.x * r.y;
+                    const float* dp = reinterpret_cast<const float*>(&ws.dpix[p * (CS / 4)]);
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) acc[6 + ch] += r.z * dp[ch];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6 + C; ++k) {
+            acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
+            acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+        }
+        if (my_q == 0 && my_vm != 0) {
+            const uint32_t gid = ws.q_ip[slot].x;
+            atomicAdd(dL_dmean2D + 3 * (size_t)gid, acc[0] * ddelx_dx);
+            atomicAdd(dL_dmean2D + 3 * (size_t)gid + 1, acc[1] * ddely_dy);
+            atomicAdd(dL_dconic + 4 * (size_t)gid, -0.5f * acc[2]);
+            atomicAdd(dL_dconic + 4 * (size_t)gid + 1, -0.5f * acc[3]);
+            atomicAdd(dL_dconic + 4 * (size_t)gid + 3, -0.5f * acc[4]);
+            atomicAdd(dL_dopacity + gid, acc[5]);
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) atomicAdd(dL_dcolors + (size_t)gid * C + ch, acc[6 + ch]);
+        }
+        __syncwarp();
+    };
 
     // back to front: lane l of chunk c holds list position total-1-(c*32+l)
     float4 nlo = make_float4(0, 0, 0, 0), nhi = make_float4(0, 0, 0, 0), nc0 = make_float4(0, 0, 0, 0),
@@ -299,13 +473,14 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
             nid = point_list[i];
         }
     }
+    __syncwarp();
     for (int c = 0; c < nchunks; ++c) {
         const float4 lo = nlo, hi = nhi, c0 = nc0, c1 = nc1;
         const uint32_t id = nid;
-        const int pos_first = total - 1 - c * 32;  // list position held by lane 0
-        const bool have = pos_first - (int)lane >= 0;
+        const int my_pos = total - 1 - c * 32 - (int)lane;
+        const bool have = my_pos >= 0;
         if (c + 1 < nchunks) {
-            const int pos = pos_first - 32 - (int)lane;
+            const int pos = my_pos - 32;
             if (pos >= 0) {
                 const size_t i = (size_t)range.x + pos;
                 nlo = pk_lo[i];
@@ -316,85 +491,25 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
             }
         }
         const bool cand = have && !(lo.x - hi.z > wx1 || lo.x + hi.z < wx0 || lo.y - hi.w > wy1 || lo.y + hi.w < wy0);
-        uint32_t bits = __ballot_sync(0xffffffffu, cand);
+        const uint32_t bits = __ballot_sync(0xffffffffu, cand);
         if (!bits) continue;
         if (cand) {
-            s_lo[warp][lane] = lo;
-            s_hi[warp][lane] = hi;
-            s_col[warp][lane * (CS / 4)] = c0;
-            if (CS > 4) s_col[warp][lane * (CS / 4) + 1] = c1;
-            s_id[warp][lane] = id;
+            const uint32_t slot = (qhead + qcount + __popc(bits & lt_mask)) & (QN - 1);
+            ws.q_lo[slot] = lo;
+            ws.q_hi[slot] = hi;
+            ws.q_col[slot * (CS / 4)] = c0;
+            if (CS > 4) ws.q_col[slot * (CS / 4) + 1] = c1;
+            ws.q_ip[slot] = make_uint2(id, (uint32_t)my_pos);
         }
+        qcount += __popc(bits);
         __syncwarp();
-        while (bits) {
-            const int j = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const int pos = pos_first - j;
-            bool valid = pos < last_contributor;  // false for outside pixels (last_contributor == 0)
-            const float4 glo = s_lo[warp][j];
-            const float4 ghi = s_hi[warp][j];
-            const float2 d = make_float2(glo.x - pixf.x, glo.y - pixf.y);
-            const float power = -0.5f * (glo.z * d.x * d.x + ghi.x * d.y * d.y) - glo.w * d.x * d.y;
-            if (power > 0.0f) valid = false;
-            const float G = exp(power);
-            const float alpha = min(0.99f, ghi.y * G);
-            if (alpha < 1.0f / 255.0f) valid = false;
-            if (!__any_sync(0xffffffffu, valid)) continue;
-
-            constexpr int V = 6 + C;
-            constexpr int VP = (V <= 8) ? 8 : 16;
-            float v[VP];
-#pragma unroll
-            for (int k = 0; k < VP; ++k) v[k] = 0.f;
-            if (valid) {
-                T = T / (1.f - alpha);
-                const float dchannel_dcolor = alpha * T;
-                float dL_dalpha = 0.0f;
-                const float* col = reinterpret_cast<const float*>(&s_col[warp][j * (CS / 4)]);
-#pragma unroll
-                for (int ch = 0; ch < C; ++ch) {
-                    const float cc = col[ch];
-                    accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-                    last_color[ch] = cc;
-                    const float dL_dchannel = dL_dpixel[ch];
-                    dL_dalpha += (cc - accum_rec[ch]) * dL_dchannel;
-                    v[6 + ch] = dchannel_dcolor * dL_dchannel;
-                }
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-                const float dL_dG = ghi.y * dL_dalpha;
-                const float gdx = G * d.x;
-                const float gdy = G * d.y;
-                const float dG_ddelx = -gdx * glo.z - gdy * glo.w;
-                const float dG_ddely = -gdy * ghi.x - gdx * glo.w;
-                v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                v[1] = dL_dG * dG_ddely * ddely_dy;
-                v[2] = -0.5f * gdx * d.x * dL_dG;
-                v[3] = -0.5f * gdx * d.y * dL_dG;
-                v[4] = -0.5f * gdy * d.y * dL_dG;
-                v[5] = G * dL_dalpha;
-            }
-            const float red = warp_transpose_reduce<VP>(v, lane);
-            const uint32_t gid = s_id[warp][j];
-            const int k = (VP == 8) ? (int)(lane >> 2) : (int)(lane >> 1);
-            const bool writer = (VP == 8) ? ((lane & 3) == 0) : ((lane & 1) == 0);
-            if (writer && k < V) {
-                float* dst;
-                switch (k) {
-                    case 0: dst = dL_dmean2D + 3 * (size_t)gid; break;
-                    case 1: dst = dL_dmean2D + 3 * (size_t)gid + 1; break;
-                    case 2: dst = dL_dconic + 4 * (size_t)gid; break;
-                    case 3: dst = dL_dconic + 4 * (size_t)gid + 1; break;
-                    case 4: dst = dL_dconic + 4 * (size_t)gid + 3; break;
-                    case 5: dst = dL_dopacity + gid; break;
-                    default: dst = dL_dcolors + (size_t)gid * C + (k - 6); break;
-                }
-                atomicAdd(dst, red);
-            }
+        while (qcount >= (uint32_t)GR) {
+            process_group(GR);
+            qhead = (qhead + GR) & (QN - 1);
+            qcount -= GR;
         }
-        __syncwarp();
     }
+    if (qcount > 0) process_group(qcount);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -409,10 +524,14 @@ struct PackedView {
 static PackedView packed_view(const BinningLayout& b) { return PackedView{b.pk_lo, b.pk_hi, b.pk_col}; }
 
 int launch_finalize_sorted(int channels, int64_t n, const uint64_t* keys_sorted, const uint32_t* point_list,
-                           const GeomLayout& g, const BinningLayout& b, uint2* ranges, size_t tiles, cudaStream_t s) {
+                           const GeomLayout& g, const BinningLayout& b, uint2* ranges, uint32_t* tile_order, size_t tiles,
+                           cudaStream_t s) {
     if (int e = check_cuda(cudaMemsetAsync(ranges, 0, tiles * sizeof(uint2), s), "memset ranges")) return e;
-    if (n <= 0) return HGS_OK;
     StageScope prof(HGS_STAGE_TILE_RANGES, s);
+    if (n <= 0) {
+        tile_order_kernel<<<1, 1024, 0, s>>>((uint32_t)tiles, ranges, tile_order);
+        return check_cuda(cudaGetLastError(), "tile_order launch");
+    }
     const unsigned nb = (unsigned)((n + 255) / 256);
     if (color_stride(channels) == 4)
         finalize_sorted_kernel<4><<<nb, 256, 0, s>>>((uint32_t)n, keys_sorted, point_list, g.rec, g.rgb, ranges, b.pk_lo,
@@ -420,17 +539,18 @@ int launch_finalize_sorted(int channels, int64_t n, const uint64_t* keys_sorted,
     else
         finalize_sorted_kernel<8><<<nb, 256, 0, s>>>((uint32_t)n, keys_sorted, point_list, g.rec, g.rgb, ranges, b.pk_lo,
                                                      b.pk_hi, b.pk_col);
+    tile_order_kernel<<<1, 1024, 0, s>>>((uint32_t)tiles, ranges, tile_order);
     return check_cuda(cudaGetLastError(), "finalize_sorted launch");
 }
 
 template <int C>
 static int launch_fwd_c(const ImageLayout& im, const BinningLayout& b, int W, int H, const float* bg, float* out_color,
                         cudaStream_t s) {
-    dim3 grid((W + HGS_TILE - 1) / HGS_TILE, (H + HGS_TILE - 1) / HGS_TILE);
+    const unsigned grid = (unsigned)(((W + HGS_TILE - 1) / HGS_TILE) * ((H + HGS_TILE - 1) / HGS_TILE));
     constexpr int CS = (C <= 4) ? 4 : 8;
     const PackedView p = packed_view(b);
     StageScope prof(HGS_STAGE_COMPOSITE_FWD, s);
-    composite_fwd_kernel<C, CS><<<grid, 256, 0, s>>>(im.ranges, W, H, p.lo, p.hi, p.col, bg, im.final_T, im.n_contrib,
+    composite_fwd_kernel<C, CS><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col, bg, im.final_T, im.n_contrib,
                                                       out_color);
     return check_cuda(cudaGetLastError(), "composite_fwd launch");
 }
@@ -454,11 +574,18 @@ int launch_composite_fwd(int channels, const ImageLayout& im, const BinningLayou
 template <int C>
 static int launch_bwd_c(const ImageLayout& im, const BinningLayout& b, const uint32_t* point_list, int W, int H,
                         const float* bg, const float* dL_dpix, const hgs_raster_grads* gr, cudaStream_t s) {
-    dim3 grid((W + HGS_TILE - 1) / HGS_TILE, (H + HGS_TILE - 1) / HGS_TILE);
+    const unsigned grid = (unsigned)(((W + HGS_TILE - 1) / HGS_TILE) * ((H + HGS_TILE - 1) / HGS_TILE));
     constexpr int CS = (C <= 4) ? 4 : 8;
     const PackedView p = packed_view(b);
+    const size_t smem = 8 * sizeof(BwdWarpSmem<CS>);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (int e = check_cuda(cudaFuncSetAttribute(composite_bwd_kernel<C, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)smem), "composite_bwd smem attr")) return e;
+        attr_set = true;
+    }
     StageScope prof(HGS_STAGE_COMPOSITE_BWD, s);
-    composite_bwd_kernel<C, CS><<<grid, 256, 0, s>>>(im.ranges, point_list, W, H, bg, p.lo, p.hi, p.col, im.final_T,
+    composite_bwd_kernel<C, CS><<<grid, 256, smem, s>>>(im.ranges, im.tile_order, point_list, W, H, bg, p.lo, p.hi, p.col, im.final_T,
                                                       im.n_contrib, dL_dpix, gr->dL_dmean2D, gr->dL_dconic,
                                                       gr->dL_dopacity, gr->dL_dcolor);
     return check_cuda(cudaGetLastError(), "composite_bwd launch");

@@ -94,6 +94,7 @@ struct ImageLayout {
     float* final_T;        // [H*W]
     uint32_t* n_contrib;   // [H*W]
     uint2* ranges;         // [tiles]  (the reference over-allocates H*W entries, rasterizer_impl.cu:172-178)
+    uint32_t* tile_order;  // [tiles]  tile ids, longest list first (CTA i composites tile_order[i])
     size_t bytes;
 };
 
@@ -106,6 +107,7 @@ __host__ __device__ inline ImageLayout carve_image(void* base, int W, int H) {
     im.final_T = (float*)(p + off);      off = align_up(off + hw * 4);
     im.n_contrib = (uint32_t*)(p + off); off = align_up(off + hw * 4);
     im.ranges = (uint2*)(p + off);       off = align_up(off + tiles * 8);
+    im.tile_order = (uint32_t*)(p + off); off = align_up(off + tiles * 4);
     im.bytes = off;
     return im;
 }

@@ -187,6 +187,9 @@ enum hgs_stage {
     HGS_STAGE_OTHER = 9,
     HGS_STAGE_COUNT = 10
 };
+/* Debug: when dev_ptr != NULL the forward compositor writes one uint4 per (tile, warp):
+ * (chunks walked, cull candidates, blends summed over lanes, pixels terminated | list chunks << 8). */
+int hgs_debug_set_stats(void* dev_ptr);
 int hgs_profile_enable(int on);
 int hgs_profile_collect(double* ms, int64_t* launches);
 const char* hgs_stage_name(int stage);
