@@ -65,8 +65,9 @@ int launch_preprocess_bwd(const hgs_raster_params*, const hgs_raster_inputs*, co
 int launch_mark_visible(int, const float*, const float*, uint8_t*, cudaStream_t);
 int launch_view_geom(int, const hgs_raster_params*, const hgs_raster_inputs*, const GeomLayout&, void*, cudaStream_t);
 int launch_emit_keys(int, const GeomLayout&, const uint2*, uint64_t*, uint32_t*, uint32_t, uint32_t, cudaStream_t);
-int launch_sort_pairs(int64_t, int, uint64_t* [2], uint32_t* [2], void*, int*, cudaStream_t);
-int launch_finalize_sorted(int, int64_t, const uint64_t*, const uint32_t*, const GeomLayout&, const BinningLayout&, uint2*,
+int launch_sort_pairs(int64_t, const uint32_t*, int, uint64_t* [2], uint32_t* [2], void*, int*, cudaStream_t);
+int launch_finalize_sorted(int, int64_t, const uint32_t*, const uint64_t*, const uint32_t*, const GeomLayout&,
+                           const BinningLayout&, uint2*,
                            uint32_t*, size_t, cudaStream_t);
 int launch_composite_fwd(int, const ImageLayout&, const BinningLayout&, int, int, const float*, float*, cudaStream_t);
 int launch_composite_bwd(int, const ImageLayout&, const BinningLayout&, const uint32_t*, int, int, const float*,
@@ -143,6 +144,20 @@ size_t hgs_image_bytes(int32_t width, int32_t height) { return carve_image(nullp
 size_t hgs_binning_bytes(int64_t n, int32_t channels) { return carve_binning(nullptr, n, channels).bytes; }
 size_t hgs_sort_bytes(int64_t n) { return carve_sort(nullptr, n).bytes; }
 
+// Inverse of hgs_binning_bytes for the two ways a binning workspace gets sized: exactly num_rendered
+// (reference-style, after the blocking read-back) or a capacity that is a multiple of 4096 (sync-free mode).
+int64_t hgs_binning_capacity(size_t bytes, int32_t channels, int64_t num_rendered) {
+    if (num_rendered >= 0 && carve_binning(nullptr, num_rendered, channels).bytes == bytes) return num_rendered;
+    int64_t lo = 0, hi = (int64_t)1 << 19;  // in units of 4096 instances (2^31 total)
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) / 2;
+        if (carve_binning(nullptr, mid * 4096, channels).bytes < bytes) lo = mid + 1; else hi = mid;
+    }
+    if (carve_binning(nullptr, lo * 4096, channels).bytes == bytes) return lo * 4096;
+    set_error("binning workspace of %zu bytes matches no capacity", bytes);
+    return HGS_ERR_INVALID;
+}
+
 int hgs_forward_stage_a(const hgs_raster_params* prm, const hgs_raster_inputs* in, void* geom_ws, int32_t* radii,
                         void* stream) {
     if (int e = validate(prm, in)) return e;
@@ -176,9 +191,10 @@ int hgs_forward_stage_b(const hgs_raster_params* prm, const hgs_raster_inputs* i
     if (int e = launch_emit_keys(N > 0 ? prm->P : 0, g, g.rects, b.keys[0], b.vals[0], gx, (uint32_t)N, s)) return e;
     if (int e = stage_check("emit_keys", prm->debug, s)) return e;
     int res = 0;
-    if (int e = launch_sort_pairs(N, end_bit_for(prm), b.keys, b.vals, b.sort_ws, &res, s)) return e;
+    const uint32_t* n_ptr = &g.hdr->num_rendered;  // live instance count stays on the device; N is only the capacity
+    if (int e = launch_sort_pairs(N, n_ptr, end_bit_for(prm), b.keys, b.vals, b.sort_ws, &res, s)) return e;
     if (int e = stage_check("sort", prm->debug, s)) return e;
-    if (int e = launch_finalize_sorted(prm->channels, N, b.keys[res], b.vals[res], g, b, im.ranges, im.tile_order, (size_t)gx * gy, s)) return e;
+    if (int e = launch_finalize_sorted(prm->channels, N, n_ptr, b.keys[res], b.vals[res], g, b, im.ranges, im.tile_order, (size_t)gx * gy, s)) return e;
     if (int e = stage_check("finalize_sorted", prm->debug, s)) return e;
     if (int e = launch_composite_fwd(prm->channels, im, b, prm->width, prm->height, in->background, out_color, s)) return e;
     return stage_check("composite_fwd", prm->debug, s);
@@ -209,6 +225,7 @@ int hgs_rasterize_forward(hgs_alloc_fn geom_alloc, void* geom_user, hgs_alloc_fn
 int hgs_rasterize_backward(const hgs_raster_params* prm, const hgs_raster_inputs* in, int64_t R, const int32_t* radii,
                            const void* geom_ws, const void* binning_ws, const void* image_ws, const float* dL_dpix,
                            const hgs_raster_grads* gr, void* stream) {
+    // R is the CAPACITY the binning workspace was carved with (== num_rendered in the reference-style exact mode)
     if (int e = validate(prm, in, false)) return e;
     cudaStream_t s = (cudaStream_t)stream;
     if (!gr || !gr->dL_dmean2D || !gr->dL_dconic || !gr->dL_dopacity || !gr->dL_dcolor || !gr->dL_dmean3D ||
@@ -266,7 +283,7 @@ int hgs_sort_pairs(int64_t n, int end_bit, uint64_t* keys_in, uint32_t* vals_in,
     uint64_t* keys[2] = {keys_in, keys_out};
     uint32_t* vals[2] = {vals_in, vals_out};
     int res = 0;
-    if (int e = launch_sort_pairs(n, end_bit, keys, vals, workspace, &res, s)) return e;
+    if (int e = launch_sort_pairs(n, nullptr, end_bit, keys, vals, workspace, &res, s)) return e;
     if (res == 0) {
         if (int e = check_cuda(cudaMemcpyAsync(keys_out, keys_in, (size_t)n * 8, cudaMemcpyDeviceToDevice, s), "copy keys")) return e;
         if (int e = check_cuda(cudaMemcpyAsync(vals_out, vals_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, s), "copy vals")) return e;
@@ -274,7 +291,7 @@ int hgs_sort_pairs(int64_t n, int end_bit, uint64_t* keys_in, uint32_t* vals_in,
     return HGS_OK;
 }
 
-int64_t hgs_state_view(int what, const hgs_raster_params* prm, const hgs_raster_inputs* in, int64_t N,
+int64_t hgs_state_view(int what, const hgs_raster_params* prm, const hgs_raster_inputs* in, int64_t N, int64_t capacity,
                        const void* geom_ws, const void* binning_ws, const void* image_ws, void* dst, void* stream) {
     if (!prm || !dst) { set_error("null args"); return HGS_ERR_INVALID; }
     cudaStream_t s = (cudaStream_t)stream;
@@ -305,7 +322,7 @@ int64_t hgs_state_view(int what, const hgs_raster_params* prm, const hgs_raster_
         }
         case HGS_VIEW_KEYS_SORTED: case HGS_VIEW_POINT_LIST: {
             if (N > 0 && !binning_ws) { set_error("null binning workspace"); return HGS_ERR_INVALID; }
-            BinningLayout b = carve_binning((void*)binning_ws, N, prm->channels);
+            BinningLayout b = carve_binning((void*)binning_ws, capacity, prm->channels);
             const int res = sort_passes(end_bit_for(prm)) & 1;
             if (what == HGS_VIEW_KEYS_SORTED) return d2d(b.keys[res], (size_t)N * 8);
             return d2d(b.vals[res], (size_t)N * 4);

@@ -91,8 +91,12 @@ __device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
 }
 
 // One read of the keys, all digit histograms at once.
-__global__ void __launch_bounds__(256) radix_histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n,
-                                                              int passes, uint32_t* __restrict__ ghist) {
+// The element count lives on the device (n_ptr, clamped to the buffer capacity) so that the host never has
+// to wait for it before launching; n_ptr == nullptr means "exactly cap elements".
+__global__ void __launch_bounds__(256) radix_histogram_kernel(const uint64_t* __restrict__ keys, uint32_t cap,
+                                                              const uint32_t* __restrict__ n_ptr, int passes,
+                                                              uint32_t* __restrict__ ghist) {
+    const uint32_t n = n_ptr ? min(*n_ptr, cap) : cap;
     __shared__ uint32_t s_hist[kMaxPasses * kRadix];
     for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
@@ -139,19 +143,22 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* tm
     return wex + incl - v;
 }
 
-__global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(
+__global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
     const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
-    uint32_t* __restrict__ vals_out, uint32_t n, int shift, const uint32_t* __restrict__ ghist /*[256]*/,
+    uint32_t* __restrict__ vals_out, uint32_t cap, const uint32_t* __restrict__ n_ptr, int shift,
+    const uint32_t* __restrict__ ghist /*[256]*/,
     uint32_t* __restrict__ status /*[ntiles*256]*/, uint32_t* __restrict__ ticket) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
 
+    const uint32_t n = n_ptr ? min(*n_ptr, cap) : cap;
+    if (blockIdx.x * (uint32_t)kSortTile >= n) return;  // tile beyond the live range (grid is sized by capacity)
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+    (void)ticket;  // blocks are dispatched in index order: predecessors of a tile are always running or done
 #pragma unroll
     for (int w = 0; w < kSortThreads / 32; ++w) sm.warp_hist[w][tid] = 0;
     __syncthreads();
-    const uint32_t tile = sm.tile;
+    const uint32_t tile = blockIdx.x;
     const uint32_t base = tile * kSortTile;
     const uint32_t nvalid = min((uint32_t)kSortTile, n - base);
 
@@ -199,14 +206,28 @@ __global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(
 
     uint32_t prev_sum = 0;
     if (tile > 0) {
+        // walk back over the predecessors kLook at a time: the status loads of one round are independent, so a
+        // round costs one L2 round trip instead of kLook of them (the serial walk dominated the pass at N ~ 2M)
+        constexpr int kLook = 8;
         int t = (int)tile - 1;
-        while (true) {
-            const uint32_t* ps = status + (size_t)t * kRadix + tid;
-            uint32_t w = ld_relaxed_u32(ps);
-            while ((w >> 30) == 0) w = ld_relaxed_u32(ps);
-            prev_sum += w & kStValMask;
-            if ((w >> 30) == 2) break;
-            --t;
+        bool found = false;
+        while (!found) {
+            uint32_t w[kLook];
+#pragma unroll
+            for (int k = 0; k < kLook; ++k)
+                w[k] = (t - k >= 0) ? ld_relaxed_u32(status + (size_t)(t - k) * kRadix + tid) : kStFlagIncl;
+#pragma unroll
+            for (int k = 0; k < kLook; ++k) {
+                if (found) continue;
+                if ((w[k] >> 30) == 0) {  // predecessor not published yet: retry from it
+                    t -= k;
+                    goto next_round;
+                }
+                prev_sum += w[k] & kStValMask;
+                if ((w[k] >> 30) == 2) found = true;
+            }
+            t -= kLook;
+        next_round:;
         }
         st_relaxed_u32(my_status, kStFlagIncl | ((prev_sum + block_count) & kStValMask));
     }
@@ -263,14 +284,15 @@ int launch_emit_keys(int P, const GeomLayout& g, const uint2* rects, uint64_t* k
 
 // Sorts n pairs on key bits [0, end_bit).  keys[0]/vals[0] hold the input; returns in *result_buf
 // which ping-pong buffer (0/1) holds the sorted output.
-int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* sort_ws, int* result_buf,
+int launch_sort_pairs(int64_t n, const uint32_t* n_ptr, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* sort_ws,
+                      int* result_buf,
                       cudaStream_t s) {
     // the sorted data always ends in buffer (passes & 1), also for the trivial sizes
     const int passes = sort_passes(end_bit);
     if (passes > kMaxPasses) { set_error("end_bit %d too large", end_bit); return HGS_ERR_INVALID; }
     *result_buf = passes & 1;
     if (n <= 0) return HGS_OK;
-    if (n == 1 || end_bit <= 0) {
+    if ((n == 1 && n_ptr == nullptr) || end_bit <= 0) {
         if (passes & 1) {
             if (int e = check_cuda(cudaMemcpyAsync(keys[1], keys[0], (size_t)n * 8, cudaMemcpyDeviceToDevice, s), "copy keys")) return e;
             if (int e = check_cuda(cudaMemcpyAsync(vals[1], vals[0], (size_t)n * 4, cudaMemcpyDeviceToDevice, s), "copy vals")) return e;
@@ -295,14 +317,14 @@ int launch_sort_pairs(int64_t n, int end_bit, uint64_t* keys[2], uint32_t* vals[
     const int hblocks = (int)(hb < 148 * 8 ? hb : 148 * 8);
     {
         StageScope prof(HGS_STAGE_SORT_HISTOGRAM, s);
-        radix_histogram_kernel<<<hblocks, 256, 0, s>>>(keys[0], nn, passes, L.hist);
+        radix_histogram_kernel<<<hblocks, 256, 0, s>>>(keys[0], nn, n_ptr, passes, L.hist);
     }
     if (int e = check_cuda(cudaGetLastError(), "radix_histogram launch")) return e;
     int cur = 0;
     for (int p = 0; p < passes; ++p) {
         StageScope prof(HGS_STAGE_SORT_ONESWEEP, s);
         onesweep_pass_kernel<<<(unsigned)L.ntiles, kSortThreads, sizeof(OnesweepSmem), s>>>(
-            keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], nn, 8 * p, L.hist + p * kRadix,
+            keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], nn, n_ptr, 8 * p, L.hist + p * kRadix,
             L.status + (size_t)p * L.ntiles * kRadix, L.tickets + p);
         if (int e = check_cuda(cudaGetLastError(), "onesweep launch")) return e;
         cur ^= 1;

@@ -36,12 +36,14 @@ int set_fwd_stats(void* dev_ptr) {
 // finalize: tile ranges + sorted-order packing
 // ------------------------------------------------------------------------------------------------
 template <int CS>
-__global__ void __launch_bounds__(256) finalize_sorted_kernel(uint32_t L, const uint64_t* __restrict__ keys,
+__global__ void __launch_bounds__(256) finalize_sorted_kernel(uint32_t cap, const uint32_t* __restrict__ n_ptr,
+                                                              const uint64_t* __restrict__ keys,
                                                               const uint32_t* __restrict__ point_list,
                                                               const float4* __restrict__ rec,
                                                               const float* __restrict__ rgb, uint2* __restrict__ ranges,
                                                               float4* __restrict__ pk_lo, float4* __restrict__ pk_hi,
                                                               float4* __restrict__ pk_col) {
+    const uint32_t L = n_ptr ? min(*n_ptr, cap) : cap;
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= L) return;
     const uint32_t id = point_list[idx];
@@ -523,7 +525,8 @@ struct PackedView {
 
 static PackedView packed_view(const BinningLayout& b) { return PackedView{b.pk_lo, b.pk_hi, b.pk_col}; }
 
-int launch_finalize_sorted(int channels, int64_t n, const uint64_t* keys_sorted, const uint32_t* point_list,
+int launch_finalize_sorted(int channels, int64_t n, const uint32_t* n_ptr, const uint64_t* keys_sorted,
+                           const uint32_t* point_list,
                            const GeomLayout& g, const BinningLayout& b, uint2* ranges, uint32_t* tile_order, size_t tiles,
                            cudaStream_t s) {
     if (int e = check_cuda(cudaMemsetAsync(ranges, 0, tiles * sizeof(uint2), s), "memset ranges")) return e;
@@ -534,10 +537,10 @@ int launch_finalize_sorted(int channels, int64_t n, const uint64_t* keys_sorted,
     }
     const unsigned nb = (unsigned)((n + 255) / 256);
     if (color_stride(channels) == 4)
-        finalize_sorted_kernel<4><<<nb, 256, 0, s>>>((uint32_t)n, keys_sorted, point_list, g.rec, g.rgb, ranges, b.pk_lo,
+        finalize_sorted_kernel<4><<<nb, 256, 0, s>>>((uint32_t)n, n_ptr, keys_sorted, point_list, g.rec, g.rgb, ranges, b.pk_lo,
                                                      b.pk_hi, b.pk_col);
     else
-        finalize_sorted_kernel<8><<<nb, 256, 0, s>>>((uint32_t)n, keys_sorted, point_list, g.rec, g.rgb, ranges, b.pk_lo,
+        finalize_sorted_kernel<8><<<nb, 256, 0, s>>>((uint32_t)n, n_ptr, keys_sorted, point_list, g.rec, g.rgb, ranges, b.pk_lo,
                                                      b.pk_hi, b.pk_col);
     tile_order_kernel<<<1, 1024, 0, s>>>((uint32_t)tiles, ranges, tile_order);
     return check_cuda(cudaGetLastError(), "finalize_sorted launch");

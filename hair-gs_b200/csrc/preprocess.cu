@@ -182,14 +182,13 @@ __device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long 
 }
 
 __global__ void __launch_bounds__(kPreprocThreads) preprocess_fwd_kernel(const PreArgs a) {
-    __shared__ uint32_t s_bid;
     __shared__ uint32_t s_warp_sum[kPreprocThreads / 32];
     __shared__ unsigned long long s_block_excl;
 
     const int tid = threadIdx.x;
-    if (tid == 0) s_bid = atomicAdd(&a.g.hdr->block_ticket, 1u);
-    __syncthreads();
-    const uint32_t bid = s_bid;
+    // Blocks are dispatched in blockIdx order, so a block only ever waits on predecessors that are already
+    // running or finished: the chained scan can use blockIdx directly (no ticket atomic + barrier at start-up).
+    const uint32_t bid = blockIdx.x;
     const int idx = (int)(bid * kPreprocThreads + tid);
 
     uint32_t touched = 0;

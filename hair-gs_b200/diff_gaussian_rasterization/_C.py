@@ -14,6 +14,20 @@ import torch
 from hairgs_b200 import _lib as L
 
 NUM_CHANNELS = 3
+SYNC_FREE = True        # False: size the binning workspace exactly, after a blocking read-back (reference behaviour)
+_capacity_hint = {}     # (device, P, H, W) -> instance capacity to try first
+_pinned_pool = []
+_pinned_next = 0
+
+
+def _pinned_triplet():
+    """Small ring of pinned int32[3] buffers for the async (num_rendered, -, overflow) read-back."""
+    global _pinned_next
+    if len(_pinned_pool) < 64:
+        _pinned_pool.append(torch.zeros(3, dtype=torch.int32).pin_memory())
+        return _pinned_pool[-1]
+    _pinned_next = (_pinned_next + 1) % 64
+    return _pinned_pool[_pinned_next]
 
 
 def _prep(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
@@ -67,15 +81,34 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
             return 0, out_color, radii, geom, torch.empty((0,), **u8), img
         L.check(lib.hgs_forward_stage_a(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(), radii.data_ptr(),
                                         stream), "forward stage A")
-        # the pass's one blocking read-back (rasterizer_impl.cu:281)
-        hdr = geom[:12].view(torch.int32).cpu()
-        if int(hdr[2]) != 0 or int(hdr[0]) < 0:
+        # The reference blocks on the instance count in the middle of the pass (rasterizer_impl.cu:281) and the GPU
+        # idles until the host has launched the rest.  Here the count stays on the device: stage B is enqueued at
+        # once into a binning workspace sized from the last count seen for this (device, P, W, H), and the host only
+        # waits for the small async read-back AFTERWARDS (the GPU is busy with stage B by then).  Too small a
+        # guess -> stage B is simply run again with the exact size.
+        host = _pinned_triplet()
+        L.check(lib.hgs_forward_read_num_rendered(geom.data_ptr(), P, host.data_ptr(), stream), "read num_rendered")
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        key = (dev.index, P, H, W)
+        cap = _capacity_hint.get(key) if SYNC_FREE else None
+        binning = None
+        if cap is not None:
+            binning = torch.empty((lib.hgs_binning_bytes(cap, C),), **u8)
+            L.check(lib.hgs_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(), binning.data_ptr(),
+                                            img.data_ptr(), cap, radii.data_ptr(), out_color.data_ptr(), stream),
+                    "forward stage B")
+        ready.synchronize()
+        N, overflow = int(host[0]), int(host[2])
+        if overflow != 0 or N < 0:
             raise L.HgsError("instance count overflows int32")
-        N = int(hdr[0])
-        binning = torch.empty((lib.hgs_binning_bytes(N, C),), **u8)
-        L.check(lib.hgs_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
-                                        binning.data_ptr() if N > 0 else None, img.data_ptr(), N, radii.data_ptr(),
-                                        out_color.data_ptr(), stream), "forward stage B")
+        if cap is None or N > cap:
+            binning = torch.empty((lib.hgs_binning_bytes(N, C),), **u8)
+            L.check(lib.hgs_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
+                                            binning.data_ptr() if N > 0 else None, img.data_ptr(), N, radii.data_ptr(),
+                                            out_color.data_ptr(), stream), "forward stage B")
+        # next guess: 25 % head-room, rounded up to the 4096-instance granularity hgs_binning_capacity inverts
+        _capacity_hint[key] = ((int(N * 1.25) + 4096 + 4095) // 4096) * 4096
     del keep
     return N, out_color, radii, geom, binning, img
 
@@ -118,7 +151,9 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                               dL_dmean3D=dL_dmeans3D.data_ptr(), dL_dcov3D=dL_dcov3D.data_ptr(),
                               dL_dsh=L.ptr(dL_dsh), dL_dscale=dL_dscales.data_ptr(),
                               dL_drot=dL_drotations.data_ptr())
-        L.check(lib.hgs_rasterize_backward(ctypes.byref(prm), ctypes.byref(inp), int(R), L.ptr(radii),
+        cap = lib.hgs_binning_capacity(binningBuffer.numel(), C, int(R))
+        L.check(int(cap), "binning capacity")
+        L.check(lib.hgs_rasterize_backward(ctypes.byref(prm), ctypes.byref(inp), int(cap), L.ptr(radii),
                                            geomBuffer.data_ptr(), L.ptr(binningBuffer), imageBuffer.data_ptr(),
                                            dpix.data_ptr(), ctypes.byref(grads), L.stream_ptr(dev)),
                 "backward")

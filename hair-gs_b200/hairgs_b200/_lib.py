@@ -59,6 +59,8 @@ def load():
     lib.hgs_image_bytes.argtypes = [c_int32, c_int32]
     lib.hgs_binning_bytes.restype = c_size_t
     lib.hgs_binning_bytes.argtypes = [c_int64, c_int32]
+    lib.hgs_binning_capacity.restype = c_int64
+    lib.hgs_binning_capacity.argtypes = [c_size_t, c_int32, c_int64]
     lib.hgs_sort_bytes.restype = c_size_t
     lib.hgs_sort_bytes.argtypes = [c_int64]
     lib.hgs_knn_bytes.restype = c_size_t
@@ -83,7 +85,7 @@ def load():
     lib.hgs_sort_pairs.restype = c_int
     lib.hgs_sort_pairs.argtypes = [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.hgs_state_view.restype = c_int64
-    lib.hgs_state_view.argtypes = [c_int, P(RasterParams), P(RasterInputs), c_int64, c_void_p, c_void_p, c_void_p,
+    lib.hgs_state_view.argtypes = [c_int, P(RasterParams), P(RasterInputs), c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p]
     lib.hgs_profile_enable.restype = c_int
     lib.hgs_profile_enable.argtypes = [c_int]
@@ -159,8 +161,11 @@ def state_view(what, prm, inp, num_rendered, geom, binning, img):
     out = torch.zeros(shape, dtype=dtype, device=geom.device)
     if out.numel() == 0:
         return out
+    cap = num_rendered
+    if binning is not None and binning.numel() > 0:
+        cap = check(int(lib.hgs_binning_capacity(binning.numel(), prm.channels, int(num_rendered))), "binning capacity")
     with torch.cuda.device(geom.device):
-        n = lib.hgs_state_view(what, ctypes.byref(prm), ctypes.byref(inp), int(num_rendered), ptr(geom), ptr(binning),
+        n = lib.hgs_state_view(what, ctypes.byref(prm), ctypes.byref(inp), int(num_rendered), int(cap), ptr(geom), ptr(binning),
                                ptr(img), out.data_ptr(), stream_ptr(geom.device))
     check(int(n), "state_view")
     assert int(n) == out.numel() * out.element_size(), (n, out.shape)

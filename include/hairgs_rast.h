@@ -100,6 +100,9 @@ const char* hgs_last_error(void);
 size_t hgs_geom_bytes(int32_t P, int32_t channels);
 size_t hgs_image_bytes(int32_t width, int32_t height);
 size_t hgs_binning_bytes(int64_t num_rendered, int32_t channels);
+/* capacity a binning workspace of `bytes` bytes was sized for: num_rendered itself if it matches, else the
+ * multiple of 4096 that does (sync-free mode); < 0 if none. */
+int64_t hgs_binning_capacity(size_t bytes, int32_t channels, int64_t num_rendered);
 
 /* Whole forward pass, reference call shape: allocates through the three callbacks, blocks once on
  * the instance count exactly like rasterizer_impl.cu:281, returns num_rendered (>= 0) or an error.
@@ -114,15 +117,19 @@ int hgs_rasterize_forward(hgs_alloc_fn geom_alloc, void* geom_user,
  * overlap the instance-count read-back (no allocation, no implicit synchronisation):
  *   A  preprocess + tile-count scan; leaves num_rendered in the geometry workspace
  *   (read it with hgs_forward_read_num_rendered: async copy into pinned host memory)
- *   B  key emission + (tile|depth) radix sort + tile ranges + compositing. */
+ *   B  key emission + (tile|depth) radix sort + tile ranges + compositing.  `capacity` is the number of
+ *      instances binning_ws was sized for (hgs_binning_bytes(capacity, channels)); the live count is read from
+ *      the geometry workspace ON THE DEVICE, so B may be enqueued before the host knows it.  If the count
+ *      turns out larger than capacity the outputs are garbage-but-in-bounds: call B again with more room. */
 int hgs_forward_stage_a(const hgs_raster_params* prm, const hgs_raster_inputs* in,
                         void* geom_ws, int32_t* radii, void* stream);
 int hgs_forward_read_num_rendered(const void* geom_ws, int32_t P, uint32_t* n_pinned_host, void* stream);
 int hgs_forward_stage_b(const hgs_raster_params* prm, const hgs_raster_inputs* in,
-                        void* geom_ws, void* binning_ws, void* image_ws, int64_t num_rendered,
+                        void* geom_ws, void* binning_ws, void* image_ws, int64_t capacity,
                         const int32_t* radii, float* out_color, void* stream);
 
-/* Backward pass.  R = num_rendered returned by the forward; workspaces are the forward's. */
+/* Backward pass.  R = the capacity binning_ws was carved with (num_rendered in exact mode, see
+ * hgs_binning_capacity); workspaces are the forward's. */
 int hgs_rasterize_backward(const hgs_raster_params* prm, const hgs_raster_inputs* in,
                            int64_t R, const int32_t* radii,
                            const void* geom_ws, const void* binning_ws, const void* image_ws,
@@ -158,7 +165,7 @@ enum hgs_view {
     HGS_VIEW_COV3D = 13         /* float[P*6]; recomputed on demand */
 };
 int64_t hgs_state_view(int what, const hgs_raster_params* prm, const hgs_raster_inputs* in,
-                       int64_t num_rendered, const void* geom_ws, const void* binning_ws,
+                       int64_t num_rendered, int64_t binning_capacity, const void* geom_ws, const void* binning_ws,
                        const void* image_ws, void* dst, void* stream);
 
 /* Stand-alone stable LSD radix sort of (u64 key, u32 value) pairs on bits [0, end_bit): the
