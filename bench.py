@@ -191,9 +191,38 @@ class Harness:
             self.last_N = N
         b.all_reduce()  # one collective per step; no-op on a single rank
 
-    # ---- end-to-end step: render() + autograd, host<->device copies inside --------------------------
-    def setup_e2e(self):
+    # ---- device-resident fused step: strand parameterisation + 7 channels in one pass ------------------
+    def setup_fused(self):
         torch = self.torch
+        from hairgs_b200 import fused
+        self.fused_mod = fused
+        H, W = self.cfg["H"], self.cfg["W"]
+        g = torch.Generator(device="cpu").manual_seed(99)
+        self.dL7 = (torch.randn(7, H, W, generator=g) / (H * W)).to(self.dev)
+        self.bg7 = torch.zeros(7, device=self.dev)
+        m = self.model
+        self.fparams = {n: p for n, p in m.named_parameters() if p.numel() > 0}
+        from hairgs_b200 import multiview
+        self.fbucket = multiview.GradBucket({n: p.shape for n, p in self.fparams.items()}, self.dev)
+
+    def step_resident_fused(self, it):
+        cam = self.cams[self.my_views[it % len(self.my_views)]]
+        m = self.model
+        self.fbucket.zero_()
+        self.fbucket.attach_to(self.fparams)
+        out = self.fused_mod.render_strands(cam, m, self.bg7)
+        out["image7"].backward(self.dL7)
+        self.fbucket.all_reduce()
+        self.last_N = 0
+
+    # ---- end-to-end step: render() + autograd, host<->device copies inside --------------------------
+    def setup_e2e(self, fused=False):
+        torch = self.torch
+        self.fused = fused
+        if fused:
+            from hairgs_b200.fused import render_strands
+            self.render_strands = render_strands
+            self.bg7 = torch.zeros(7, device=self.dev)
         import diff_gaussian_rasterization as dgr
         dgr._RasterizeGaussians.backend = self.C
         from gaussian_renderer import render
@@ -205,6 +234,9 @@ class Harness:
         for p in self.params:
             p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
             o += p.numel()
+        if getattr(self, "copy_stream", None) is not None:
+            self._prefetched = -1
+            return
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         H, W = self.cfg["H"], self.cfg["W"]
         self.tgt_dev = [torch.empty(7, H, W, device=self.dev) for _ in range(2)]
@@ -250,15 +282,21 @@ class Harness:
         self.flat_grad.zero_()
         m = self.model
         loss = None
-        for s in cfg["sets"]:
-            out = self.render(cam, m, self.bg, override_color=colour_override(m, s))["render"]
-            if s == "sh":
-                term = (out - tgt[0:3]).abs().mean()
-            elif s == "mask":
-                term = 0.01 * (out[0:1] - tgt[3:4]).abs().mean()  # lambda_mask, arguments/__init__.py:86
-            else:
-                term = (out - tgt[4:7]).abs().mean()
-            loss = term if loss is None else loss + term
+        if self.fused:
+            # ONE fused pass: strand parameterisation + 7 channels (hairgs_b200.fused.render_strands)
+            out = self.render_strands(cam, m, self.bg7)
+            loss = ((out["render"] - tgt[0:3]).abs().mean() + 0.01 * (out["mask"] - tgt[3:4]).abs().mean() +
+                    (out["orientation"] - tgt[4:7]).abs().mean())
+        else:
+            for s in cfg["sets"]:
+                out = self.render(cam, m, self.bg, override_color=colour_override(m, s))["render"]
+                if s == "sh":
+                    term = (out - tgt[0:3]).abs().mean()
+                elif s == "mask":
+                    term = 0.01 * (out[0:1] - tgt[3:4]).abs().mean()  # lambda_mask, arguments/__init__.py:86
+                else:
+                    term = (out - tgt[4:7]).abs().mean()
+                loss = term if loss is None else loss + term
         loss.backward()
         if self.world > 1:
             torch.distributed.all_reduce(self.flat_grad)
@@ -346,9 +384,9 @@ def algorithmic_bytes(stage, P, N, HW, T, M, D, sh_mode, C=3):
     if stage == "tile_ranges":
         return 8 * N + 8 * T
     if stage == "composite_fwd":
-        return 40 * N + 20 * HW
+        return (28 + 4 * C) * N + (8 + 4 * C) * HW
     if stage == "composite_bwd":
-        return 40 * N + 20 * HW + 36 * N
+        return (28 + 4 * C) * N + (8 + 4 * C) * HW + 4 * (6 + C) * N
     if stage == "preprocess_bwd":
         return P * (96 + 40) + (P * (12 * (D + 1) ** 2 + 15) + P * 12 * M if sh_mode else 0)
     return 0
@@ -435,8 +473,23 @@ def main():
     lib.hgs_profile_collect(None, launches)
     launches_per_step = int(sum(launches))
 
-    h.setup_e2e()
+    can_fuse = args.impl == "ours" and cfg["kind"] == "strands" and tuple(cfg["sets"]) == ("sh", "mask", "orientation")
+    ms_res_3pass, ms_e2e_3pass = ms_res, None
+    h.setup_e2e(fused=False)
     ms_e2e = timed_loop(torch, h.step_e2e, args.steps, args.warmup, world, dev, flush)
+    if can_fuse:
+        # the same view (same 7 output planes, same parameter gradients) through the fused strand entry
+        ms_e2e_3pass = ms_e2e
+        h.setup_fused()
+        ms_res = timed_loop(torch, h.step_resident_fused, args.steps, args.warmup, world, dev, flush)
+        launches = (ctypes.c_int64 * 10)()
+        lib.hgs_profile_collect(None, launches)
+        h.step_resident_fused(0)
+        launches = (ctypes.c_int64 * 10)()
+        lib.hgs_profile_collect(None, launches)
+        launches_per_step = int(sum(launches))
+        h.setup_e2e(fused=True)
+        ms_e2e = timed_loop(torch, h.step_e2e, args.steps, args.warmup, world, dev, flush)
     clk = clocks.stop() if rank == 0 else None
     import diff_gaussian_rasterization as dgr
     dgr._RasterizeGaussians.backend = dgr._C
@@ -458,8 +511,10 @@ def main():
         lib.hgs_profile_collect(None, None)  # reset the launch counters accumulated by the e2e loop
         lib.hgs_profile_enable(1)
         prof_steps = min(args.steps, 8)
+        prof_step = h.step_resident_fused if can_fuse else h.step_resident
+        C_prof = 7 if can_fuse else 3
         for it in range(prof_steps):
-            h.step_resident(it)
+            prof_step(it)
         ms = (ctypes.c_double * 10)()
         cnt = (ctypes.c_int64 * 10)()
         lib.hgs_profile_collect(ms, cnt)
@@ -470,13 +525,13 @@ def main():
                 continue
             name = lib.hgs_stage_name(sidx).decode()
             per_launch_ms = ms[sidx] / cnt[sidx]
-            ab = algorithmic_bytes(name, P, N, HW, T, M, D, True)
+            ab = algorithmic_bytes(name, P, N, HW, T, M, D, True, C_prof)
             stages[name] = {"ms_per_launch": round(per_launch_ms, 5), "launches_per_step": cnt[sidx] / prof_steps,
                             "share": round(ms[sidx] / total, 4) if total else None,
                             "achieved_GBps": round(ab / per_launch_ms / 1e6, 1) if per_launch_ms > 0 and ab else None,
                             "frac_of_hbm_peak": round(ab / per_launch_ms / 1e6 / peak, 4) if per_launch_ms > 0 and ab else None}
         dom = max(stages, key=lambda k: stages[k]["ms_per_launch"] * stages[k]["launches_per_step"])
-        ab = algorithmic_bytes(dom, P, N, HW, T, M, D, True)
+        ab = algorithmic_bytes(dom, P, N, HW, T, M, D, True, C_prof)
         ach = ab / stages[dom]["ms_per_launch"] / 1e6
         roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
@@ -494,6 +549,12 @@ def main():
                      "d2h_bytes_per_step": h.d2h_bytes, "ms_per_step": round(ms_e2e / args.steps, 4),
                      "api": "gaussian_renderer.render() + autograd, targets/camera prefetched from pinned host memory"},
                 gpu_launches=launches_per_step * args.steps, clocks=clk)
+    if can_fuse:
+        config["path"] = ("fused strand entry: strand parameterisation + RGB/mask/orientation in ONE rasterization pass "
+                          "(hairgs_b200.fused.render_strands); the three-pass drop-in path is reported as *_dropin_3pass")
+        line["value_dropin_3pass"] = round(views / (ms_res_3pass / 1000.0), 2)
+        line["e2e"]["value_dropin_3pass"] = round(views / (ms_e2e_3pass / 1000.0), 2)
+        line["e2e"]["api"] = "hairgs_b200.fused.render_strands() + autograd, targets/camera prefetched from pinned host memory"
     line["n_gpus"] = world
     if args.impl == "reference":
         line["impl"] = "reference"

@@ -63,6 +63,9 @@ int launch_preprocess_fwd(const hgs_raster_params*, const hgs_raster_inputs*, co
 int launch_preprocess_bwd(const hgs_raster_params*, const hgs_raster_inputs*, const GeomLayout&, const int32_t*,
                           const hgs_raster_grads*, cudaStream_t);
 int launch_mark_visible(int, const float*, const float*, uint8_t*, cudaStream_t);
+int launch_strand_preprocess_fwd(const hgs_raster_params*, const hgs_strand_inputs*, const GeomLayout&, int32_t*, cudaStream_t);
+int launch_strand_preprocess_bwd(const hgs_raster_params*, const hgs_strand_inputs*, const GeomLayout&,
+                                 const hgs_strand_grads*, cudaStream_t);
 int launch_view_geom(int, const hgs_raster_params*, const hgs_raster_inputs*, const GeomLayout&, void*, cudaStream_t);
 int launch_emit_keys(int, const GeomLayout&, const uint2*, uint64_t*, uint32_t*, uint32_t, uint32_t, cudaStream_t);
 int launch_sort_pairs(int64_t, const uint32_t*, int, uint64_t* [2], uint32_t* [2], void*, int*, cudaStream_t);
@@ -176,11 +179,9 @@ int hgs_forward_read_num_rendered(const void* geom_ws, int32_t P, uint32_t* n_pi
                                       (cudaStream_t)stream), "read num_rendered");
 }
 
-int hgs_forward_stage_b(const hgs_raster_params* prm, const hgs_raster_inputs* in, void* geom_ws, void* binning_ws,
-                        void* image_ws, int64_t N, const int32_t* radii, float* out_color, void* stream) {
-    (void)radii;
-    if (int e = validate(prm, in)) return e;
-    cudaStream_t s = (cudaStream_t)stream;
+// bin + sort + finalize + composite, shared by the generic and the strand entry
+static int stage_b_impl(const hgs_raster_params* prm, const float* background, void* geom_ws, void* binning_ws,
+                        void* image_ws, int64_t N, float* out_color, cudaStream_t s) {
     if (!geom_ws || !image_ws || (N > 0 && !binning_ws) || !out_color) { set_error("null workspace/output"); return HGS_ERR_INVALID; }
     if (N < 0 || N > 0x7fffffffll) { set_error("num_rendered out of range"); return HGS_ERR_OVERFLOW; }
     GeomLayout g = carve_geom(geom_ws, prm->P, prm->channels);
@@ -196,8 +197,82 @@ int hgs_forward_stage_b(const hgs_raster_params* prm, const hgs_raster_inputs* i
     if (int e = stage_check("sort", prm->debug, s)) return e;
     if (int e = launch_finalize_sorted(prm->channels, N, n_ptr, b.keys[res], b.vals[res], g, b, im.ranges, im.tile_order, (size_t)gx * gy, s)) return e;
     if (int e = stage_check("finalize_sorted", prm->debug, s)) return e;
-    if (int e = launch_composite_fwd(prm->channels, im, b, prm->width, prm->height, in->background, out_color, s)) return e;
+    if (int e = launch_composite_fwd(prm->channels, im, b, prm->width, prm->height, background, out_color, s)) return e;
     return stage_check("composite_fwd", prm->debug, s);
+}
+
+int hgs_forward_stage_b(const hgs_raster_params* prm, const hgs_raster_inputs* in, void* geom_ws, void* binning_ws,
+                        void* image_ws, int64_t N, const int32_t* radii, float* out_color, void* stream) {
+    (void)radii;
+    if (int e = validate(prm, in)) return e;
+    return stage_b_impl(prm, in->background, geom_ws, binning_ws, image_ws, N, out_color, (cudaStream_t)stream);
+}
+
+static int validate_strands(const hgs_raster_params* prm, const hgs_strand_inputs* in) {
+    if (!prm || !in) { set_error("null params"); return HGS_ERR_INVALID; }
+    if (prm->channels != 7) { set_error("strand entry renders exactly 7 channels (rgb, mask, orientation)"); return HGS_ERR_INVALID; }
+    if (prm->P < 0 || prm->width <= 0 || prm->height <= 0) { set_error("bad sizes"); return HGS_ERR_INVALID; }
+    if ((prm->width + HGS_TILE - 1) / HGS_TILE > 0xffff || (prm->height + HGS_TILE - 1) / HGS_TILE > 0xffff) { set_error("image too large"); return HGS_ERR_INVALID; }
+    if (prm->D < 0 || prm->D > 3 || (prm->D + 1) * (prm->D + 1) > prm->M) { set_error("SH degree %d incompatible with M=%d", prm->D, prm->M); return HGS_ERR_INVALID; }
+    if (prm->P > 0 && (!in->endpoints || !in->endpoint_pairs || !in->width || !in->opacity_logit || !in->mask_logit ||
+                       !in->features || !in->viewmatrix || !in->projmatrix || !in->cam_pos || !in->background)) {
+        set_error("missing required strand input pointer");
+        return HGS_ERR_INVALID;
+    }
+    return HGS_OK;
+}
+
+int hgs_strands_forward_stage_a(const hgs_raster_params* prm, const hgs_strand_inputs* in, void* geom_ws, int32_t* radii,
+                                void* stream) {
+    if (int e = validate_strands(prm, in)) return e;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!geom_ws) { set_error("null geometry workspace"); return HGS_ERR_INVALID; }
+    GeomLayout g = carve_geom(geom_ws, prm->P, prm->channels);
+    if (prm->P == 0) return check_cuda(cudaMemsetAsync(g.hdr, 0, g.clear_bytes, s), "memset geom header");
+    if (int e = launch_strand_preprocess_fwd(prm, in, g, radii, s)) return e;
+    return stage_check("strand preprocess", prm->debug, s);
+}
+
+int hgs_strands_forward_stage_b(const hgs_raster_params* prm, const hgs_strand_inputs* in, void* geom_ws, void* binning_ws,
+                                void* image_ws, int64_t capacity, float* out_color, void* stream) {
+    if (int e = validate_strands(prm, in)) return e;
+    return stage_b_impl(prm, in->background, geom_ws, binning_ws, image_ws, capacity, out_color, (cudaStream_t)stream);
+}
+
+int hgs_strands_backward(const hgs_raster_params* prm, const hgs_strand_inputs* in, int64_t R, const void* geom_ws,
+                         const void* binning_ws, const void* image_ws, const float* dL_dpix, const hgs_strand_grads* gr,
+                         void* stream) {
+    if (int e = validate_strands(prm, in)) return e;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!gr || !gr->dL_dmean2D || !gr->dL_dconic || !gr->dL_dopacity || !gr->dL_dcolor || !gr->dL_dendpoints ||
+        !gr->dL_dwidth || !gr->dL_dopacity_logit || !gr->dL_dmask_logit || !gr->dL_dfeatures) { set_error("missing gradient output pointer"); return HGS_ERR_INVALID; }
+    if (!geom_ws || !image_ws || !dL_dpix || (R > 0 && !binning_ws)) { set_error("null workspace"); return HGS_ERR_INVALID; }
+    const int P = prm->P;
+    if (int e = check_cuda(cudaMemsetAsync(gr->dL_dendpoints, 0, (size_t)in->num_endpoints * 3 * 4, s), "memset dL_dendpoints")) return e;
+    if (P == 0) return HGS_OK;
+    GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels);
+    ImageLayout im = carve_image((void*)image_ws, prm->width, prm->height);
+    BinningLayout b = carve_binning((void*)binning_ws, R, prm->channels);
+    const int res = sort_passes(end_bit_for(prm)) & 1;
+    const size_t Pz = (size_t)P;
+    if (gr->dL_dconic == gr->dL_dmean2D + 3 * Pz && gr->dL_dopacity == gr->dL_dconic + 4 * Pz &&
+        gr->dL_dcolor == gr->dL_dopacity + Pz) {
+        if (int e = check_cuda(cudaMemsetAsync(gr->dL_dmean2D, 0, Pz * (8 + 7) * 4, s), "memset grads")) return e;
+    } else {
+        if (int e = check_cuda(cudaMemsetAsync(gr->dL_dmean2D, 0, Pz * 3 * 4, s), "memset dL_dmean2D")) return e;
+        if (int e = check_cuda(cudaMemsetAsync(gr->dL_dconic, 0, Pz * 4 * 4, s), "memset dL_dconic")) return e;
+        if (int e = check_cuda(cudaMemsetAsync(gr->dL_dopacity, 0, Pz * 4, s), "memset dL_dopacity")) return e;
+        if (int e = check_cuda(cudaMemsetAsync(gr->dL_dcolor, 0, Pz * 7 * 4, s), "memset dL_dcolor")) return e;
+    }
+    if (R > 0) {
+        hgs_raster_grads rg;
+        memset(&rg, 0, sizeof(rg));
+        rg.dL_dmean2D = gr->dL_dmean2D; rg.dL_dconic = gr->dL_dconic; rg.dL_dopacity = gr->dL_dopacity; rg.dL_dcolor = gr->dL_dcolor;
+        if (int e = launch_composite_bwd(7, im, b, b.vals[res], prm->width, prm->height, in->background, dL_dpix, &rg, s)) return e;
+        if (int e = stage_check("composite_bwd", prm->debug, s)) return e;
+    }
+    if (int e = launch_strand_preprocess_bwd(prm, in, g, gr, s)) return e;
+    return stage_check("strand preprocess_bwd", prm->debug, s);
 }
 
 int hgs_rasterize_forward(hgs_alloc_fn geom_alloc, void* geom_user, hgs_alloc_fn binning_alloc, void* binning_user,

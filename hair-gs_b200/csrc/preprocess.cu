@@ -38,7 +38,50 @@ struct PreArgs {
     int32_t* radii;
     GeomLayout g;
     uint32_t nblocks;
+    // strand-aligned entry (kStrand): Gaussians derived from segment end points (scene/hair_gaussian_model.py:134-206)
+    const float* endpoints;      // [E,3]
+    const long long* pairs;      // [P,2]
+    const float* width;          // [P] log sigma_yz
+    const float* opacity_logit;  // [P]
+    const float* mask_logit;     // [P]
 };
+
+static constexpr float kDistToScale = 0.5102133812190369f;  // scene/gaussian_model.py:35
+static constexpr float kMinVal = 1e-7f;                     // HairGaussianModel.min_val
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Segment -> Gaussian (scene/hair_gaussian_model.py:134-201): centre, unit direction (x axis when collapsed),
+// sigma_x = max(|e1-e0|/2 * k, 1e-7), sigma_yz = exp(width).  With S = diag(sx, w, w) and R's first column = d the
+// covariance R S^2 R^T is w^2 I + (sx^2 - w^2) d d^T — independent of the roll about d, so the quaternion the
+// reference builds on the torch side (utils/transform.py:69-86 + pytorch3d matrix_to_quaternion) never has to exist.
+struct StrandGeom {
+    float3 mean, dhat, diff;
+    float dist, sx, syz;
+    bool collapsed;
+};
+__device__ __forceinline__ StrandGeom strand_geom(const float* __restrict__ endpoints, const long long* __restrict__ pairs,
+                                                  const float* __restrict__ width, int idx, float mod) {
+    StrandGeom sg;
+    const long long i0 = pairs[2 * (size_t)idx], i1 = pairs[2 * (size_t)idx + 1];
+    const float3 e0 = make_float3(endpoints[3 * i0], endpoints[3 * i0 + 1], endpoints[3 * i0 + 2]);
+    const float3 e1 = make_float3(endpoints[3 * i1], endpoints[3 * i1 + 1], endpoints[3 * i1 + 2]);
+    sg.mean = make_float3((e0.x + e1.x) * 0.5f, (e0.y + e1.y) * 0.5f, (e0.z + e1.z) * 0.5f);
+    sg.diff = make_float3(e1.x - e0.x, e1.y - e0.y, e1.z - e0.z);
+    sg.dist = sqrtf(sg.diff.x * sg.diff.x + sg.diff.y * sg.diff.y + sg.diff.z * sg.diff.z);
+    sg.collapsed = !(sg.dist > kMinVal);
+    sg.dhat = sg.collapsed ? make_float3(1.f, 0.f, 0.f)
+                           : make_float3(sg.diff.x / sg.dist, sg.diff.y / sg.dist, sg.diff.z / sg.dist);
+    sg.sx = fmaxf(sg.dist * 0.5f * kDistToScale, kMinVal) * mod;
+    sg.syz = expf(width[idx]) * mod;
+    return sg;
+}
+__device__ __forceinline__ void strand_cov3d(const StrandGeom& sg, float* cov3D) {
+    const float a = sg.sx * sg.sx, b = sg.syz * sg.syz, c = a - b;
+    const float3 d = sg.dhat;
+    cov3D[0] = b + c * d.x * d.x; cov3D[1] = c * d.x * d.y; cov3D[2] = c * d.x * d.z;
+    cov3D[3] = b + c * d.y * d.y; cov3D[4] = c * d.y * d.z; cov3D[5] = b + c * d.z * d.z;
+}
 
 // Sigma = (S R)^T (S R) from scale and raw (un-normalised) quaternion (forward.cu:118-152).
 __device__ __forceinline__ void cov3d_from_scale_rot(const float3 scale, float mod, const float4 rot, float* cov3D) {
@@ -181,6 +224,7 @@ __device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long 
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
 
+template <bool kStrand>
 __global__ void __launch_bounds__(kPreprocThreads) preprocess_fwd_kernel(const PreArgs a) {
     __shared__ uint32_t s_warp_sum[kPreprocThreads / 32];
     __shared__ unsigned long long s_block_excl;
@@ -195,7 +239,14 @@ __global__ void __launch_bounds__(kPreprocThreads) preprocess_fwd_kernel(const P
     int radius_i = 0;
     if (idx < a.P) {
         do {
-            const float3 p_orig = make_float3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+            StrandGeom sg;
+            float3 p_orig;
+            if (kStrand) {
+                sg = strand_geom(a.endpoints, a.pairs, a.width, idx, a.scale_modifier);
+                p_orig = sg.mean;
+            } else {
+                p_orig = make_float3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+            }
             // near-plane cull (auxiliary.h:139-164)
             const float4 p_hom = xform_point_4x4(p_orig, a.projmatrix);
             const float p_w = 1.0f / (p_hom.w + 0.0000001f);
@@ -205,7 +256,10 @@ __global__ void __launch_bounds__(kPreprocThreads) preprocess_fwd_kernel(const P
 
             float cov3D_local[6];
             const float* cov3D;
-            if (a.cov3D_precomp != nullptr) {
+            if (kStrand) {
+                strand_cov3d(sg, cov3D_local);
+                cov3D = cov3D_local;
+            } else if (a.cov3D_precomp != nullptr) {
                 cov3D = a.cov3D_precomp + (size_t)idx * 6;
             } else {
                 const float3 sc = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
@@ -233,7 +287,15 @@ __global__ void __launch_bounds__(kPreprocThreads) preprocess_fwd_kernel(const P
             if ((rmax.x - rmin.x) * (rmax.y - rmin.y) == 0) break;
 
             float* rgb_out = a.g.rgb + (size_t)idx * a.cstride;
-            if (a.colors_precomp == nullptr) {
+            if (kStrand) {
+                // 7 channels in one pass: SH colour, mask, world-space strand direction (loss/losses.py:246-249,311-312)
+                uint32_t cb;
+                const float3 c = sh_to_rgb(a.D, a.shs + (size_t)idx * a.M * 3, p_orig,
+                                           make_float3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]), cb);
+                reinterpret_cast<float4*>(rgb_out)[0] = make_float4(c.x, c.y, c.z, sigmoidf_(a.mask_logit[idx]));
+                reinterpret_cast<float4*>(rgb_out)[1] = make_float4(sg.dhat.x, sg.dhat.y, sg.dhat.z, 0.f);
+                a.g.clamped[idx] = (uint8_t)cb;
+            } else if (a.colors_precomp == nullptr) {
                 uint32_t cb;
                 const float3 c = sh_to_rgb(a.D, a.shs + (size_t)idx * a.M * 3, p_orig,
                                            make_float3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]), cb);
@@ -249,7 +311,7 @@ __global__ void __launch_bounds__(kPreprocThreads) preprocess_fwd_kernel(const P
                 if (a.cstride > 4) reinterpret_cast<float4*>(rgb_out)[1] = make_float4(tmp[4], tmp[5], tmp[6], tmp[7]);
             }
 
-            const float opacity = a.opacities[idx];
+            const float opacity = kStrand ? sigmoidf_(a.opacity_logit[idx]) : a.opacities[idx];
             const float2 ext = alpha_extent(conic.x, conic.y, conic.z, opacity);
             a.g.depths[idx] = p_view.z;
             radius_i = (int)my_radius;
@@ -357,6 +419,18 @@ struct PreBwdArgs {
     float* dL_dsh;            // [P,M,3]
     float* dL_dscale;         // [P,3]
     float* dL_drot;           // [P,4]
+    // strand-aligned entry
+    const uint32_t* tiles_touched;
+    const float* endpoints;
+    const long long* pairs;
+    const float* width;
+    const float* opacity_logit;
+    const float* mask_logit;
+    const float* dL_dopacity;     // [P] w.r.t. the activated opacity (from the compositor)
+    float* dL_dendpoints;         // [E,3] accumulated with atomics (pre-zeroed)
+    float* dL_dwidth;             // [P]
+    float* dL_dopacity_logit;     // [P]
+    float* dL_dmask_logit;        // [P]
 };
 
 __device__ __forceinline__ float3 dnormvdv3(const float3 v, const float3 dv) {  // auxiliary.h:107-117
@@ -369,13 +443,22 @@ __device__ __forceinline__ float3 dnormvdv3(const float3 v, const float3 dv) {  
     return r;
 }
 
+template <bool kStrand>
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreBwdArgs a) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.P) return;
     const bool has_sh = (a.shs != nullptr) && a.M > 0;
-    const bool has_sr = (a.scales != nullptr);
+    const bool has_sr = !kStrand && (a.scales != nullptr);
 
-    if (!(a.radii[idx] > 0)) {
+    if (kStrand) {
+        if (!(a.tiles_touched[idx] > 0)) {
+            a.dL_dwidth[idx] = 0.f;
+            a.dL_dopacity_logit[idx] = 0.f;
+            a.dL_dmask_logit[idx] = 0.f;
+            for (int i = 0; i < a.M * 3; ++i) a.dL_dsh[(size_t)idx * a.M * 3 + i] = 0.f;
+            return;
+        }
+    } else if (!(a.radii[idx] > 0)) {
         // culled: the reference leaves the torch::zeros fill in place (rasterize_points.cu:151-159)
         a.dL_dmean3D[3 * idx] = 0.f; a.dL_dmean3D[3 * idx + 1] = 0.f; a.dL_dmean3D[3 * idx + 2] = 0.f;
 #pragma unroll
@@ -386,13 +469,22 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreBwdArgs a)
         return;
     }
 
-    const float3 mean = make_float3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+    StrandGeom sg;
+    float3 mean;
+    if (kStrand) {
+        sg = strand_geom(a.endpoints, a.pairs, a.width, idx, a.scale_modifier);
+        mean = sg.mean;
+    } else {
+        mean = make_float3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+    }
 
     // ---- 3D covariance: recomputed (bit-identical to the forward) instead of stored ------------
     float cov3D[6];
     float3 sc = make_float3(0.f, 0.f, 0.f);
     float4 rq = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a.cov3D_precomp != nullptr) {
+    if (kStrand) {
+        strand_cov3d(sg, cov3D);
+    } else if (a.cov3D_precomp != nullptr) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) cov3D[i] = a.cov3D_precomp[6 * (size_t)idx + i];
     } else {
@@ -446,8 +538,10 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreBwdArgs a)
 #pragma unroll
         for (int i = 0; i < 6; ++i) dcov[i] = 0;
     }
+    if (!kStrand) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) a.dL_dcov3D[6 * (size_t)idx + i] = dcov[i];
+        for (int i = 0; i < 6; ++i) a.dL_dcov3D[6 * (size_t)idx + i] = dcov[i];
+    }
 
     const float dL_dT00 = 2 * (T.m[0][0] * V[0][0] + T.m[0][1] * V[0][1] + T.m[0][2] * V[0][2]) * dL_da +
                           (T.m[1][0] * V[0][0] + T.m[1][1] * V[0][1] + T.m[1][2] * V[0][2]) * dL_db;
@@ -593,6 +687,46 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreBwdArgs a)
     } else if (a.dL_dsh) {
         for (int i = 0; i < a.M * 3; ++i) a.dL_dsh[(size_t)idx * a.M * 3 + i] = 0.f;
     }
+    if (kStrand) {
+        // ---- back through the strand parameterisation ---------------------------------------------------------
+        // Sigma = b I + (a-b) d d^T, a = sx^2, b = syz^2; G = symmetric dL/dSigma (off-diagonals halved, as in
+        // backward_distwar.cu:309-313).
+        const float mod = a.scale_modifier;
+        const float3 d = sg.dhat;
+        const float gxx = dcov[0], gyy = dcov[3], gzz = dcov[5];
+        const float gxy = 0.5f * dcov[1], gxz = 0.5f * dcov[2], gyz = 0.5f * dcov[4];
+        const float3 Gd = make_float3(gxx * d.x + gxy * d.y + gxz * d.z, gxy * d.x + gyy * d.y + gyz * d.z,
+                                      gxz * d.x + gyz * d.y + gzz * d.z);
+        const float dGd = d.x * Gd.x + d.y * Gd.y + d.z * Gd.z;
+        const float av = sg.sx * sg.sx, bv = sg.syz * sg.syz;
+        const float dL_da = dGd, dL_db = (gxx + gyy + gzz) - dGd;
+        a.dL_dwidth[idx] = dL_db * 2.f * bv;  // b = (mod*exp(w))^2
+        // sx = max(dist/2*k, 1e-7)*mod
+        const bool sx_live = sg.dist * 0.5f * kDistToScale > kMinVal;
+        const float dL_ddist = sx_live ? dL_da * 2.f * sg.sx * (0.5f * kDistToScale * mod) : 0.f;
+        float3 dL_dd = make_float3(2.f * (av - bv) * Gd.x, 2.f * (av - bv) * Gd.y, 2.f * (av - bv) * Gd.z);
+        // orientation colour channels 4..6 carry d itself
+        const float* dcol = a.dL_dcolor + (size_t)idx * a.channels;
+        dL_dd.x += dcol[4]; dL_dd.y += dcol[5]; dL_dd.z += dcol[6];
+        float3 dL_ddiff = make_float3(0.f, 0.f, 0.f);
+        if (!sg.collapsed) {
+            const float dd = d.x * dL_dd.x + d.y * dL_dd.y + d.z * dL_dd.z;
+            const float inv = 1.f / sg.dist;
+            dL_ddiff = make_float3((dL_dd.x - d.x * dd) * inv + d.x * dL_ddist, (dL_dd.y - d.y * dd) * inv + d.y * dL_ddist,
+                                   (dL_dd.z - d.z * dd) * inv + d.z * dL_ddist);
+        }
+        const long long i0 = a.pairs[2 * (size_t)idx], i1 = a.pairs[2 * (size_t)idx + 1];
+        atomicAdd(a.dL_dendpoints + 3 * i0, 0.5f * dmean.x - dL_ddiff.x);
+        atomicAdd(a.dL_dendpoints + 3 * i0 + 1, 0.5f * dmean.y - dL_ddiff.y);
+        atomicAdd(a.dL_dendpoints + 3 * i0 + 2, 0.5f * dmean.z - dL_ddiff.z);
+        atomicAdd(a.dL_dendpoints + 3 * i1, 0.5f * dmean.x + dL_ddiff.x);
+        atomicAdd(a.dL_dendpoints + 3 * i1 + 1, 0.5f * dmean.y + dL_ddiff.y);
+        atomicAdd(a.dL_dendpoints + 3 * i1 + 2, 0.5f * dmean.z + dL_ddiff.z);
+        const float o = sigmoidf_(a.opacity_logit[idx]), m = sigmoidf_(a.mask_logit[idx]);
+        a.dL_dopacity_logit[idx] = a.dL_dopacity[idx] * o * (1.f - o);
+        a.dL_dmask_logit[idx] = dcol[3] * m * (1.f - m);
+        return;
+    }
     a.dL_dmean3D[3 * idx] = dmean.x;
     a.dL_dmean3D[3 * idx + 1] = dmean.y;
     a.dL_dmean3D[3 * idx + 2] = dmean.z;
@@ -722,10 +856,35 @@ int launch_preprocess_fwd(const hgs_raster_params* prm, const hgs_raster_inputs*
     a.viewmatrix = in->viewmatrix; a.projmatrix = in->projmatrix; a.cam_pos = in->cam_pos;
     a.radii = radii; a.g = g;
     a.nblocks = (prm->P + kPreprocThreads - 1) / kPreprocThreads;
+    a.endpoints = nullptr; a.pairs = nullptr; a.width = nullptr; a.opacity_logit = nullptr; a.mask_logit = nullptr;
     if (int e = check_cuda(cudaMemsetAsync(g.hdr, 0, g.clear_bytes, s), "memset geom header")) return e;
     StageScope prof(HGS_STAGE_PREPROCESS_FWD, s);
-    preprocess_fwd_kernel<<<a.nblocks, kPreprocThreads, 0, s>>>(a);
+    preprocess_fwd_kernel<false><<<a.nblocks, kPreprocThreads, 0, s>>>(a);
     return check_cuda(cudaGetLastError(), "preprocess_fwd launch");
+}
+
+int launch_strand_preprocess_fwd(const hgs_raster_params* prm, const hgs_strand_inputs* in, const GeomLayout& g,
+                                 int32_t* radii, cudaStream_t s) {
+    PreArgs a;
+    a.P = prm->P; a.D = prm->D; a.M = prm->M; a.W = prm->width; a.H = prm->height;
+    a.channels = prm->channels; a.cstride = g.cstride;
+    a.tan_fovx = prm->tan_fovx; a.tan_fovy = prm->tan_fovy;
+    a.focal_y = prm->height / (2.0f * prm->tan_fovy);
+    a.focal_x = prm->width / (2.0f * prm->tan_fovx);
+    a.scale_modifier = prm->scale_modifier;
+    a.grid_x = (prm->width + HGS_TILE - 1) / HGS_TILE;
+    a.grid_y = (prm->height + HGS_TILE - 1) / HGS_TILE;
+    a.means3D = nullptr; a.scales = nullptr; a.rotations = nullptr; a.opacities = nullptr;
+    a.shs = in->features; a.cov3D_precomp = nullptr; a.colors_precomp = nullptr;
+    a.viewmatrix = in->viewmatrix; a.projmatrix = in->projmatrix; a.cam_pos = in->cam_pos;
+    a.radii = radii; a.g = g;
+    a.nblocks = (prm->P + kPreprocThreads - 1) / kPreprocThreads;
+    a.endpoints = in->endpoints; a.pairs = (const long long*)in->endpoint_pairs; a.width = in->width;
+    a.opacity_logit = in->opacity_logit; a.mask_logit = in->mask_logit;
+    if (int e = check_cuda(cudaMemsetAsync(g.hdr, 0, g.clear_bytes, s), "memset geom header")) return e;
+    StageScope prof(HGS_STAGE_PREPROCESS_FWD, s);
+    preprocess_fwd_kernel<true><<<a.nblocks, kPreprocThreads, 0, s>>>(a);
+    return check_cuda(cudaGetLastError(), "strand preprocess_fwd launch");
 }
 
 int launch_preprocess_bwd(const hgs_raster_params* prm, const hgs_raster_inputs* in, const GeomLayout& g,
@@ -742,9 +901,34 @@ int launch_preprocess_bwd(const hgs_raster_params* prm, const hgs_raster_inputs*
     a.dL_dmean2D = gr->dL_dmean2D; a.dL_dconic = gr->dL_dconic; a.dL_dcolor = gr->dL_dcolor;
     a.dL_dmean3D = gr->dL_dmean3D; a.dL_dcov3D = gr->dL_dcov3D; a.dL_dsh = gr->dL_dsh;
     a.dL_dscale = gr->dL_dscale; a.dL_drot = gr->dL_drot;
+    a.tiles_touched = g.tiles_touched; a.endpoints = nullptr; a.pairs = nullptr; a.width = nullptr;
+    a.opacity_logit = nullptr; a.mask_logit = nullptr; a.dL_dopacity = nullptr; a.dL_dendpoints = nullptr;
+    a.dL_dwidth = nullptr; a.dL_dopacity_logit = nullptr; a.dL_dmask_logit = nullptr;
     StageScope prof(HGS_STAGE_PREPROCESS_BWD, s);
-    preprocess_bwd_kernel<<<(prm->P + 255) / 256, 256, 0, s>>>(a);
+    preprocess_bwd_kernel<false><<<(prm->P + 255) / 256, 256, 0, s>>>(a);
     return check_cuda(cudaGetLastError(), "preprocess_bwd launch");
+}
+
+int launch_strand_preprocess_bwd(const hgs_raster_params* prm, const hgs_strand_inputs* in, const GeomLayout& g,
+                                 const hgs_strand_grads* gr, cudaStream_t s) {
+    PreBwdArgs a;
+    a.P = prm->P; a.D = prm->D; a.M = prm->M; a.channels = prm->channels;
+    a.tan_fovx = prm->tan_fovx; a.tan_fovy = prm->tan_fovy;
+    a.focal_y = prm->height / (2.0f * prm->tan_fovy);
+    a.focal_x = prm->width / (2.0f * prm->tan_fovx);
+    a.scale_modifier = prm->scale_modifier;
+    a.means3D = nullptr; a.radii = nullptr; a.shs = in->features; a.clamped = g.clamped;
+    a.scales = nullptr; a.rotations = nullptr; a.cov3D_precomp = nullptr;
+    a.viewmatrix = in->viewmatrix; a.projmatrix = in->projmatrix; a.cam_pos = in->cam_pos;
+    a.dL_dmean2D = gr->dL_dmean2D; a.dL_dconic = gr->dL_dconic; a.dL_dcolor = gr->dL_dcolor;
+    a.dL_dmean3D = nullptr; a.dL_dcov3D = nullptr; a.dL_dsh = gr->dL_dfeatures; a.dL_dscale = nullptr; a.dL_drot = nullptr;
+    a.tiles_touched = g.tiles_touched; a.endpoints = in->endpoints; a.pairs = (const long long*)in->endpoint_pairs;
+    a.width = in->width; a.opacity_logit = in->opacity_logit; a.mask_logit = in->mask_logit;
+    a.dL_dopacity = gr->dL_dopacity; a.dL_dendpoints = gr->dL_dendpoints; a.dL_dwidth = gr->dL_dwidth;
+    a.dL_dopacity_logit = gr->dL_dopacity_logit; a.dL_dmask_logit = gr->dL_dmask_logit;
+    StageScope prof(HGS_STAGE_PREPROCESS_BWD, s);
+    preprocess_bwd_kernel<true><<<(prm->P + 255) / 256, 256, 0, s>>>(a);
+    return check_cuda(cudaGetLastError(), "strand preprocess_bwd launch");
 }
 
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s) {

@@ -35,6 +35,17 @@ class RasterGrads(ctypes.Structure):
                                         "dL_dcov3D", "dL_dsh", "dL_dscale", "dL_drot")]
 
 
+class StrandInputs(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("background", "endpoints", "endpoint_pairs", "width", "opacity_logit",
+                                        "mask_logit", "features", "viewmatrix", "projmatrix", "cam_pos")] + \
+               [("num_endpoints", c_int64)]
+
+
+class StrandGrads(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("dL_dmean2D", "dL_dconic", "dL_dopacity", "dL_dcolor", "dL_dendpoints",
+                                        "dL_dwidth", "dL_dopacity_logit", "dL_dmask_logit", "dL_dfeatures")]
+
+
 ALLOC_FN = ctypes.CFUNCTYPE(c_void_p, c_void_p, c_size_t)
 
 _lib = None
@@ -87,6 +98,16 @@ def load():
     lib.hgs_state_view.restype = c_int64
     lib.hgs_state_view.argtypes = [c_int, P(RasterParams), P(RasterInputs), c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p]
+    lib.hgs_strands_forward_stage_a.restype = c_int
+    lib.hgs_strands_forward_stage_a.argtypes = [P(RasterParams), P(StrandInputs), c_void_p, c_void_p, c_void_p]
+    lib.hgs_strands_forward_stage_b.restype = c_int
+    lib.hgs_strands_forward_stage_b.argtypes = [P(RasterParams), P(StrandInputs), c_void_p, c_void_p, c_void_p, c_int64,
+                                                c_void_p, c_void_p]
+    lib.hgs_strands_backward.restype = c_int
+    lib.hgs_strands_backward.argtypes = [P(RasterParams), P(StrandInputs), c_int64, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, P(StrandGrads), c_void_p]
+    lib.hgs_debug_set_stats.restype = c_int
+    lib.hgs_debug_set_stats.argtypes = [c_void_p]
     lib.hgs_profile_enable.restype = c_int
     lib.hgs_profile_enable.argtypes = [c_int]
     lib.hgs_profile_collect.restype = c_int

@@ -1,0 +1,148 @@
+"""Fused strand render path (SURVEY.md §8f rows N1 + N2): what Hair-GS computes per training view with THREE render()
+calls — RGB via SH, mask via override_color=get_mask.repeat(1,3), orientation via override_color=get_orientation
+(train.py:146-155, loss/losses.py:246-249,311-312,341-346) — plus the ~25 torch kernels of the strand getters
+(scene/hair_gaussian_model.py:134-206) per call, done here in ONE rasterization pass:
+
+  * the preprocess kernel derives the Gaussians from (endpoints, endpoint_pairs, width) and applies the sigmoid /
+    exp activations itself (hgs_strands_forward_stage_a);
+  * geometry (cull, scan, keys, sort, ranges) runs once and seven channels are composited together;
+  * one backward pass returns gradients w.r.t. the RAW parameters (end points scattered to their joints, width,
+    opacity / mask logits, SH features) and the screen-space mean gradients Hair-GS uses for densification statistics.
+
+Equivalence with the three-pass drop-in path is tested to the north_star tolerances
+(tests/test_gpu_parity.py::test_fused_strands_equals_three_pass_dropin).
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib as L
+from diff_gaussian_rasterization import _C as _dgr  # capacity hints / pinned read-back ring are shared
+
+
+def _prep(endpoints, endpoint_pairs, width, opacity_logit, mask_logit, features, s):
+    if not endpoints.is_cuda:
+        raise L.HgsError("endpoints must be a CUDA tensor: this rasterizer has no CPU path")
+    dev = endpoints.device
+    if endpoint_pairs.dtype != torch.int64 or not endpoint_pairs.is_cuda:
+        raise L.HgsError("endpoint_pairs must be a CUDA int64 tensor [P,2]")
+    keep = dict(endpoints=L.f32c(endpoints, "endpoints", dev), width=L.f32c(width, "width", dev),
+                opacity_logit=L.f32c(opacity_logit, "opacity_logit", dev), mask_logit=L.f32c(mask_logit, "mask_logit", dev),
+                features=L.f32c(features, "features", dev), background=L.f32c(s["bg"], "bg", dev),
+                viewmatrix=L.f32c(s["viewmatrix"], "viewmatrix", dev), projmatrix=L.f32c(s["projmatrix"], "projmatrix", dev),
+                cam_pos=L.f32c(s["campos"], "campos", dev), endpoint_pairs=endpoint_pairs.contiguous())
+    if keep["background"] is None or keep["background"].numel() != 7:
+        raise L.HgsError("the fused strand pass needs a 7-channel background (rgb, mask, orientation)")
+    P = endpoint_pairs.shape[0]
+    M = features.shape[1] if features.numel() else 0
+    prm = L.RasterParams(P=P, D=int(s["sh_degree"]), M=int(M), width=int(s["image_width"]), height=int(s["image_height"]),
+                         channels=7, tan_fovx=float(s["tanfovx"]), tan_fovy=float(s["tanfovy"]),
+                         scale_modifier=float(s["scale_modifier"]), prefiltered=0, debug=int(bool(s["debug"])))
+    inp = L.StrandInputs(num_endpoints=int(endpoints.shape[0]), **{k: L.ptr(v) for k, v in keep.items()})
+    return dev, prm, inp, keep
+
+
+class _RasterizeStrands(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, endpoints, endpoint_pairs, width, opacity_logit, mask_logit, features, means2D, settings):
+        lib = L.load()
+        dev, prm, inp, keep = _prep(endpoints, endpoint_pairs, width, opacity_logit, mask_logit, features, settings)
+        P, H, W = prm.P, prm.height, prm.width
+        u8 = dict(dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            stream = L.stream_ptr(dev)
+            image = torch.empty((7, H, W), dtype=torch.float32, device=dev)
+            radii = torch.empty((P,), dtype=torch.int32, device=dev)
+            geom = torch.empty((lib.hgs_geom_bytes(P, 7),), **u8)
+            img = torch.empty((lib.hgs_image_bytes(W, H),), **u8)
+            L.check(lib.hgs_strands_forward_stage_a(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
+                                                    radii.data_ptr(), stream), "strands stage A")
+            host = _dgr._pinned_triplet()
+            L.check(lib.hgs_forward_read_num_rendered(geom.data_ptr(), P, host.data_ptr(), stream), "read num_rendered")
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(dev))
+            key = (dev.index, P, H, W, 7)
+            cap = _dgr._capacity_hint.get(key) if _dgr.SYNC_FREE else None
+            binning = None
+            if cap is not None:
+                binning = torch.empty((lib.hgs_binning_bytes(cap, 7),), **u8)
+                L.check(lib.hgs_strands_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
+                                                        binning.data_ptr(), img.data_ptr(), cap, image.data_ptr(), stream),
+                        "strands stage B")
+            ready.synchronize()
+            N, overflow = int(host[0]), int(host[2])
+            if overflow != 0 or N < 0:
+                raise L.HgsError("instance count overflows int32")
+            if cap is None or N > cap:
+                cap = N
+                binning = torch.empty((lib.hgs_binning_bytes(N, 7),), **u8)
+                L.check(lib.hgs_strands_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
+                                                        binning.data_ptr() if N > 0 else None, img.data_ptr(), N,
+                                                        image.data_ptr(), stream), "strands stage B")
+            _dgr._capacity_hint[key] = ((int(N * 1.25) + 4096 + 4095) // 4096) * 4096
+        ctx.settings, ctx.capacity, ctx.num_rendered = settings, cap, N
+        ctx.save_for_backward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit, features, geom, binning, img)
+        ctx.mark_non_differentiable(radii)
+        return image, radii
+
+    @staticmethod
+    def backward(ctx, grad_image, _):
+        lib = L.load()
+        endpoints, endpoint_pairs, width, opacity_logit, mask_logit, features, geom, binning, img = ctx.saved_tensors
+        dev, prm, inp, keep = _prep(endpoints, endpoint_pairs, width, opacity_logit, mask_logit, features, ctx.settings)
+        P, M, E = prm.P, prm.M, endpoints.shape[0]
+        f32 = dict(dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            dpix = L.f32c(grad_image, "grad_image", dev)
+            acc = torch.empty((P * 15,), **f32)  # mean2D 3 | conic 4 | opacity 1 | colour 7 : one memset in the library
+            d_mean2D = acc[:3 * P].view(P, 3)
+            out = torch.empty((3 * E + 3 * P + 3 * M * P,), **f32)
+            d_end = out[:3 * E].view(E, 3)
+            d_width = out[3 * E:3 * E + P].view(P, 1)
+            d_opac = out[3 * E + P:3 * E + 2 * P].view(P, 1)
+            d_mask = out[3 * E + 2 * P:3 * E + 3 * P].view(P, 1)
+            d_feat = out[3 * E + 3 * P:].view(P, M, 3)
+            grads = L.StrandGrads(dL_dmean2D=acc.data_ptr(), dL_dconic=acc[3 * P:].data_ptr(),
+                                  dL_dopacity=acc[7 * P:].data_ptr(), dL_dcolor=acc[8 * P:].data_ptr(),
+                                  dL_dendpoints=d_end.data_ptr(), dL_dwidth=d_width.data_ptr(),
+                                  dL_dopacity_logit=d_opac.data_ptr(), dL_dmask_logit=d_mask.data_ptr(),
+                                  dL_dfeatures=d_feat.data_ptr())
+            L.check(lib.hgs_strands_backward(ctypes.byref(prm), ctypes.byref(inp), int(ctx.capacity), geom.data_ptr(),
+                                             L.ptr(binning), img.data_ptr(), dpix.data_ptr(), ctypes.byref(grads),
+                                             L.stream_ptr(dev)), "strands backward")
+        return (d_end, None, d_width.view_as(width), d_opac.view_as(opacity_logit), d_mask.view_as(mask_logit), d_feat,
+                d_mean2D, None)
+
+
+def rasterize_strands(endpoints, endpoint_pairs, width, opacity_logit, mask_logit, features, means2D, *, image_height,
+                      image_width, tanfovx, tanfovy, bg, scale_modifier, viewmatrix, projmatrix, sh_degree, campos,
+                      debug=False):
+    """-> (image[7,H,W] = rgb | mask | orientation, radii[P])."""
+    settings = dict(image_height=image_height, image_width=image_width, tanfovx=tanfovx, tanfovy=tanfovy, bg=bg,
+                    scale_modifier=scale_modifier, viewmatrix=viewmatrix, projmatrix=projmatrix, sh_degree=sh_degree,
+                    campos=campos, debug=debug)
+    return _RasterizeStrands.apply(endpoints, endpoint_pairs, width, opacity_logit, mask_logit, features, means2D,
+                                   settings)
+
+
+def render_strands(viewpoint_camera, pc, bg_color, scaling_modifier=1.0, debug=False):
+    """One-pass counterpart of the three render() calls of a Hair-GS Stage-III iteration.  `pc` is a
+    HairGaussianModel-like object (hairgs_b200.models.StrandModel): _endpoints, endpoint_pairs, _width, _opacity, _mask,
+    get_features, active_sh_degree.  bg_color: [7].  Returns render / mask / orientation images plus the usual
+    viewspace_points / visibility_filter / radii entries of gaussian_renderer.render()."""
+    P = pc.endpoint_pairs.shape[0]
+    screenspace_points = torch.zeros((P, 3), dtype=pc._endpoints.dtype, requires_grad=True, device=pc._endpoints.device) + 0
+    try:
+        screenspace_points.retain_grad()
+    except Exception:
+        pass
+    image, radii = rasterize_strands(
+        pc._endpoints, pc.endpoint_pairs, pc._width, pc._opacity, pc._mask, pc.get_features, screenspace_points,
+        image_height=int(viewpoint_camera.image_height), image_width=int(viewpoint_camera.image_width),
+        tanfovx=math.tan(viewpoint_camera.FoVx * 0.5), tanfovy=math.tan(viewpoint_camera.FoVy * 0.5), bg=bg_color,
+        scale_modifier=scaling_modifier, viewmatrix=viewpoint_camera.world_view_transform,
+        projmatrix=viewpoint_camera.full_proj_transform, sh_degree=pc.active_sh_degree,
+        campos=viewpoint_camera.camera_center, debug=debug)
+    return {"render": image[0:3], "mask": image[3:4], "orientation": image[4:7], "image7": image,
+            "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii}

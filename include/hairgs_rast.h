@@ -93,6 +93,47 @@ typedef struct hgs_raster_grads {
     float* dL_drot;      /* [P,4] */
 } hgs_raster_grads;
 
+/* ---- Fused strand-aligned entry (SURVEY.md §8f rows N1 + N2; no single reference counterpart) ----------------
+ * One pass renders what Hair-GS obtains from three render() calls per training view (train.py:146-155,
+ * loss/losses.py:246-249,311-312,341-346): channels 0-2 SH colour, 3 mask = sigmoid(mask_logit), 4-6 the world-space
+ * unit direction of the segment.  The Gaussians are derived inside the preprocess kernel from the segment end points
+ * exactly as HairGaussianModel's getters do (scene/hair_gaussian_model.py:134-206): mean = (e0+e1)/2,
+ * sigma_x = max(|e1-e0|/2 * 0.51021, 1e-7), sigma_yz = exp(width), x axis rotated onto the segment,
+ * opacity = sigmoid(opacity_logit); the backward returns gradients w.r.t. the RAW parameters. prm->channels must be 7. */
+typedef struct hgs_strand_inputs {
+    const float* background;       /* [7] */
+    const float* endpoints;        /* [E,3] joints */
+    const int64_t* endpoint_pairs; /* [P,2] */
+    const float* width;            /* [P] log sigma_yz */
+    const float* opacity_logit;    /* [P] */
+    const float* mask_logit;       /* [P] */
+    const float* features;         /* [P,M,3] SH coefficients (dc first) */
+    const float* viewmatrix;       /* [16] */
+    const float* projmatrix;       /* [16] */
+    const float* cam_pos;          /* [3] */
+    int64_t num_endpoints;         /* E */
+} hgs_strand_inputs;
+
+typedef struct hgs_strand_grads {
+    float* dL_dmean2D;        /* [P,3] screen-space mean gradients (densification statistics), z = 0 */
+    float* dL_dconic;         /* [P,4] scratch */
+    float* dL_dopacity;       /* [P]   scratch (w.r.t. activated opacity) */
+    float* dL_dcolor;         /* [P,7] scratch */
+    float* dL_dendpoints;     /* [E,3] */
+    float* dL_dwidth;         /* [P] */
+    float* dL_dopacity_logit; /* [P] */
+    float* dL_dmask_logit;    /* [P] */
+    float* dL_dfeatures;      /* [P,M,3] */
+} hgs_strand_grads;
+
+int hgs_strands_forward_stage_a(const hgs_raster_params* prm, const hgs_strand_inputs* in, void* geom_ws,
+                                int32_t* radii, void* stream);
+int hgs_strands_forward_stage_b(const hgs_raster_params* prm, const hgs_strand_inputs* in, void* geom_ws,
+                                void* binning_ws, void* image_ws, int64_t capacity, float* out_color, void* stream);
+int hgs_strands_backward(const hgs_raster_params* prm, const hgs_strand_inputs* in, int64_t capacity,
+                         const void* geom_ws, const void* binning_ws, const void* image_ws, const float* dL_dpix,
+                         const hgs_strand_grads* grads, void* stream);
+
 int hgs_abi_version(void);
 const char* hgs_last_error(void);
 
