@@ -298,9 +298,12 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[VP], uint32_t 
 //      Compared with reducing every candidate across the 32 pixel lanes (16 shuffles + ~50 ALU ops each), this
 //      cuts the instruction count per candidate roughly in half and the atomics per warp 4x
 //      (profiles/r1_composite.md).
+template <int QN>
+__device__ __forceinline__ uint32_t qwrap(uint32_t x) { return x >= (uint32_t)QN ? x - QN : x; }
+
 template <int CS>
 struct BwdWarpSmem {
-    static constexpr int QN = 64;  // candidate queue capacity (32 new + < 8 left over), power of two
+    static constexpr int QN = 40;  // candidate queue capacity: 32 new + < 8 left over (ring, wrapped by subtraction)
     static constexpr int GR = 8;   // candidates per group
     float4 q_lo[QN];
     float4 q_hi[QN];
@@ -312,7 +315,7 @@ struct BwdWarpSmem {
 };
 
 template <int C, int CS>
-__global__ void __launch_bounds__(256) composite_bwd_kernel(
+__global__ void __launch_bounds__(256, 3) composite_bwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
     const uint32_t* __restrict__ point_list, int W, int H,
     const float* __restrict__ bg_color, const float4* __restrict__ pk_lo, const float4* __restrict__ pk_hi,
@@ -349,11 +352,10 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
     if (total == 0) return;
     const int nchunks = (total + 31) >> 5;
 
-    float accum_rec[C], dL_dpixel[C], last_color[C];
+    float accum_rec[C], dL_dpixel[C];
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) {
         accum_rec[ch] = 0.f;
-        last_color[ch] = 0.f;
         dL_dpixel[ch] = inside ? dL_dpixels[(size_t)ch * H * W + pix_id] : 0.f;
     }
     {
@@ -363,7 +365,6 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
         ws.dpix[lane * (CS / 4)] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
         if (CS > 4) ws.dpix[lane * (CS / 4) + 1] = make_float4(tmp[4], tmp[5], tmp[6], tmp[7]);
     }
-    float last_alpha = 0.f;
     float bg_dot_dpixel = 0;
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) bg_dot_dpixel += bg_color[ch] * dL_dpixel[ch];
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
     auto process_group = [&](const uint32_t n) {
         // ---- phase 1: lanes = pixels, candidates in list order ------------------------------------------
         for (uint32_t g = 0; g < n; ++g) {
-            const uint32_t slot = (qhead + g) & (QN - 1);
+            const uint32_t slot = qwrap<QN>(qhead + g);
             const float4 glo = ws.q_lo[slot];
             const float4 ghi = ws.q_hi[slot];
             const int pos = (int)ws.q_ip[slot].y;
@@ -392,20 +393,23 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
             const uint32_t vm = __ballot_sync(0xffffffffu, valid);
             if (lane == 0) ws.vmask[g] = vm;
             if (valid) {
-                T = T / (1.f - alpha);
+                // one reciprocal serves T/(1-alpha) and T_final/(1-alpha) (backward_distwar.cu:960,991 divide twice)
+                const float om = 1.f - alpha;
+                const float rcp = 1.f / om;
+                T = T * rcp;
                 const float dchannel_dcolor = alpha * T;
                 float dL_dalpha = 0.0f;
                 const float* col = reinterpret_cast<const float*>(&ws.q_col[slot * (CS / 4)]);
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) {
                     const float cc = col[ch];
-                    accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-                    last_color[ch] = cc;
                     dL_dalpha += (cc - accum_rec[ch]) * dL_dpixel[ch];
+                    // colour accumulated behind the NEXT (nearer) instance; the reference performs this same update
+                    // lazily at the start of the next iteration from (last_alpha, last_color) (:972-973)
+                    accum_rec[ch] = alpha * cc + om * accum_rec[ch];
                 }
                 dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                dL_dalpha += (-T_final * rcp) * bg_dot_dpixel;
                 ws.slab[g * 33 + lane] = make_float4(G, dL_dalpha, dchannel_dcolor, 0.f);
             }
         }
@@ -415,7 +419,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
 #pragma unroll
         for (int k = 0; k < 6 + C; ++k) acc[k] = 0.f;
         uint32_t my_vm = 0;
-        const uint32_t slot = (qhead + my_g) & (QN - 1);
+        const uint32_t slot = qwrap<QN>(qhead + my_g);
         if (my_g < n) {
             my_vm = ws.vmask[my_g];
             uint32_t m = (my_vm >> (my_q * 8)) & 0xffu;
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
         const uint32_t bits = __ballot_sync(0xffffffffu, cand);
         if (!bits) continue;
         if (cand) {
-            const uint32_t slot = (qhead + qcount + __popc(bits & lt_mask)) & (QN - 1);
+            const uint32_t slot = qwrap<QN>(qhead + qcount + __popc(bits & lt_mask));
             ws.q_lo[slot] = lo;
             ws.q_hi[slot] = hi;
             ws.q_col[slot * (CS / 4)] = c0;
@@ -507,7 +511,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
         __syncwarp();
         while (qcount >= (uint32_t)GR) {
             process_group(GR);
-            qhead = (qhead + GR) & (QN - 1);
+            qhead = qwrap<QN>(qhead + GR);
             qcount -= GR;
         }
     }

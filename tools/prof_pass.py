@@ -20,7 +20,10 @@ if use_ref:
 else:
     import diff_gaussian_rasterization._C as backend
 h = bench.Harness(bench.WORKLOADS[name], dev, backend, 1, 0)
+fused = len(sys.argv) > 3 and sys.argv[3] == "fused"
+if fused:
+    h.setup_fused()
 for it in range(iters):
-    h.step_resident(it)
+    (h.step_resident_fused if fused else h.step_resident)(it)
 torch.cuda.synchronize()
 print("done", name, "P", h.P, "N", h.last_N)
