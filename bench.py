@@ -381,8 +381,9 @@ def algorithmic_bytes(stage, P, N, HW, T, M, D, sh_mode, C=3):
         return 8 * N
     if stage == "sort_onesweep":
         return 24 * N  # one pass: read + write of (u64 key, u32 value)
-    if stage == "tile_ranges":
-        return 8 * N + 8 * T
+    if stage == "tile_ranges":  # finalize_sorted: keys + ids read, 32 B record + colour gathered and re-written sorted
+        cs = 16 if C <= 4 else 32
+        return 12 * N + 2 * (32 + cs) * N + 12 * T
     if stage == "composite_fwd":
         return (28 + 4 * C) * N + (8 + 4 * C) * HW
     if stage == "composite_bwd":

@@ -172,6 +172,9 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
     }
 
     // ---- per-warp ranking with match.any ---------------------------------------------------------
+    // One shared-memory atomic per distinct digit per round hands every peer group its running count: no
+    // __syncwarp between rounds, so the 16 rounds pipeline instead of serialising on LDS->STS round trips.
+    // (Atomics of one warp to one address are performed in program order, which is what stability needs.)
     uint32_t rank[kSortItems];
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t* wh = sm.warp_hist[warp];
@@ -179,12 +182,12 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
     for (int r = 0; r < kSortItems; ++r) {
         const uint32_t d = (uint32_t)(key[r] >> shift) & 0xffu;
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const uint32_t prev = wh[d];
-        __syncwarp();
         const uint32_t lrank = __popc(peers & lt_mask);
-        if (lrank == 0) wh[d] = prev + __popc(peers);
-        __syncwarp();
-        rank[r] = prev + lrank;
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lrank == 0) old = atomicAdd(&wh[d], (uint32_t)__popc(peers));
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[r] = old + lrank;
     }
     __syncthreads();
 

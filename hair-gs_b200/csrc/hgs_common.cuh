@@ -258,6 +258,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// non-blocking prefetch of the cache line(s) holding [p, p+bytes): lets a thread start every input stream it will
+// need before the first data-dependent early-out (otherwise each cull test exposes one full DRAM latency)
+__device__ __forceinline__ void prefetch_l1(const void* p, int bytes = 1) {
+    const char* c = (const char*)p;
+    for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L1 [%0];\n" ::"l"(c + o));
+    if (bytes > 1) asm volatile("prefetch.global.L1 [%0];\n" ::"l"(c + bytes - 1));
+}
+
 // streaming 128-bit loads (read-once data: keep it out of L1)
 __device__ __forceinline__ float4 ldg_stream4(const float4* p) {
     float4 r;

@@ -238,6 +238,20 @@ __global__ void __launch_bounds__(kPreprocThreads) preprocess_fwd_kernel(const P
     uint32_t touched = 0;
     int radius_i = 0;
     if (idx < a.P) {
+        // start every input stream now: the cull / degenerate early-outs below would otherwise serialise them
+        if (kStrand) {
+            prefetch_l1(a.width + idx);
+            prefetch_l1(a.opacity_logit + idx);
+            prefetch_l1(a.mask_logit + idx);
+            prefetch_l1(a.shs + (size_t)idx * a.M * 3, a.M * 12);
+        } else {
+            if (a.scales) prefetch_l1(a.scales + 3 * (size_t)idx, 12);
+            if (a.rotations) prefetch_l1(a.rotations + 4 * (size_t)idx);
+            if (a.cov3D_precomp) prefetch_l1(a.cov3D_precomp + 6 * (size_t)idx, 24);
+            prefetch_l1(a.opacities + idx);
+            if (a.colors_precomp) prefetch_l1(a.colors_precomp + (size_t)idx * a.channels, a.channels * 4);
+            else prefetch_l1(a.shs + (size_t)idx * a.M * 3, a.M * 12);
+        }
         do {
             StrandGeom sg;
             float3 p_orig;
@@ -449,6 +463,27 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreBwdArgs a)
     if (idx >= a.P) return;
     const bool has_sh = (a.shs != nullptr) && a.M > 0;
     const bool has_sr = !kStrand && (a.scales != nullptr);
+
+    // start every input stream before the visibility test
+    prefetch_l1(a.dL_dconic + 4 * (size_t)idx);
+    prefetch_l1(a.dL_dmean2D + 3 * (size_t)idx, 12);
+    prefetch_l1(a.dL_dcolor + (size_t)idx * a.channels, a.channels * 4);
+    if (has_sh) {
+        prefetch_l1(a.shs + (size_t)idx * a.M * 3, a.M * 12);
+        prefetch_l1(a.clamped + idx);
+    }
+    if (kStrand) {
+        prefetch_l1(a.pairs + 2 * (size_t)idx);
+        prefetch_l1(a.width + idx);
+        prefetch_l1(a.opacity_logit + idx);
+        prefetch_l1(a.mask_logit + idx);
+        prefetch_l1(a.dL_dopacity + idx);
+    } else {
+        prefetch_l1(a.means3D + 3 * (size_t)idx, 12);
+        if (a.scales) prefetch_l1(a.scales + 3 * (size_t)idx, 12);
+        if (a.rotations) prefetch_l1(a.rotations + 4 * (size_t)idx);
+        if (a.cov3D_precomp) prefetch_l1(a.cov3D_precomp + 6 * (size_t)idx, 24);
+    }
 
     if (kStrand) {
         if (!(a.tiles_touched[idx] > 0)) {
