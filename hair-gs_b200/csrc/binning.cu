@@ -113,10 +113,8 @@ __global__ void __launch_bounds__(256) radix_histogram_kernel(const uint64_t* __
 }
 
 struct OnesweepSmem {
-    union {
-        uint64_t keys[kSortTile];
-        uint32_t vals[kSortTile];
-    } u;
+    uint64_t keys[kSortTile];
+    uint32_t vals[kSortTile];
     uint32_t warp_hist[kSortThreads / 32][kRadix];
     uint32_t excl[kRadix];   // block-local exclusive digit offsets
     uint32_t gbase[kRadix];  // global position of local sorted index 0 of each digit (minus excl)
@@ -204,14 +202,33 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
     if (tile == 0) st_relaxed_u32(my_status, kStFlagIncl | block_count);
     else st_relaxed_u32(my_status, kStFlagAgg | block_count);
 
+    // values: issue the loads now, they are consumed after the key scatter
+    uint32_t val[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t li = wbase + r * 32;
+        val[r] = (li < nvalid) ? vals_in[base + li] : 0u;
+    }
+
     const uint32_t local_excl = block_excl_scan_256(block_count, sm.scan_tmp);
     const uint32_t gexcl = block_excl_scan_256(ghist[tid], sm.scan_tmp);
+    sm.excl[tid] = local_excl;
+    __syncthreads();
 
+    // ---- scatter keys AND values into block-sorted order in shared memory: needs only block-local offsets, so it
+    //      overlaps the predecessors' chain latency instead of waiting behind the look-back ------------------------
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t d = (uint32_t)(key[r] >> shift) & 0xffu;
+        const uint32_t pos = sm.excl[d] + wh[d] + rank[r];
+        sm.keys[pos] = key[r];
+        sm.vals[pos] = val[r];
+    }
+
+    // ---- decoupled look-back: kLook predecessors per L2 round trip --------------------------------------------------
     uint32_t prev_sum = 0;
     if (tile > 0) {
-        // walk back over the predecessors kLook at a time: the status loads of one round are independent, so a
-        // round costs one L2 round trip instead of kLook of them (the serial walk dominated the pass at N ~ 2M)
-        constexpr int kLook = 8;
+        constexpr int kLook = 16;
         int t = (int)tile - 1;
         bool found = false;
         while (!found) {
@@ -234,42 +251,20 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
         }
         st_relaxed_u32(my_status, kStFlagIncl | ((prev_sum + block_count) & kStValMask));
     }
-    sm.excl[tid] = local_excl;
     sm.gbase[tid] = gexcl + prev_sum - local_excl;
     __syncthreads();
 
-    // ---- scatter keys into block-sorted order in shared memory, then coalesced to global ----------
-    uint32_t pos[kSortItems];
-#pragma unroll
-    for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t d = (uint32_t)(key[r] >> shift) & 0xffu;
-        pos[r] = sm.excl[d] + wh[d] + rank[r];
-        sm.u.keys[pos[r]] = key[r];
-    }
-    __syncthreads();
-    uint32_t gidx[kSortItems];
+    // ---- coalesced runs out to global -------------------------------------------------------------------------------
 #pragma unroll
     for (int k = 0; k < kSortItems; ++k) {
         const uint32_t li = tid + k * kSortThreads;
-        gidx[k] = 0xffffffffu;
         if (li < nvalid) {
-            const uint64_t kk = sm.u.keys[li];
+            const uint64_t kk = sm.keys[li];
             const uint32_t d = (uint32_t)(kk >> shift) & 0xffu;
-            gidx[k] = sm.gbase[d] + li;
-            keys_out[gidx[k]] = kk;
+            const uint32_t gi = sm.gbase[d] + li;
+            keys_out[gi] = kk;
+            vals_out[gi] = sm.vals[li];
         }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t li = wbase + r * 32;
-        if (li < nvalid) sm.u.vals[pos[r]] = vals_in[base + li];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kSortItems; ++k) {
-        const uint32_t li = tid + k * kSortThreads;
-        if (li < nvalid) vals_out[gidx[k]] = sm.u.vals[li];
     }
 }
 
