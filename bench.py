@@ -375,6 +375,8 @@ def algorithmic_bytes(stage, P, N, HW, T, M, D, sh_mode, C=3):
     """SURVEY.md §8(d) compulsory traffic per launch of each stage."""
     if stage == "preprocess_fwd":
         return P * (44 + (12 * (D + 1) ** 2 if sh_mode else 12) + 8) + P * (28 + 12)
+    if stage == "tile_scan":
+        return 8 * P
     if stage == "emit_keys":
         return 20 * P + 12 * N
     if stage == "sort_histogram":
@@ -469,10 +471,10 @@ def main():
     import ctypes
     ms_res = timed_loop(torch, h.step_resident, args.steps, args.warmup, world, dev, flush)
     # kernels of libhairgs_rast.so launched per step (the library counts its own launches)
-    launches = (ctypes.c_int64 * 10)()
+    launches = (ctypes.c_int64 * 16)()
     lib.hgs_profile_collect(None, launches)  # reset
     h.step_resident(0)
-    launches = (ctypes.c_int64 * 10)()
+    launches = (ctypes.c_int64 * 16)()
     lib.hgs_profile_collect(None, launches)
     launches_per_step = int(sum(launches))
 
@@ -485,10 +487,10 @@ def main():
         ms_e2e_3pass = ms_e2e
         h.setup_fused()
         ms_res = timed_loop(torch, h.step_resident_fused, args.steps, args.warmup, world, dev, flush)
-        launches = (ctypes.c_int64 * 10)()
+        launches = (ctypes.c_int64 * 16)()
         lib.hgs_profile_collect(None, launches)
         h.step_resident_fused(0)
-        launches = (ctypes.c_int64 * 10)()
+        launches = (ctypes.c_int64 * 16)()
         lib.hgs_profile_collect(None, launches)
         launches_per_step = int(sum(launches))
         h.setup_e2e(fused=True)
@@ -518,12 +520,12 @@ def main():
         C_prof = 7 if can_fuse else 3
         for it in range(prof_steps):
             prof_step(it)
-        ms = (ctypes.c_double * 10)()
-        cnt = (ctypes.c_int64 * 10)()
+        ms = (ctypes.c_double * 16)()
+        cnt = (ctypes.c_int64 * 16)()
         lib.hgs_profile_collect(ms, cnt)
         lib.hgs_profile_enable(0)
         total = sum(ms)
-        for sidx in range(10):
+        for sidx in range(11):
             if cnt[sidx] == 0:
                 continue
             name = lib.hgs_stage_name(sidx).decode()

@@ -135,7 +135,7 @@ int hgs_profile_collect(double* ms, int64_t* launches) {
 const char* hgs_stage_name(int stage) {
     static const char* names[HGS_STAGE_COUNT] = {"preprocess_fwd", "emit_keys", "sort_histogram", "sort_onesweep",
                                                   "tile_ranges", "composite_fwd", "composite_bwd", "preprocess_bwd",
-                                                  "knn", "other"};
+                                                  "knn", "other", "tile_scan"};
     return (stage >= 0 && stage < HGS_STAGE_COUNT) ? names[stage] : "?";
 }
 

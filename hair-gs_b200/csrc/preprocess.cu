@@ -226,14 +226,7 @@ __device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long 
 
 template <bool kStrand>
 __global__ void __launch_bounds__(kPreprocThreads) preprocess_fwd_kernel(const PreArgs a) {
-    __shared__ uint32_t s_warp_sum[kPreprocThreads / 32];
-    __shared__ unsigned long long s_block_excl;
-
-    const int tid = threadIdx.x;
-    // Blocks are dispatched in blockIdx order, so a block only ever waits on predecessors that are already
-    // running or finished: the chained scan can use blockIdx directly (no ticket atomic + barrier at start-up).
-    const uint32_t bid = blockIdx.x;
-    const int idx = (int)(bid * kPreprocThreads + tid);
+    const int idx = (int)(blockIdx.x * kPreprocThreads + threadIdx.x);
 
     uint32_t touched = 0;
     int radius_i = 0;
@@ -338,63 +331,107 @@ __global__ void __launch_bounds__(kPreprocThreads) preprocess_fwd_kernel(const P
         a.g.tiles_touched[idx] = touched;
     }
 
-    // ---- block-wide inclusive scan of `touched` ------------------------------------------------
+}
+
+// ------------------------------------------------------------------------------------------------
+// tiles_touched -> inclusive offsets (replaces cub::DeviceScan::InclusiveSum, rasterizer_impl.cu:277)
+// ------------------------------------------------------------------------------------------------
+// Single-pass chained scan: 4096 values per block (16 per thread, 128-bit loads/stores), block aggregate published
+// to a status array, predecessors resolved by a warp-wide decoupled look-back in blockIdx order.  The grand total
+// lands in hdr->num_rendered so the host never needs it to launch the rest of the pass.  (A first version fused this
+// into preprocess_fwd; ncu showed the two block barriers it needs as that kernel's top stall — 14 warps per issue —
+// because every warp of the heavy kernel waited for the slowest one.  8 B/Gaussian of extra traffic is cheaper.)
+static constexpr int kScanThreads = 256;
+static constexpr int kScanItems = 16;
+static constexpr int kScanTile = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(int P, const uint32_t* __restrict__ touched,
+                                                                 uint32_t* __restrict__ offsets,
+                                                                 unsigned long long* __restrict__ scan_state,
+                                                                 GeomHeader* __restrict__ hdr, uint32_t nblocks) {
+    __shared__ uint32_t s_warp_sum[kScanThreads / 32];
+    __shared__ unsigned long long s_block_excl;
+    const int tid = threadIdx.x;
+    const uint32_t bid = blockIdx.x;
     const uint32_t lane = tid & 31, warp = tid >> 5;
-    uint32_t incl = touched;
+    const int base = (int)(bid * kScanTile) + tid * kScanItems;
+
+    uint32_t v[kScanItems];
+    if (base + kScanItems <= P) {
+#pragma unroll
+        for (int q = 0; q < kScanItems / 4; ++q) {
+            const uint4 t = reinterpret_cast<const uint4*>(touched + base)[q];
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) v[k] = (base + k < P) ? touched[base + k] : 0u;
+    }
+#pragma unroll
+    for (int k = 1; k < kScanItems; ++k) v[k] += v[k - 1];
+    uint32_t incl = v[kScanItems - 1];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= (uint32_t)o) incl += n;
     }
     if (lane == 31) s_warp_sum[warp] = incl;
     __syncthreads();
     uint32_t warp_excl = 0, block_total = 0;
 #pragma unroll
-    for (int w = 0; w < kPreprocThreads / 32; ++w) {
-        const uint32_t v = s_warp_sum[w];
-        if ((uint32_t)w < warp) warp_excl += v;
-        block_total += v;
+    for (int w = 0; w < kScanThreads / 32; ++w) {
+        const uint32_t x = s_warp_sum[w];
+        if ((uint32_t)w < warp) warp_excl += x;
+        block_total += x;
     }
-
-    // ---- chained scan across blocks (decoupled look-back, warp 0) ------------------------------
     if (warp == 0) {
         unsigned long long excl = 0;
         if (bid == 0) {
-            if (lane == 0) st_relaxed(&a.g.scan_state[0], kFlagIncl | (unsigned long long)block_total);
+            if (lane == 0) st_relaxed(&scan_state[0], kFlagIncl | (unsigned long long)block_total);
         } else {
-            if (lane == 0) st_relaxed(&a.g.scan_state[bid], kFlagAgg | (unsigned long long)block_total);
+            if (lane == 0) st_relaxed(&scan_state[bid], kFlagAgg | (unsigned long long)block_total);
             int look = (int)bid - 1;
             while (true) {
                 const int j = look - (int)lane;
-                unsigned long long w = (j >= 0) ? ld_relaxed(&a.g.scan_state[j]) : kFlagIncl;
+                unsigned long long w = (j >= 0) ? ld_relaxed(&scan_state[j]) : kFlagIncl;
                 while (__any_sync(0xffffffffu, (w >> 62) == 0)) {
-                    if ((w >> 62) == 0) w = ld_relaxed(&a.g.scan_state[j]);
+                    if ((w >> 62) == 0) w = ld_relaxed(&scan_state[j]);
                 }
                 const uint32_t incl_mask = __ballot_sync(0xffffffffu, (w >> 62) == 2);
-                unsigned long long v = w & kValMask;
+                unsigned long long x = w & kValMask;
                 if (incl_mask) {
                     const int first = __ffs(incl_mask) - 1;
-                    if ((int)lane > first) v = 0;
+                    if ((int)lane > first) x = 0;
                 }
 #pragma unroll
-                for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                excl += v;
+                for (int o = 16; o >= 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                excl += x;
                 if (incl_mask) break;
                 look -= 32;
             }
-            if (lane == 0) st_relaxed(&a.g.scan_state[bid], kFlagIncl | (excl + block_total));
+            if (lane == 0) st_relaxed(&scan_state[bid], kFlagIncl | (excl + block_total));
         }
         if (lane == 0) {
             s_block_excl = excl;
-            if (bid == a.nblocks - 1) {
+            if (bid == nblocks - 1) {
                 const unsigned long long total = excl + block_total;
-                a.g.hdr->num_rendered = (uint32_t)min(total, (unsigned long long)0xffffffffu);
-                if (total > 0x7fffffffull) a.g.hdr->overflow = 1;
+                hdr->num_rendered = (uint32_t)min(total, (unsigned long long)0xffffffffu);
+                if (total > 0x7fffffffull) hdr->overflow = 1;
             }
         }
     }
     __syncthreads();
-    if (idx < a.P) a.g.offsets[idx] = (uint32_t)(s_block_excl + warp_excl + incl);
+    const uint32_t thread_excl = (uint32_t)s_block_excl + warp_excl + (incl - v[kScanItems - 1]);
+    if (base + kScanItems <= P) {
+#pragma unroll
+        for (int q = 0; q < kScanItems / 4; ++q)
+            reinterpret_cast<uint4*>(offsets + base)[q] = make_uint4(thread_excl + v[4 * q], thread_excl + v[4 * q + 1],
+                                                                    thread_excl + v[4 * q + 2], thread_excl + v[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k)
+            if (base + k < P) offsets[base + k] = thread_excl + v[k];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -875,6 +912,13 @@ __global__ void view_cov3d_kernel(int P, const float* __restrict__ scales, const
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
+static int launch_tile_scan(int P, const GeomLayout& g, cudaStream_t s) {
+    const uint32_t nb = (uint32_t)((P + kScanTile - 1) / kScanTile);
+    StageScope prof(HGS_STAGE_TILE_SCAN, s);
+    tile_scan_kernel<<<nb, kScanThreads, 0, s>>>(P, g.tiles_touched, g.offsets, g.scan_state, g.hdr, nb);
+    return check_cuda(cudaGetLastError(), "tile_scan launch");
+}
+
 int launch_preprocess_fwd(const hgs_raster_params* prm, const hgs_raster_inputs* in, const GeomLayout& g,
                           int32_t* radii, cudaStream_t s) {
     PreArgs a;
@@ -893,9 +937,12 @@ int launch_preprocess_fwd(const hgs_raster_params* prm, const hgs_raster_inputs*
     a.nblocks = (prm->P + kPreprocThreads - 1) / kPreprocThreads;
     a.endpoints = nullptr; a.pairs = nullptr; a.width = nullptr; a.opacity_logit = nullptr; a.mask_logit = nullptr;
     if (int e = check_cuda(cudaMemsetAsync(g.hdr, 0, g.clear_bytes, s), "memset geom header")) return e;
-    StageScope prof(HGS_STAGE_PREPROCESS_FWD, s);
-    preprocess_fwd_kernel<false><<<a.nblocks, kPreprocThreads, 0, s>>>(a);
-    return check_cuda(cudaGetLastError(), "preprocess_fwd launch");
+    {
+        StageScope prof(HGS_STAGE_PREPROCESS_FWD, s);
+        preprocess_fwd_kernel<false><<<a.nblocks, kPreprocThreads, 0, s>>>(a);
+    }
+    if (int e = check_cuda(cudaGetLastError(), "preprocess_fwd launch")) return e;
+    return launch_tile_scan(prm->P, g, s);
 }
 
 int launch_strand_preprocess_fwd(const hgs_raster_params* prm, const hgs_strand_inputs* in, const GeomLayout& g,
@@ -917,9 +964,12 @@ int launch_strand_preprocess_fwd(const hgs_raster_params* prm, const hgs_strand_
     a.endpoints = in->endpoints; a.pairs = (const long long*)in->endpoint_pairs; a.width = in->width;
     a.opacity_logit = in->opacity_logit; a.mask_logit = in->mask_logit;
     if (int e = check_cuda(cudaMemsetAsync(g.hdr, 0, g.clear_bytes, s), "memset geom header")) return e;
-    StageScope prof(HGS_STAGE_PREPROCESS_FWD, s);
-    preprocess_fwd_kernel<true><<<a.nblocks, kPreprocThreads, 0, s>>>(a);
-    return check_cuda(cudaGetLastError(), "strand preprocess_fwd launch");
+    {
+        StageScope prof(HGS_STAGE_PREPROCESS_FWD, s);
+        preprocess_fwd_kernel<true><<<a.nblocks, kPreprocThreads, 0, s>>>(a);
+    }
+    if (int e = check_cuda(cudaGetLastError(), "strand preprocess_fwd launch")) return e;
+    return launch_tile_scan(prm->P, g, s);
 }
 
 int launch_preprocess_bwd(const hgs_raster_params* prm, const hgs_raster_inputs* in, const GeomLayout& g,

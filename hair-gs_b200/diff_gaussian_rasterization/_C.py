@@ -20,6 +20,14 @@ _pinned_pool = []
 _pinned_next = 0
 
 
+def _next_capacity(old, n):
+    """Capacity to try next time for this (device, P, H, W): 25 % head-room over the count just seen, in 256 Ki
+    steps, and never shrinking — views of one scene then settle on ONE workspace size, which the caching allocator
+    serves from the same block every call (sizes that wander per view make it fall back to cudaMalloc)."""
+    want = ((int(n * 1.25) + 4096 + 262143) // 262144) * 262144
+    return max(old or 0, want)
+
+
 def _pinned_triplet():
     """Small ring of pinned int32[3] buffers for the async (num_rendered, -, overflow) read-back."""
     global _pinned_next
@@ -108,7 +116,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                                             binning.data_ptr() if N > 0 else None, img.data_ptr(), N, radii.data_ptr(),
                                             out_color.data_ptr(), stream), "forward stage B")
         # next guess: 25 % head-room, rounded up to the 4096-instance granularity hgs_binning_capacity inverts
-        _capacity_hint[key] = ((int(N * 1.25) + 4096 + 4095) // 4096) * 4096
+        _capacity_hint[key] = _next_capacity(_capacity_hint.get(key), N)
     del keep
     return N, out_color, radii, geom, binning, img
 

@@ -80,7 +80,7 @@ class _RasterizeStrands(torch.autograd.Function):
                 L.check(lib.hgs_strands_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
                                                         binning.data_ptr() if N > 0 else None, img.data_ptr(), N,
                                                         image.data_ptr(), stream), "strands stage B")
-            _dgr._capacity_hint[key] = ((int(N * 1.25) + 4096 + 4095) // 4096) * 4096
+            _dgr._capacity_hint[key] = _dgr._next_capacity(_dgr._capacity_hint.get(key), N)
         ctx.settings, ctx.capacity, ctx.num_rendered = settings, cap, N
         ctx.save_for_backward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit, features, geom, binning, img)
         ctx.mark_non_differentiable(radii)

@@ -233,7 +233,8 @@ enum hgs_stage {
     HGS_STAGE_PREPROCESS_BWD = 7,
     HGS_STAGE_KNN = 8,
     HGS_STAGE_OTHER = 9,
-    HGS_STAGE_COUNT = 10
+    HGS_STAGE_TILE_SCAN = 10,
+    HGS_STAGE_COUNT = 11
 };
 /* Debug: when dev_ptr != NULL the forward compositor writes one uint4 per (tile, warp):
  * (chunks walked, cull candidates, blends summed over lanes, pixels terminated | list chunks << 8). */
