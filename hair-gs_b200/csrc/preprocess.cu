@@ -57,7 +57,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 // reference builds on the torch side (utils/transform.py:69-86 + pytorch3d matrix_to_quaternion) never has to exist.
 struct StrandGeom {
     float3 mean, dhat, diff;
-    float dist, sx, syz;
+    float dist, sx, syz, ew;  // sx, syz include scale_modifier; ew = exp(width)
     bool collapsed;
 };
 __device__ __forceinline__ StrandGeom strand_geom(const float* __restrict__ endpoints, const long long* __restrict__ pairs,
@@ -73,7 +73,8 @@ __device__ __forceinline__ StrandGeom strand_geom(const float* __restrict__ endp
     sg.dhat = sg.collapsed ? make_float3(1.f, 0.f, 0.f)
                            : make_float3(sg.diff.x / sg.dist, sg.diff.y / sg.dist, sg.diff.z / sg.dist);
     sg.sx = fmaxf(sg.dist * 0.5f * kDistToScale, kMinVal) * mod;
-    sg.syz = expf(width[idx]) * mod;
+    sg.ew = expf(width[idx]);
+    sg.syz = sg.ew * mod;
     return sg;
 }
 __device__ __forceinline__ void strand_cov3d(const StrandGeom& sg, float* cov3D) {
@@ -772,10 +773,14 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreBwdArgs a)
         const float dGd = d.x * Gd.x + d.y * Gd.y + d.z * Gd.z;
         const float av = sg.sx * sg.sx, bv = sg.syz * sg.syz;
         const float dL_da = dGd, dL_db = (gxx + gyy + gzz) - dGd;
-        a.dL_dwidth[idx] = dL_db * 2.f * bv;  // b = (mod*exp(w))^2
+        // NB the reference returns dL/d(mod*scale) as "dL_dscale" (backward_distwar.cu:296-326 never multiplies by
+        // scale_modifier), and Hair-GS's autograd then chains that through exp()/norm(): reproduced here so both entries
+        // train identically for scaling_modifier != 1 (they coincide at the training value 1.0).
+        (void)mod;
+        a.dL_dwidth[idx] = dL_db * 2.f * sg.syz * sg.ew;  // "dL_dscale_y + dL_dscale_z" = dL_db * 2 syz, times dexp(w)/dw
         // sx = max(dist/2*k, 1e-7)*mod
         const bool sx_live = sg.dist * 0.5f * kDistToScale > kMinVal;
-        const float dL_ddist = sx_live ? dL_da * 2.f * sg.sx * (0.5f * kDistToScale * mod) : 0.f;
+        const float dL_ddist = sx_live ? dL_da * 2.f * sg.sx * (0.5f * kDistToScale) : 0.f;
         float3 dL_dd = make_float3(2.f * (av - bv) * Gd.x, 2.f * (av - bv) * Gd.y, 2.f * (av - bv) * Gd.z);
         // orientation colour channels 4..6 carry d itself
         const float* dcol = a.dL_dcolor + (size_t)idx * a.channels;

@@ -168,3 +168,23 @@ def test_strand_parameterisation():
     assert torch.allclose(first_col, (e1 - e0)[ok] / dist[ok, None], atol=1e-6)
     assert torch.allclose(orient[ok], (e1 - e0)[ok] / dist[ok, None])
     assert torch.allclose(rot[ok].norm(dim=1), torch.ones(int(ok.sum()), dtype=torch.float64), atol=1e-6)
+
+
+def test_fused_strand_entry_validation_without_gpu():
+    lib = L.load()
+    prm = L.RasterParams(P=10, D=0, M=1, width=64, height=64, channels=3, tan_fovx=1.0, tan_fovy=1.0,
+                         scale_modifier=1.0, prefiltered=0, debug=0)
+    inp = L.StrandInputs()
+    assert lib.hgs_strands_forward_stage_a(ctypes.byref(prm), ctypes.byref(inp), None, None, None) == -1
+    assert b"7 channels" in lib.hgs_last_error()
+    prm.channels = 7
+    assert lib.hgs_strands_forward_stage_a(ctypes.byref(prm), ctypes.byref(inp), None, None, None) == -1
+    assert b"missing required strand input" in lib.hgs_last_error()
+    from hairgs_b200 import fused, models
+    sc = scenes.strand_scene(5, 6, seed=1)
+    cam = scenes.orbit_cameras(2, 32, 32)[0]
+    with pytest.raises(L.HgsError, match="no CPU path"):
+        fused.render_strands(cam, models.StrandModel(sc), torch.zeros(7))
+    assert lib.hgs_binning_capacity(lib.hgs_binning_bytes(12345, 3), 3, 12345) == 12345
+    assert lib.hgs_binning_capacity(lib.hgs_binning_bytes(8 * 4096, 7), 7, 999) == 8 * 4096
+    assert lib.hgs_binning_capacity(lib.hgs_binning_bytes(8 * 4096, 7) + 256, 7, 999) < 0

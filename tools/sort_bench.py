@@ -6,7 +6,8 @@ import torch
 from hairgs_b200 import _lib as L
 lib = L.load()
 dev = torch.device("cuda:0")
-for n in (1 << 20, 1730000, 1 << 23, 1 << 25):
+sizes = [int(a) for a in sys.argv[1:]] or [1 << 20, 1730000, 1 << 23, 1 << 25]
+for n in sizes:
     for end_bit in (45,):
         g = torch.Generator(device="cuda").manual_seed(1)
         keys = (torch.randint(0, 4096, (n,), generator=g, device=dev, dtype=torch.int64) << 32) | \
