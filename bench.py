@@ -221,7 +221,10 @@ class Harness:
         self.fused = fused
         if fused:
             from hairgs_b200.fused import render_strands
+            from hairgs_b200 import losses
             self.render_strands = render_strands
+            self.weighted_l1 = losses.weighted_l1
+            self.w7 = losses.l1_groups([(0, 3, 1.0), (3, 4, 0.01), (4, 7, 1.0)], self.cfg["H"], self.cfg["W"], self.dev)
             self.bg7 = torch.zeros(7, device=self.dev)
         import diff_gaussian_rasterization as dgr
         dgr._RasterizeGaussians.backend = self.C
@@ -284,9 +287,9 @@ class Harness:
         loss = None
         if self.fused:
             # ONE fused pass: strand parameterisation + 7 channels (hairgs_b200.fused.render_strands)
+            # ... and the same three l1_loss terms (loss/losses.py:16-17) in one kernel (hairgs_b200.losses)
             out = self.render_strands(cam, m, self.bg7)
-            loss = ((out["render"] - tgt[0:3]).abs().mean() + 0.01 * (out["mask"] - tgt[3:4]).abs().mean() +
-                    (out["orientation"] - tgt[4:7]).abs().mean())
+            loss = self.weighted_l1(out["image7"], tgt, self.w7)
         else:
             for s in cfg["sets"]:
                 out = self.render(cam, m, self.bg, override_color=colour_override(m, s))["render"]
@@ -395,7 +398,33 @@ def algorithmic_bytes(stage, P, N, HW, T, M, D, sh_mode, C=3):
     return 0
 
 
+class StdoutToStderr:
+    """Route fd 1 to stderr while native code may print (the reference writes a banner to stdout from
+    BACKWARD::render, backward_distwar.cu:1121-1205; NCCL may print its version) so that stdout carries exactly ONE
+    line: the JSON result."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def main():
+    with StdoutToStderr():
+        line = run()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def run():
     args = parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -413,7 +442,7 @@ def main():
     use_ref_gpu = False
     if args.impl == "reference":
         if rank != 0:
-            return 0  # the reference is single-GPU (utils/general.py:116): rank 0 alone measures it
+            return None  # the reference is single-GPU (utils/general.py:116): rank 0 alone measures it
         world = 1
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import refload
@@ -426,8 +455,7 @@ def main():
                                       "sample": f"{args.cpu_sample_views} view(s) of {args.workload}, all colour sets, fwd+bwd"},
                         e2e={"value": vps, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                         gpu_launches=0)
-            print(json.dumps(line))
-            return 0
+            return line
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     dev = torch.device(f"cuda:{local_rank}")
@@ -538,8 +566,13 @@ def main():
         dom = max(stages, key=lambda k: stages[k]["ms_per_launch"] * stages[k]["launches_per_step"])
         ab = algorithmic_bytes(dom, P, N, HW, T, M, D, True, C_prof)
         ach = ab / stages[dom]["ms_per_launch"] / 1e6
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload, {}).get(dom)
+        except Exception:
+            pass
         roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": ab,
                     "note": "compositors are issue/latency-bound (serial transmittance chain), see DESIGN.md; "
                             "HBM-bound stages are listed under 'stages'"}
@@ -547,7 +580,7 @@ def main():
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
-        return 0
+        return None
 
     line = dict(base_line, value=round(value, 2), ms_per_step=round(ms_res / args.steps, 4),
                 e2e={"value": round(e2e_value, 2), "unit": "views/s", "h2d_bytes_per_step": h.h2d_bytes,
@@ -559,7 +592,8 @@ def main():
                           "(hairgs_b200.fused.render_strands); the three-pass drop-in path is reported as *_dropin_3pass")
         line["value_dropin_3pass"] = round(views / (ms_res_3pass / 1000.0), 2)
         line["e2e"]["value_dropin_3pass"] = round(views / (ms_e2e_3pass / 1000.0), 2)
-        line["e2e"]["api"] = "hairgs_b200.fused.render_strands() + autograd, targets/camera prefetched from pinned host memory"
+        line["e2e"]["api"] = ("hairgs_b200.fused.render_strands() + hairgs_b200.losses.weighted_l1() + autograd, "
+                              "targets/camera prefetched from pinned host memory")
     line["n_gpus"] = world
     if args.impl == "reference":
         line["impl"] = "reference"
@@ -576,10 +610,9 @@ def main():
             line["cpu_baseline"] = {"value": round(vps, 4), "unit": "views/s", "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_sample_views} view(s) of {args.workload} (all colour sets, "
                                               f"fwd+bwd) through the OpenMP C port in oracle/, {dt:.1f} s"}
-    print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
-    return 0
+    return line
 
 
 if __name__ == "__main__":

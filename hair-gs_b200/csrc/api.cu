@@ -76,6 +76,7 @@ int launch_composite_fwd(int, const ImageLayout&, const BinningLayout&, int, int
 int launch_composite_bwd(int, const ImageLayout&, const BinningLayout&, const uint32_t*, int, int, const float*,
                          const float*, const hgs_raster_grads*, cudaStream_t);
 int set_fwd_stats(void* dev_ptr);
+int launch_weighted_l1(int, long long, const float*, const float*, const float*, float*, float*, cudaStream_t);
 size_t knn_bytes(int P);
 int launch_knn(int P, const float* points, float* out, void* ws, cudaStream_t s);
 
@@ -340,6 +341,12 @@ int hgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, c
     if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) { set_error("bad mark_visible args"); return HGS_ERR_INVALID; }
     if (P == 0) return HGS_OK;
     return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+int hgs_weighted_l1(int32_t C, int64_t HW, const float* image, const float* target, const float* weights, float* loss,
+                    float* dL_dimage, void* stream) {
+    if (C < 0 || HW < 0 || (C > 0 && HW > 0 && (!image || !target || !weights || !dL_dimage)) || !loss) { set_error("bad weighted_l1 args"); return HGS_ERR_INVALID; }
+    return launch_weighted_l1(C, HW, image, target, weights, loss, dL_dimage, (cudaStream_t)stream);
 }
 
 size_t hgs_knn_bytes(int32_t P) { return knn_bytes(P); }

@@ -180,6 +180,13 @@ int hgs_rasterize_backward(const hgs_raster_params* prm, const hgs_raster_inputs
 int hgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present, void* stream);
 
+/* Weighted L1 over a stack of image planes, value and gradient in one pass (first piece of SURVEY §8f N3):
+ *   *loss = sum_c weights[c] * sum_i |image[c][i] - target[c][i]|,   dL_dimage[c][i] = weights[c] * sign(image - target).
+ * With weights[c] = lambda_c / (planes_in_group * H*W) this is Hair-GS's l1_loss (loss/losses.py:16-17) summed over the
+ * RGB / mask / orientation groups.  Planes must be 16-byte aligned and H*W a multiple of 4.  *loss is overwritten. */
+int hgs_weighted_l1(int32_t C, int64_t HW, const float* image, const float* target, const float* weights, float* loss,
+                    float* dL_dimage, void* stream);
+
 /* Mean squared distance to the 3 nearest neighbours of every point (distCUDA2).
  * workspace: hgs_knn_bytes(P) bytes of device scratch. */
 size_t hgs_knn_bytes(int32_t P);
