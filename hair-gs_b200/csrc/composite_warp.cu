@@ -172,28 +172,53 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restr
                 }
                 __syncwarp();
                 const uint32_t pos_base = (uint32_t)(c * 32) + 1u;
+                // Two candidates per trip: their evaluate parts (distance, power, expf, alpha) do not depend on the
+                // transmittance chain, so issuing them together gives every warp two independent expf chains to
+                // overlap — the kernel's duration is set by the single warp with the most candidates
+                // (profiles/r1_fused_step.md), i.e. by per-warp latency, not by throughput.
                 while (bits) {
-                    const int j = __ffs(bits) - 1;
+                    const int j0 = __ffs(bits) - 1;
                     bits &= bits - 1;
-                    if (done) continue;
-                    const float4 glo = s_lo[warp][j];
-                    const float4 ghi = s_hi[warp][j];
-                    const float2 d = make_float2(glo.x - pixf.x, glo.y - pixf.y);
-                    const float power = -0.5f * (glo.z * d.x * d.x + ghi.x * d.y * d.y) - glo.w * d.x * d.y;
-                    if (power > 0.0f) continue;
-                    const float alpha = min(0.99f, ghi.y * exp(power));
-                    if (alpha < 1.0f / 255.0f) continue;
-                    const float test_T = T * (1 - alpha);
-                    if (test_T < 0.0001f) {
-                        done = true;
-                        continue;
-                    }
-                    const float* col = reinterpret_cast<const float*>(&s_col[warp][j * (CS / 4)]);
+                    const bool two = bits != 0;
+                    const int j1 = two ? __ffs(bits) - 1 : j0;
+                    bits &= bits - 1;
+                    const float4 glo0 = s_lo[warp][j0], ghi0 = s_hi[warp][j0];
+                    const float4 glo1 = s_lo[warp][j1], ghi1 = s_hi[warp][j1];
+                    const float2 d0 = make_float2(glo0.x - pixf.x, glo0.y - pixf.y);
+                    const float2 d1 = make_float2(glo1.x - pixf.x, glo1.y - pixf.y);
+                    const float power0 = -0.5f * (glo0.z * d0.x * d0.x + ghi0.x * d0.y * d0.y) - glo0.w * d0.x * d0.y;
+                    const float power1 = -0.5f * (glo1.z * d1.x * d1.x + ghi1.x * d1.y * d1.y) - glo1.w * d1.x * d1.y;
+                    const float alpha0 = min(0.99f, ghi0.y * exp(power0));
+                    const float alpha1 = min(0.99f, ghi1.y * exp(power1));
+                    // same skip rules as forward.cu:336-345, evaluated as predicates
+                    const bool ok0 = !(power0 > 0.0f) && !(alpha0 < 1.0f / 255.0f);
+                    const bool ok1 = two && !(power1 > 0.0f) && !(alpha1 < 1.0f / 255.0f);
+                    if (ok0 && !done) {
+                        const float test_T = T * (1 - alpha0);
+                        if (test_T < 0.0001f) {
+                            done = true;
+                        } else {
+                            const float* col = reinterpret_cast<const float*>(&s_col[warp][j0 * (CS / 4)]);
 #pragma unroll
-                    for (int ch = 0; ch < C; ++ch) Cacc[ch] += col[ch] * alpha * T;
-                    T = test_T;
-                    last_contributor = pos_base + (uint32_t)j;
-                    st_blend++;
+                            for (int ch = 0; ch < C; ++ch) Cacc[ch] += col[ch] * alpha0 * T;
+                            T = test_T;
+                            last_contributor = pos_base + (uint32_t)j0;
+                            st_blend++;
+                        }
+                    }
+                    if (ok1 && !done) {
+                        const float test_T = T * (1 - alpha1);
+                        if (test_T < 0.0001f) {
+                            done = true;
+                        } else {
+                            const float* col = reinterpret_cast<const float*>(&s_col[warp][j1 * (CS / 4)]);
+#pragma unroll
+                            for (int ch = 0; ch < C; ++ch) Cacc[ch] += col[ch] * alpha1 * T;
+                            T = test_T;
+                            last_contributor = pos_base + (uint32_t)j1;
+                            st_blend++;
+                        }
+                    }
                 }
                 __syncwarp();
                 if (__all_sync(0xffffffffu, done)) break;
@@ -378,8 +403,8 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_kernel(
 
     auto process_group = [&](const uint32_t n) {
         // ---- phase 1: lanes = pixels, candidates in list order ------------------------------------------
-        for (uint32_t g = 0; g < n; ++g) {
-            const uint32_t slot = qwrap<QN>(qhead + g);
+        // evaluate part of one candidate (distance, power, expf, alpha, validity); independent of the recurrence
+        auto evaluate = [&](uint32_t slot, float& G, float& alpha) -> bool {
             const float4 glo = ws.q_lo[slot];
             const float4 ghi = ws.q_hi[slot];
             const int pos = (int)ws.q_ip[slot].y;
@@ -387,31 +412,48 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_kernel(
             const float2 d = make_float2(glo.x - pixf.x, glo.y - pixf.y);
             const float power = -0.5f * (glo.z * d.x * d.x + ghi.x * d.y * d.y) - glo.w * d.x * d.y;
             if (power > 0.0f) valid = false;
-            const float G = exp(power);
-            const float alpha = min(0.99f, ghi.y * G);
+            G = exp(power);
+            alpha = min(0.99f, ghi.y * G);
             if (alpha < 1.0f / 255.0f) valid = false;
-            const uint32_t vm = __ballot_sync(0xffffffffu, valid);
-            if (lane == 0) ws.vmask[g] = vm;
-            if (valid) {
-                // one reciprocal serves T/(1-alpha) and T_final/(1-alpha) (backward_distwar.cu:960,991 divide twice)
-                const float om = 1.f - alpha;
-                const float rcp = 1.f / om;
-                T = T * rcp;
-                const float dchannel_dcolor = alpha * T;
-                float dL_dalpha = 0.0f;
-                const float* col = reinterpret_cast<const float*>(&ws.q_col[slot * (CS / 4)]);
+            return valid;
+        };
+        // recurrence step of backward_distwar.cu:960-991 for one contributing (pixel, candidate) pair
+        auto recur = [&](uint32_t g, uint32_t slot, float G, float alpha) {
+            // one reciprocal serves T/(1-alpha) and T_final/(1-alpha) (the reference divides twice)
+            const float om = 1.f - alpha;
+            const float rcp = 1.f / om;
+            T = T * rcp;
+            const float dchannel_dcolor = alpha * T;
+            float dL_dalpha = 0.0f;
+            const float* col = reinterpret_cast<const float*>(&ws.q_col[slot * (CS / 4)]);
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) {
-                    const float cc = col[ch];
-                    dL_dalpha += (cc - accum_rec[ch]) * dL_dpixel[ch];
-                    // colour accumulated behind the NEXT (nearer) instance; the reference performs this same update
-                    // lazily at the start of the next iteration from (last_alpha, last_color) (:972-973)
-                    accum_rec[ch] = alpha * cc + om * accum_rec[ch];
-                }
-                dL_dalpha *= T;
-                dL_dalpha += (-T_final * rcp) * bg_dot_dpixel;
-                ws.slab[g * 33 + lane] = make_float4(G, dL_dalpha, dchannel_dcolor, 0.f);
+            for (int ch = 0; ch < C; ++ch) {
+                const float cc = col[ch];
+                dL_dalpha += (cc - accum_rec[ch]) * dL_dpixel[ch];
+                // colour accumulated behind the NEXT (nearer) instance; the reference performs this same update
+                // lazily at the start of the next iteration from (last_alpha, last_color) (:972-973)
+                accum_rec[ch] = alpha * cc + om * accum_rec[ch];
             }
+            dL_dalpha *= T;
+            dL_dalpha += (-T_final * rcp) * bg_dot_dpixel;
+            ws.slab[g * 33 + lane] = make_float4(G, dL_dalpha, dchannel_dcolor, 0.f);
+        };
+        // two candidates per trip: both evaluate parts are issued before either recurrence step (two independent
+        // expf chains per warp to overlap, as in the forward)
+        for (uint32_t g = 0; g < n; g += 2) {
+            const bool two = g + 1 < n;
+            const uint32_t slot0 = qwrap<QN>(qhead + g), slot1 = two ? qwrap<QN>(qhead + g + 1) : slot0;
+            float G0, a0, G1, a1;
+            const bool v0 = evaluate(slot0, G0, a0);
+            const bool v1 = evaluate(slot1, G1, a1) && two;
+            const uint32_t vm0 = __ballot_sync(0xffffffffu, v0);
+            const uint32_t vm1 = __ballot_sync(0xffffffffu, v1);
+            if (lane == 0) {
+                ws.vmask[g] = vm0;
+                if (two) ws.vmask[g + 1] = vm1;
+            }
+            if (v0) recur(g, slot0, G0, a0);
+            if (v1) recur(g + 1, slot1, G1, a1);
         }
         __syncwarp();
         // ---- phase 2: lanes = (candidate my_g, pixel quarter my_q) ---------------------------------------
