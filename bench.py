@@ -23,6 +23,7 @@ port when that build is absent.
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -48,6 +49,8 @@ WORKLOADS = {
                  desc="stress: 4M strand-aligned Gaussians at 2048x2048"),
 }
 L2_BYTES = 126 * 1024 * 1024
+# arguments/__init__.py:84-86 defaults
+LOSS_LAMBDAS = dict(lambda_dssim=0.2, lambda_mask=0.01, lambda_orientation=100.0)
 
 
 def parse_args():
@@ -145,8 +148,18 @@ class Harness:
         self.bg = torch.zeros(3, device=dev)
         H, W = cfg["H"], cfg["W"]
         g = torch.Generator(device="cpu").manual_seed(1234)
-        # synthetic targets per view (pinned host memory): rgb[3], mask[1], orientation[3]
-        self.targets_host = [torch.rand(7, H, W, generator=g).pin_memory() for _ in self.my_views]
+        # synthetic targets per view (pinned host memory).  Workloads that train on RGB + mask + orientation carry
+        # what Hair-GS's cameras hold (scene/cameras.py:60-85): original_image[3], float_mask[1], orientation_field[1]
+        # in [0, pi), orientation_confidence[1]; the others an RGB image.
+        self.hair_loss = tuple(cfg["sets"]) == ("sh", "mask", "orientation")
+        self.n_tgt = 6 if self.hair_loss else 7
+        self.targets_host = []
+        for _ in self.my_views:
+            t = torch.rand(self.n_tgt, H, W, generator=g)
+            if self.hair_loss:
+                t[3] = (t[3] < 0.5).float()
+                t[4] *= math.pi
+            self.targets_host.append(t.pin_memory())
         # device-resident inputs of the `value` loop
         with torch.no_grad():
             m = self.model
@@ -224,6 +237,7 @@ class Harness:
             from hairgs_b200 import losses
             self.render_strands = render_strands
             self.weighted_l1 = losses.weighted_l1
+            self.hair_image_loss = losses.hair_image_loss
             self.w7 = losses.l1_groups([(0, 3, 1.0), (3, 4, 0.01), (4, 7, 1.0)], self.cfg["H"], self.cfg["W"], self.dev)
             self.bg7 = torch.zeros(7, device=self.dev)
         import diff_gaussian_rasterization as dgr
@@ -242,7 +256,10 @@ class Harness:
             return
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         H, W = self.cfg["H"], self.cfg["W"]
-        self.tgt_dev = [torch.empty(7, H, W, device=self.dev) for _ in range(2)]
+        self.tgt_dev = [torch.empty(self.n_tgt, H, W, device=self.dev) for _ in range(2)]
+        from hairgs_b200 import losses
+        self.hair_image_loss_torch = losses.hair_image_loss_torch
+        self.view_rot = [losses.view_rot_of(self.cams[v].world_view_transform.cpu()) for v in self.my_views]
         self.cam_host = []
         for v in self.my_views:
             c = self.cams[v]
@@ -252,7 +269,7 @@ class Harness:
         self.copy_done = [torch.cuda.Event() for _ in range(2)]
         self.slot_free = [torch.cuda.Event() for _ in range(2)]
         self.loss_host = torch.zeros(1).pin_memory()
-        self.h2d_bytes = 7 * H * W * 4 + 35 * 4
+        self.h2d_bytes = self.n_tgt * H * W * 4 + 35 * 4
         self.d2h_bytes = 4
         self._prefetched = -1
 
@@ -285,20 +302,26 @@ class Harness:
         self.flat_grad.zero_()
         m = self.model
         loss = None
-        if self.fused:
-            # ONE fused pass: strand parameterisation + 7 channels (hairgs_b200.fused.render_strands)
-            # ... and the same three l1_loss terms (loss/losses.py:16-17) in one kernel (hairgs_b200.losses)
+        lam = LOSS_LAMBDAS
+        if self.fused and self.hair_loss:
+            # ONE fused pass: strand parameterisation + 7 channels (hairgs_b200.fused.render_strands), then Hair-GS's
+            # image loss (l1 + d-ssim + BCE mask + orientation, loss/losses.py:319-346) as one fused op
+            out = self.render_strands(cam, m, self.bg7)
+            loss, _ = self.hair_image_loss(out["image7"], tgt[0:3], tgt[3], tgt[4], tgt[5],
+                                           self.view_rot[it % len(self.my_views)], orient_mask=tgt[3] > 0.5, **lam)
+        elif self.fused:
             out = self.render_strands(cam, m, self.bg7)
             loss = self.weighted_l1(out["image7"], tgt, self.w7)
+        elif self.hair_loss:
+            # the reference's composition: three render() calls (loss/losses.py:245-248, 311-312, train.py:146-155) and
+            # the torch ops of loss_function
+            outs = {s: self.render(cam, m, self.bg, override_color=colour_override(m, s))["render"] for s in cfg["sets"]}
+            loss, _ = self.hair_image_loss_torch(outs["sh"], outs["mask"][0], outs["orientation"], tgt[0:3], tgt[3], tgt[4],
+                                                 tgt[5], cam.world_view_transform, orient_mask=tgt[3] > 0.5, **lam)
         else:
             for s in cfg["sets"]:
                 out = self.render(cam, m, self.bg, override_color=colour_override(m, s))["render"]
-                if s == "sh":
-                    term = (out - tgt[0:3]).abs().mean()
-                elif s == "mask":
-                    term = 0.01 * (out[0:1] - tgt[3:4]).abs().mean()  # lambda_mask, arguments/__init__.py:86
-                else:
-                    term = (out - tgt[4:7]).abs().mean()
+                term = (out - tgt[0:3]).abs().mean()
                 loss = term if loss is None else loss + term
         loss.backward()
         if self.world > 1:
@@ -433,7 +456,10 @@ def run():
 
     import torch
     config = {"workload": f"{args.workload}: {cfg['desc']}", "views": cfg["views"], "colour_sets": list(cfg["sets"]),
-              "resolution": [cfg["W"], cfg["H"]], "sharding": f"views round-robin over {world} rank(s)"}
+              "resolution": [cfg["W"], cfg["H"]], "sharding": f"views round-robin over {world} rank(s)",
+              "e2e_loss": ("Hair-GS image loss: (1-0.2) l1 + 0.2 d-ssim + 0.01 BCE mask + 100 orientation "
+                           "(loss/losses.py:319-346, arguments/__init__.py:84-86)"
+                           if tuple(cfg["sets"]) == ("sh", "mask", "orientation") else "l1")}
     base_line = {"metric": "train views/s (fwd+bwd rasterize incl. grad accumulation" +
                            (", NCCL all-reduce" if world > 1 else "") + ")", "unit": "views/s", "n_gpus": world,
                  "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",

@@ -77,6 +77,7 @@ int launch_composite_bwd(int, const ImageLayout&, const BinningLayout&, const ui
                          const float*, const hgs_raster_grads*, cudaStream_t);
 int set_fwd_stats(void* dev_ptr);
 int launch_weighted_l1(int, long long, const float*, const float*, const float*, float*, float*, cudaStream_t);
+int launch_hair_image_loss(const hgs_hair_loss&, cudaStream_t);
 size_t knn_bytes(int P);
 int launch_knn(int P, const float* points, float* out, void* ws, cudaStream_t s);
 
@@ -347,6 +348,12 @@ int hgs_weighted_l1(int32_t C, int64_t HW, const float* image, const float* targ
                     float* dL_dimage, void* stream) {
     if (C < 0 || HW < 0 || (C > 0 && HW > 0 && (!image || !target || !weights || !dL_dimage)) || !loss) { set_error("bad weighted_l1 args"); return HGS_ERR_INVALID; }
     return launch_weighted_l1(C, HW, image, target, weights, loss, dL_dimage, (cudaStream_t)stream);
+}
+
+int hgs_hair_image_loss(const hgs_hair_loss* a, void* stream) {
+    if (!a || a->height <= 0 || a->width <= 0 || !a->image7 || !a->gt_rgb || !a->gt_mask || !a->gt_theta || !a->confidence ||
+        !a->terms || !a->scratch || !a->dL_dimage) { set_error("bad hair_image_loss args"); return HGS_ERR_INVALID; }
+    return launch_hair_image_loss(*a, (cudaStream_t)stream);
 }
 
 size_t hgs_knn_bytes(int32_t P) { return knn_bytes(P); }

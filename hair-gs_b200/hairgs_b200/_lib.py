@@ -108,6 +108,8 @@ def load():
                                          c_void_p, P(StrandGrads), c_void_p]
     lib.hgs_weighted_l1.restype = c_int
     lib.hgs_weighted_l1.argtypes = [c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.hgs_hair_image_loss.restype = c_int
+    lib.hgs_hair_image_loss.argtypes = [P(HairLoss), c_void_p]
     lib.hgs_debug_set_stats.restype = c_int
     lib.hgs_debug_set_stats.argtypes = [c_void_p]
     lib.hgs_profile_enable.restype = c_int
@@ -120,6 +122,15 @@ def load():
         raise ImportError("libhairgs_rast.so ABI version mismatch; rebuild")
     _lib = lib
     return lib
+
+
+class HairLoss(ctypes.Structure):
+    """hgs_hair_loss (include/hairgs_rast.h)."""
+    _fields_ = [("height", c_int32), ("width", c_int32), ("image7", c_void_p), ("gt_rgb", c_void_p),
+                ("gt_mask", c_void_p), ("gt_theta", c_void_p), ("confidence", c_void_p), ("orient_mask", c_void_p),
+                ("view_rot", ctypes.c_float * 9), ("bg_orient", ctypes.c_float * 3), ("l_l1", ctypes.c_float),
+                ("l_dssim", ctypes.c_float), ("l_mask", ctypes.c_float), ("l_orient", ctypes.c_float),
+                ("terms", c_void_p), ("scratch", c_void_p), ("dL_dimage", c_void_p)]
 
 
 class HgsError(RuntimeError):

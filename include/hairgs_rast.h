@@ -187,6 +187,35 @@ int hgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
 int hgs_weighted_l1(int32_t C, int64_t HW, const float* image, const float* target, const float* weights, float* loss,
                     float* dL_dimage, void* stream);
 
+/* Hair-GS's image-space loss of one training view, value and gradient w.r.t. the seven planes the
+ * one-pass strand entry renders (rgb | mask logit | world orientation), replacing loss_function's image terms
+ * (loss/losses.py:319-346):
+ *   total = l_l1 * mean|rgb - gt_rgb|                                   (l1_loss, losses.py:16-17)
+ *         + l_dssim * (1 - ssim(rgb, gt_rgb))                           (11x11 Gaussian window, sigma 1.5, losses.py:24-84)
+ *         + l_mask * BCEWithLogits(mask, gt_mask)                       (mask_loss_rast, losses.py:292-316)
+ *         + l_orient * mean_{orient_mask}(angle_diff(theta, gt_theta) * confidence)   (orientation_loss_rast, :224-289)
+ * (the reference sets l_l1 = 1 - lambda_dssim).  theta = atan2 of the view-space xy of the orientation, folded to
+ * [0, pi); angle_diff is the bidirectional distance pi/2 - ||theta - gt| - pi/2|.  orient_mask NULL selects the pixels
+ * whose orientation differs from bg_orient (losses.py:266-268).
+ * terms[8] (device): 0 total, 1 l1, 2 dssim, 3 mask, 4 orientation, 5 orientation pixel count, 6-7 unused.
+ * scratch: 9*H*W floats.  dL_dimage: [7,H,W], every element written. */
+typedef struct hgs_hair_loss {
+    int32_t height, width;
+    const float* image7;
+    const float* gt_rgb;            /* [3,H,W] */
+    const float* gt_mask;           /* [H,W] */
+    const float* gt_theta;          /* [H,W] radians in [0, pi) */
+    const float* confidence;        /* [H,W] */
+    const uint8_t* orient_mask;     /* [H,W] bool, may be NULL */
+    float view_rot[9];              /* world_view_transform[:3,:3], row-major (view = world @ view_rot) */
+    float bg_orient[3];
+    float l_l1, l_dssim, l_mask, l_orient;
+    float* terms;
+    float* scratch;
+    float* dL_dimage;
+} hgs_hair_loss;
+int hgs_hair_image_loss(const hgs_hair_loss* args, void* stream);
+
 /* Mean squared distance to the 3 nearest neighbours of every point (distCUDA2).
  * workspace: hgs_knn_bytes(P) bytes of device scratch. */
 size_t hgs_knn_bytes(int32_t P);
