@@ -611,15 +611,17 @@ def run():
     line = dict(base_line, value=round(value, 2), ms_per_step=round(ms_res / args.steps, 4),
                 e2e={"value": round(e2e_value, 2), "unit": "views/s", "h2d_bytes_per_step": h.h2d_bytes,
                      "d2h_bytes_per_step": h.d2h_bytes, "ms_per_step": round(ms_e2e / args.steps, 4),
-                     "api": "gaussian_renderer.render() + autograd, targets/camera prefetched from pinned host memory"},
+                     "api": "gaussian_renderer.render() + torch loss (loss/losses.py composition) + autograd, "
+                            "targets/camera prefetched from pinned host memory"},
                 gpu_launches=launches_per_step * args.steps, clocks=clk)
     if can_fuse:
         config["path"] = ("fused strand entry: strand parameterisation + RGB/mask/orientation in ONE rasterization pass "
                           "(hairgs_b200.fused.render_strands); the three-pass drop-in path is reported as *_dropin_3pass")
         line["value_dropin_3pass"] = round(views / (ms_res_3pass / 1000.0), 2)
         line["e2e"]["value_dropin_3pass"] = round(views / (ms_e2e_3pass / 1000.0), 2)
-        line["e2e"]["api"] = ("hairgs_b200.fused.render_strands() + hairgs_b200.losses.weighted_l1() + autograd, "
-                              "targets/camera prefetched from pinned host memory")
+        line["e2e"]["api"] = ("hairgs_b200.fused.render_strands() + hairgs_b200.losses."
+                              + ("hair_image_loss()" if h.hair_loss else "weighted_l1()") +
+                              " + autograd, targets/camera prefetched from pinned host memory")
     line["n_gpus"] = world
     if args.impl == "reference":
         line["impl"] = "reference"
