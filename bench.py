@@ -50,6 +50,9 @@ WORKLOADS = {
 }
 L2_BYTES = 126 * 1024 * 1024
 # arguments/__init__.py:84-86 defaults
+# arguments/__init__.py optimisation defaults (position / feature / opacity / scaling / mask learning rates)
+ADAM_LRS = {"_endpoints": 1.6e-4, "_xyz": 1.6e-4, "_features_dc": 0.025, "_features_rest": 0.00125, "_opacity": 0.05,
+            "_width": 5e-3, "_scaling": 5e-3, "_rotation": 1e-3, "_mask": 0.01}
 LOSS_LAMBDAS = dict(lambda_dssim=0.2, lambda_mask=0.01, lambda_orientation=100.0)
 
 
@@ -229,9 +232,12 @@ class Harness:
         self.last_N = 0
 
     # ---- end-to-end step: render() + autograd, host<->device copies inside --------------------------
-    def setup_e2e(self, fused=False):
+    def setup_e2e(self, fused=False, optimizer=None):
+        """optimizer: None (gradients only), "flat" (hairgs_b200.optim.FlatAdam: one launch over the flat bucket) or
+        "torch" (torch.optim.Adam(eps=1e-15) + zero_grad(set_to_none=True), scene/gaussian_model.py:250, train.py:203-204)."""
         torch = self.torch
         self.fused = fused
+        self.opt_mode = optimizer
         if fused:
             from hairgs_b200.fused import render_strands
             from hairgs_b200 import losses
@@ -251,6 +257,16 @@ class Harness:
         for p in self.params:
             p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
             o += p.numel()
+        if optimizer is not None:
+            groups = [{"params": [p], "lr": ADAM_LRS.get(n, 1e-3), "name": n}
+                      for n, p in self.model.named_parameters() if p.numel() > 0]
+            if optimizer == "flat":
+                from hairgs_b200.optim import FlatAdam
+                self.opt = FlatAdam(groups)          # re-homes p.data / p.grad into its flat buffers
+            else:
+                for p in self.params:
+                    p.grad = None
+                self.opt = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
         if getattr(self, "copy_stream", None) is not None:
             self._prefetched = -1
             return
@@ -299,7 +315,8 @@ class Harness:
         cam = Camera(base.image_width, base.image_height, base.FoVx, base.FoVy, cd[0:16].view(4, 4), cd[16:32].view(4, 4),
                      cd[32:35])
         tgt = self.tgt_dev[slot]
-        self.flat_grad.zero_()
+        if self.opt_mode is None:
+            self.flat_grad.zero_()
         m = self.model
         loss = None
         lam = LOSS_LAMBDAS
@@ -325,7 +342,12 @@ class Harness:
                 loss = term if loss is None else loss + term
         loss.backward()
         if self.world > 1:
-            torch.distributed.all_reduce(self.flat_grad)
+            torch.distributed.all_reduce(self.opt.grads.flat if self.opt_mode == "flat" else self.flat_grad)
+        if self.opt_mode == "flat":
+            self.opt.step(grad_scale=1.0 / self.world)   # clears the gradient bucket too
+        elif self.opt_mode == "torch":
+            self.opt.step()
+            self.opt.zero_grad(set_to_none=True)
         self.slot_free[slot].record(cur)
         self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
 
@@ -549,6 +571,10 @@ def run():
         launches_per_step = int(sum(launches))
         h.setup_e2e(fused=True)
         ms_e2e = timed_loop(torch, h.step_e2e, args.steps, args.warmup, world, dev, flush)
+    # the same e2e step with the optimiser included ("optimiser step excluded and also reported included");
+    # runs last because it moves the parameters
+    h.setup_e2e(fused=can_fuse, optimizer="flat" if args.impl == "ours" else "torch")
+    ms_e2e_opt = timed_loop(torch, h.step_e2e, args.steps, args.warmup, world, dev, flush)
     clk = clocks.stop() if rank == 0 else None
     import diff_gaussian_rasterization as dgr
     dgr._RasterizeGaussians.backend = dgr._C
@@ -614,6 +640,9 @@ def run():
                      "api": "gaussian_renderer.render() + torch loss (loss/losses.py composition) + autograd, "
                             "targets/camera prefetched from pinned host memory"},
                 gpu_launches=launches_per_step * args.steps, clocks=clk)
+    line["e2e"]["value_incl_optimizer"] = round(views / (ms_e2e_opt / 1000.0), 2)
+    line["e2e"]["optimizer"] = ("hairgs_b200.optim.FlatAdam (hgs_adam_step, one launch)" if args.impl == "ours"
+                                else "torch.optim.Adam(eps=1e-15) + zero_grad(set_to_none=True)")
     if can_fuse:
         config["path"] = ("fused strand entry: strand parameterisation + RGB/mask/orientation in ONE rasterization pass "
                           "(hairgs_b200.fused.render_strands); the three-pass drop-in path is reported as *_dropin_3pass")

@@ -78,6 +78,9 @@ int launch_composite_bwd(int, const ImageLayout&, const BinningLayout&, const ui
 int set_fwd_stats(void* dev_ptr);
 int launch_weighted_l1(int, long long, const float*, const float*, const float*, float*, float*, cudaStream_t);
 int launch_hair_image_loss(const hgs_hair_loss&, cudaStream_t);
+int launch_adam_flat(long long, float*, float*, float*, float*, int, const int64_t*, const float*, int, float, float, float,
+                     float, int, cudaStream_t);
+int launch_densify_stats(int, const int*, const float*, int, int*, float*, float*, float*, cudaStream_t);
 size_t knn_bytes(int P);
 int launch_knn(int P, const float* points, float* out, void* ws, cudaStream_t s);
 
@@ -354,6 +357,27 @@ int hgs_hair_image_loss(const hgs_hair_loss* a, void* stream) {
     if (!a || a->height <= 0 || a->width <= 0 || !a->image7 || !a->gt_rgb || !a->gt_mask || !a->gt_theta || !a->confidence ||
         !a->terms || !a->scratch || !a->dL_dimage) { set_error("bad hair_image_loss args"); return HGS_ERR_INVALID; }
     return launch_hair_image_loss(*a, (cudaStream_t)stream);
+}
+
+int hgs_adam_step(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, int32_t n_groups,
+                  const int64_t* group_end, const float* lr, int32_t step, float beta1, float beta2, float eps,
+                  float grad_scale, int32_t zero_grad, void* stream) {
+    if (n < 0 || n_groups < 1 || n_groups > HGS_ADAM_MAX_GROUPS || step < 1 || !group_end || !lr ||
+        (n > 0 && (!param || !grad || !exp_avg || !exp_avg_sq))) { set_error("bad adam_step args"); return HGS_ERR_INVALID; }
+    for (int g = 0; g < n_groups; ++g)
+        if (group_end[g] < (g ? group_end[g - 1] : 0) || group_end[g] > n) { set_error("adam_step: group_end must be non-decreasing and <= n"); return HGS_ERR_INVALID; }
+    if (group_end[n_groups - 1] != n) { set_error("adam_step: groups must cover the bucket"); return HGS_ERR_INVALID; }
+    return launch_adam_flat(n, param, grad, exp_avg, exp_avg_sq, n_groups, group_end, lr, step, beta1, beta2, eps, grad_scale,
+                            zero_grad, (cudaStream_t)stream);
+}
+
+int hgs_densify_stats(int32_t P, const int32_t* radii, const float* dL_dmean2D, int32_t grad_stride, float* max_radii2D,
+                      float* xyz_gradient_accum, float* denom, void* stream) {
+    if (P < 0 || grad_stride < 2 || (P > 0 && (!radii || !dL_dmean2D || !max_radii2D || !xyz_gradient_accum || !denom))) {
+        set_error("bad densify_stats args"); return HGS_ERR_INVALID;
+    }
+    return launch_densify_stats(P, radii, dL_dmean2D, grad_stride, nullptr, max_radii2D, xyz_gradient_accum, denom,
+                                (cudaStream_t)stream);
 }
 
 size_t hgs_knn_bytes(int32_t P) { return knn_bytes(P); }

@@ -216,6 +216,23 @@ typedef struct hgs_hair_loss {
 } hgs_hair_loss;
 int hgs_hair_image_loss(const hgs_hair_loss* args, void* stream);
 
+/* Optimiser step over the flat parameter bucket: torch.optim.Adam as Hair-GS configures it
+ * (scene/gaussian_model.py:250: per-group lr, betas (0.9, 0.999), eps 1e-15, no weight decay, no amsgrad) for every
+ * parameter group in ONE launch.  Group g covers flat elements [group_end[g-1], group_end[g]) and steps with lr[g];
+ * `step` is the 1-based iteration count (bias correction); the gradient is multiplied by grad_scale first (1/views for a
+ * multi-view batch) and, if zero_grad != 0, cleared afterwards (optimizer.zero_grad, train.py:204).
+ * All four buffers hold n floats and must be 16-byte aligned; group_end and lr are HOST arrays. */
+#define HGS_ADAM_MAX_GROUPS 16
+int hgs_adam_step(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                  int32_t n_groups, const int64_t* group_end, const float* lr, int32_t step,
+                  float beta1, float beta2, float eps, float grad_scale, int32_t zero_grad, void* stream);
+
+/* update_densification_stats (scene/gaussian_model.py:675-682) for the Gaussians with radii > 0:
+ *   max_radii2D = max(max_radii2D, radii);  xyz_gradient_accum += |dL_dmean2D.xy|;  denom += 1.
+ * dL_dmean2D has grad_stride floats per Gaussian (3 for viewspace_points.grad). */
+int hgs_densify_stats(int32_t P, const int32_t* radii, const float* dL_dmean2D, int32_t grad_stride,
+                      float* max_radii2D, float* xyz_gradient_accum, float* denom, void* stream);
+
 /* Mean squared distance to the 3 nearest neighbours of every point (distCUDA2).
  * workspace: hgs_knn_bytes(P) bytes of device scratch. */
 size_t hgs_knn_bytes(int32_t P);
