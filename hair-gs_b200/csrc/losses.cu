@@ -78,9 +78,15 @@ int launch_weighted_l1(int C, long long HW, const float* img, const float* tgt, 
 //   ssim_bwd_kernel      : convolves the three derivative maps back (same tiling) and adds the L1 term's sign()
 //   hair_pointwise_kernel: BCE-with-logits and the orientation chain, forward value and analytic gradient per pixel
 // =====================================================================================================================
-static constexpr int kSsimTile = 16;
+static constexpr int kSsimTile = 32;                        // output tile edge
 static constexpr int kSsimHalo = 5;
-static constexpr int kSsimIn = kSsimTile + 2 * kSsimHalo;  // 26
+static constexpr int kSsimIn = kSsimTile + 2 * kSsimHalo;   // 42
+static constexpr int kSsimInStride = kSsimIn + 1;           // 43: odd stride, the 4-row x 8-segment warp footprint of
+                                                            //     the horizontal pass maps to 32 distinct banks
+static constexpr int kSsimHStride = kSsimTile + 1;          // 33
+static constexpr int kSsimStrip = 4;                        // outputs per thread along the filtered axis
+static constexpr int kSsimTaps = 11;
+static constexpr int kSsimWin = kSsimStrip + kSsimTaps - 1; // 14 inputs feed 4 outputs
 
 __device__ __constant__ float kGauss11[11];  // normalised 11-tap Gaussian, sigma 1.5 (loss/losses.py:24-40)
 
@@ -111,18 +117,41 @@ __global__ void __launch_bounds__(256) hair_loss_count_kernel(const HairLossArgs
     const long long HW = (long long)a.height * a.width;
     float cnt = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
-        const float ox = a.image7[4 * HW + i], oy = a.image7[5 * HW + i], oz = a.image7[6 * HW + i];
+        float ox = 0.f, oy = 0.f, oz = 0.f;
+        if (!a.orient_mask) { ox = a.image7[4 * HW + i]; oy = a.image7[5 * HW + i]; oz = a.image7[6 * HW + i]; }
         cnt += orient_in_mask(a, i, ox, oy, oz) ? 1.f : 0.f;
     }
     const float r = block_sum_256(cnt, s_part);
     if (threadIdx.x == 0 && r != 0.f) atomicAdd(a.terms + 5, r);
 }
 
-// grid (ceil(W/16), ceil(H/16), 3 channels), 256 threads
-__global__ void __launch_bounds__(256) ssim_fwd_kernel(const HairLossArgs a) {
-    __shared__ float s_x[kSsimIn][kSsimIn + 1];
-    __shared__ float s_y[kSsimIn][kSsimIn + 1];
-    __shared__ float s_h[5][kSsimIn][kSsimTile + 1];  // horizontally filtered x, y, xx, yy, xy
+// Separable 11-tap filter with register sliding windows: every thread produces kSsimStrip consecutive outputs from
+// kSsimWin inputs, so a tap costs one FMA and 1/4 of a shared-memory read instead of one read per FMA.
+//   pass 1 (rows):    item = (input row r, 4-column segment)  -> 42 x 8 items
+//   pass 2 (columns): item = (output column, 4-row strip)     -> 32 x 8 items = one per thread; a warp owns one strip row
+template <int NM>
+__device__ __forceinline__ void ssim_vertical(const float (*s_h)[kSsimIn][kSsimHStride], int col, int strip,
+                                              float (&out)[NM][kSsimStrip]) {
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+        float w[kSsimWin];
+#pragma unroll
+        for (int i = 0; i < kSsimWin; ++i) w[i] = s_h[m][strip * kSsimStrip + i][col];
+#pragma unroll
+        for (int j = 0; j < kSsimStrip; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < kSsimTaps; ++k) acc += kGauss11[k] * w[j + k];
+            out[m][j] = acc;
+        }
+    }
+}
+
+// grid (ceil(W/32), ceil(H/32), 3 channels), 256 threads
+__global__ void __launch_bounds__(256, 2) ssim_fwd_kernel(const HairLossArgs a) {
+    __shared__ float s_x[kSsimIn][kSsimInStride];
+    __shared__ float s_y[kSsimIn][kSsimInStride];
+    __shared__ float s_h[5][kSsimIn][kSsimHStride];  // row-filtered x, y, xx, yy, xy
     __shared__ float s_part[8];
     const int H = a.height, W = a.width, c = blockIdx.z;
     const long long HW = (long long)H * W;
@@ -130,54 +159,70 @@ __global__ void __launch_bounds__(256) ssim_fwd_kernel(const HairLossArgs a) {
     const float* Y = a.gt_rgb + c * HW;
     const int x0 = blockIdx.x * kSsimTile - kSsimHalo, y0 = blockIdx.y * kSsimTile - kSsimHalo;
     for (int i = threadIdx.x; i < kSsimIn * kSsimIn; i += 256) {
-        const int r = i / kSsimIn, q = i % kSsimIn;
+        const int r = i / kSsimIn, q = i - r * kSsimIn;
         const int yy = y0 + r, xx = x0 + q;
         const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;  // zero padding (F.conv2d padding=5)
-        s_x[r][q] = in ? X[(long long)yy * W + xx] : 0.f;
-        s_y[r][q] = in ? Y[(long long)yy * W + xx] : 0.f;
+        s_x[r][q] = in ? __ldg(X + (long long)yy * W + xx) : 0.f;
+        s_y[r][q] = in ? __ldg(Y + (long long)yy * W + xx) : 0.f;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kSsimIn * kSsimTile; i += 256) {
-        const int r = i / kSsimTile, q = i % kSsimTile;
-        float mx = 0, my = 0, mxx = 0, myy = 0, mxy = 0;
+    for (int i = threadIdx.x; i < kSsimIn * (kSsimTile / kSsimStrip); i += 256) {
+        const int r = i >> 3, c0 = (i & 7) * kSsimStrip;
+        float vx[kSsimWin], vy[kSsimWin];
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
-            const float g = kGauss11[k], vx = s_x[r][q + k], vy = s_y[r][q + k];
-            mx += g * vx; my += g * vy; mxx += g * vx * vx; myy += g * vy * vy; mxy += g * vx * vy;
+        for (int j = 0; j < kSsimWin; ++j) { vx[j] = s_x[r][c0 + j]; vy[j] = s_y[r][c0 + j]; }
+        float acc[5][kSsimStrip];
+#pragma unroll
+        for (int m = 0; m < 5; ++m)
+#pragma unroll
+            for (int j = 0; j < kSsimStrip; ++j) acc[m][j] = 0.f;
+#pragma unroll
+        for (int t = 0; t < kSsimWin; ++t) {
+            const float x = vx[t], y = vy[t], xx = x * x, yy = y * y, xy = x * y;
+#pragma unroll
+            for (int j = 0; j < kSsimStrip; ++j) {
+                const int k = t - j;
+                if (k >= 0 && k < kSsimTaps) {
+                    const float g = kGauss11[k];
+                    acc[0][j] += g * x; acc[1][j] += g * y; acc[2][j] += g * xx; acc[3][j] += g * yy; acc[4][j] += g * xy;
+                }
+            }
         }
-        s_h[0][r][q] = mx; s_h[1][r][q] = my; s_h[2][r][q] = mxx; s_h[3][r][q] = myy; s_h[4][r][q] = mxy;
+#pragma unroll
+        for (int m = 0; m < 5; ++m)
+#pragma unroll
+            for (int j = 0; j < kSsimStrip; ++j) s_h[m][r][c0 + j] = acc[m][j];
     }
     __syncthreads();
-    const int tx = threadIdx.x % kSsimTile, ty = threadIdx.x / kSsimTile;
-    const int px = blockIdx.x * kSsimTile + tx, py = blockIdx.y * kSsimTile + ty;
-    float ssim_val = 0.f, l1_val = 0.f;
-    if (px < W && py < H) {
-        float mu1 = 0, mu2 = 0, e11 = 0, e22 = 0, e12 = 0;
+    const int col = threadIdx.x & 31, strip = threadIdx.x >> 5;
+    float mom[5][kSsimStrip];
+    ssim_vertical<5>(s_h, col, strip, mom);
+    const int px = blockIdx.x * kSsimTile + col;
+    float ssim_sum = 0.f, l1_sum = 0.f;
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
-            const float g = kGauss11[k];
-            mu1 += g * s_h[0][ty + k][tx]; mu2 += g * s_h[1][ty + k][tx]; e11 += g * s_h[2][ty + k][tx];
-            e22 += g * s_h[3][ty + k][tx]; e12 += g * s_h[4][ty + k][tx];
+    for (int j = 0; j < kSsimStrip; ++j) {
+        const int ly = strip * kSsimStrip + j, py = blockIdx.y * kSsimTile + ly;
+        if (px < W && py < H) {
+            const float mu1 = mom[0][j], mu2 = mom[1][j], e11 = mom[2][j], e22 = mom[3][j], e12 = mom[4][j];
+            const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+            const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+            const float s11 = e11 - mu1_sq, s22 = e22 - mu2_sq, s12 = e12 - mu12;
+            const float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2, B1 = mu1_sq + mu2_sq + C1, B2 = s11 + s22 + C2;
+            const float inv = 1.f / (B1 * B2);
+            const float ssim_val = A1 * A2 * inv;
+            // d ssim / d(mu1, E[x^2], E[xy]) with s11 = E[x^2]-mu1^2, s12 = E[xy]-mu1 mu2
+            const float d_A1 = A2 * inv, d_A2 = A1 * inv, d_B1 = -ssim_val / B1, d_B2 = -ssim_val / B2;
+            const float d_mu1 = d_A1 * 2.f * mu2 + d_B1 * 2.f * mu1 + d_B2 * (-2.f * mu1) + d_A2 * 2.f * (-mu2);
+            const long long p = (long long)py * W + px;
+            a.scratch[(0 * 3 + c) * HW + p] = d_mu1;
+            a.scratch[(1 * 3 + c) * HW + p] = d_B2;         // d/dE[x^2]
+            a.scratch[(2 * 3 + c) * HW + p] = 2.f * d_A2;   // d/dE[xy]
+            ssim_sum += ssim_val;
+            l1_sum += fabsf(s_x[ly + kSsimHalo][col + kSsimHalo] - s_y[ly + kSsimHalo][col + kSsimHalo]);
         }
-        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-        const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
-        const float s11 = e11 - mu1_sq, s22 = e22 - mu2_sq, s12 = e12 - mu12;
-        const float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2, B1 = mu1_sq + mu2_sq + C1, B2 = s11 + s22 + C2;
-        const float inv = 1.f / (B1 * B2);
-        ssim_val = A1 * A2 * inv;
-        // d ssim / d(mu1, E[x^2], E[xy]) with s11 = E[x^2]-mu1^2, s12 = E[xy]-mu1 mu2
-        const float d_A1 = A2 * inv, d_A2 = A1 * inv, d_B1 = -ssim_val / B1, d_B2 = -ssim_val / B2;
-        const float d_e11 = d_B2;              // via s11
-        const float d_e12 = 2.f * d_A2;        // via s12
-        const float d_mu1 = d_A1 * 2.f * mu2 + d_B1 * 2.f * mu1 + d_B2 * (-2.f * mu1) + d_A2 * 2.f * (-mu2);
-        const long long p = (long long)py * W + px;
-        a.scratch[(0 * 3 + c) * HW + p] = d_mu1;
-        a.scratch[(1 * 3 + c) * HW + p] = d_e11;
-        a.scratch[(2 * 3 + c) * HW + p] = d_e12;
-        l1_val = fabsf(s_x[ty + kSsimHalo][tx + kSsimHalo] - s_y[ty + kSsimHalo][tx + kSsimHalo]);
     }
-    const float rs = block_sum_256(ssim_val, s_part);
-    const float rl = block_sum_256(l1_val, s_part);
+    const float rs = block_sum_256(ssim_sum, s_part);
+    const float rl = block_sum_256(l1_sum, s_part);
     if (threadIdx.x == 0) {
         atomicAdd(a.terms + 2, rs);
         atomicAdd(a.terms + 1, rl);
@@ -185,48 +230,54 @@ __global__ void __launch_bounds__(256) ssim_fwd_kernel(const HairLossArgs a) {
 }
 
 // dL/dx = -(l_dssim / n) * [ conv(d_mu1) + 2 x conv(d_e11) + y conv(d_e12) ] + (l_l1 / n) * sign(x - y)
-__global__ void __launch_bounds__(256) ssim_bwd_kernel(const HairLossArgs a) {
-    __shared__ float s_m[3][kSsimIn][kSsimIn + 1];
-    __shared__ float s_h[3][kSsimIn][kSsimTile + 1];
+__global__ void __launch_bounds__(256, 2) ssim_bwd_kernel(const HairLossArgs a) {
+    __shared__ float s_m[3][kSsimIn][kSsimInStride];
+    __shared__ float s_h[3][kSsimIn][kSsimHStride];
     const int H = a.height, W = a.width, c = blockIdx.z;
     const long long HW = (long long)H * W;
     const int x0 = blockIdx.x * kSsimTile - kSsimHalo, y0 = blockIdx.y * kSsimTile - kSsimHalo;
     for (int i = threadIdx.x; i < kSsimIn * kSsimIn; i += 256) {
-        const int r = i / kSsimIn, q = i % kSsimIn;
+        const int r = i / kSsimIn, q = i - r * kSsimIn;
         const int yy = y0 + r, xx = x0 + q;
         const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
         const long long p = (long long)yy * W + xx;
 #pragma unroll
-        for (int m = 0; m < 3; ++m) s_m[m][r][q] = in ? a.scratch[(m * 3 + c) * HW + p] : 0.f;
+        for (int m = 0; m < 3; ++m) s_m[m][r][q] = in ? __ldg(a.scratch + (m * 3 + c) * HW + p) : 0.f;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kSsimIn * kSsimTile; i += 256) {
-        const int r = i / kSsimTile, q = i % kSsimTile;
-        float v0 = 0, v1 = 0, v2 = 0;
+    for (int i = threadIdx.x; i < kSsimIn * (kSsimTile / kSsimStrip); i += 256) {
+        const int r = i >> 3, c0 = (i & 7) * kSsimStrip;
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
-            const float g = kGauss11[k];
-            v0 += g * s_m[0][r][q + k]; v1 += g * s_m[1][r][q + k]; v2 += g * s_m[2][r][q + k];
+        for (int m = 0; m < 3; ++m) {
+            float w[kSsimWin];
+#pragma unroll
+            for (int j = 0; j < kSsimWin; ++j) w[j] = s_m[m][r][c0 + j];
+#pragma unroll
+            for (int j = 0; j < kSsimStrip; ++j) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < kSsimTaps; ++k) acc += kGauss11[k] * w[j + k];
+                s_h[m][r][c0 + j] = acc;
+            }
         }
-        s_h[0][r][q] = v0; s_h[1][r][q] = v1; s_h[2][r][q] = v2;
     }
     __syncthreads();
-    const int tx = threadIdx.x % kSsimTile, ty = threadIdx.x / kSsimTile;
-    const int px = blockIdx.x * kSsimTile + tx, py = blockIdx.y * kSsimTile + ty;
-    if (px < W && py < H) {
-        float c0 = 0, c1 = 0, c2 = 0;
+    const int col = threadIdx.x & 31, strip = threadIdx.x >> 5;
+    float cv[3][kSsimStrip];
+    ssim_vertical<3>(s_h, col, strip, cv);
+    const int px = blockIdx.x * kSsimTile + col;
+    const float n = 3.f * (float)HW;
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
-            const float g = kGauss11[k];
-            c0 += g * s_h[0][ty + k][tx]; c1 += g * s_h[1][ty + k][tx]; c2 += g * s_h[2][ty + k][tx];
+    for (int j = 0; j < kSsimStrip; ++j) {
+        const int py = blockIdx.y * kSsimTile + strip * kSsimStrip + j;
+        if (px < W && py < H) {
+            const long long p = (long long)py * W + px;
+            const float x = a.image7[c * HW + p], y = a.gt_rgb[c * HW + p];
+            const float dssim = cv[0][j] + 2.f * x * cv[1][j] + y * cv[2][j];
+            const float d = x - y;
+            const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+            a.dL_dimage[c * HW + p] = -(a.l_dssim / n) * dssim + (a.l_l1 / n) * sgn;
         }
-        const long long p = (long long)py * W + px;
-        const float x = a.image7[c * HW + p], y = a.gt_rgb[c * HW + p];
-        const float n = 3.f * (float)HW;
-        const float dssim = c0 + 2.f * x * c1 + y * c2;
-        const float d = x - y;
-        const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-        a.dL_dimage[c * HW + p] = -(a.l_dssim / n) * dssim + (a.l_l1 / n) * sgn;
     }
 }
 
