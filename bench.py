@@ -147,9 +147,21 @@ class Harness:
         self.torch, self.cfg, self.dev, self.C, self.world, self.rank = torch, cfg, dev, backend, world, rank
         self.model, self.cams = build_workload(cfg, dev)
         from hairgs_b200 import multiview
-        self.my_views, _ = multiview.shard_views(len(self.cams), world, rank)
         self.bg = torch.zeros(3, device=dev)
         H, W = cfg["H"], cfg["W"]
+        self.empty = torch.Tensor([])
+        costs = None
+        if world > 1:
+            # deal views of similar cost (tile-instance count N) into the same lock-step iteration
+            with torch.no_grad():
+                m = self.model
+                costs = [backend.rasterize_gaussians(
+                    self.bg, m.get_xyz.contiguous(), self.empty, m.get_opacity.contiguous(), m.get_scaling.contiguous(),
+                    m.get_rotation.contiguous(), 1.0, self.empty, c.world_view_transform, c.full_proj_transform,
+                    c.tanfovx, c.tanfovy, H, W, m.get_features.contiguous(), cfg["D"], c.camera_center, False, False)[0]
+                    for c in self.cams]
+        self.view_costs = costs
+        self.my_views, _ = multiview.shard_views(len(self.cams), world, rank, costs=costs)
         g = torch.Generator(device="cpu").manual_seed(1234)
         # synthetic targets per view (pinned host memory).  Workloads that train on RGB + mask + orientation carry
         # what Hair-GS's cameras hold (scene/cameras.py:60-85): original_image[3], float_mask[1], orientation_field[1]
@@ -478,7 +490,7 @@ def run():
 
     import torch
     config = {"workload": f"{args.workload}: {cfg['desc']}", "views": cfg["views"], "colour_sets": list(cfg["sets"]),
-              "resolution": [cfg["W"], cfg["H"]], "sharding": f"views round-robin over {world} rank(s)",
+              "resolution": [cfg["W"], cfg["H"]], "sharding": f"views dealt over {world} rank(s), ordered by tile-instance count" if world > 1 else "1 rank",
               "e2e_loss": ("Hair-GS image loss: (1-0.2) l1 + 0.2 d-ssim + 0.01 BCE mask + 100 orientation "
                            "(loss/losses.py:319-346, arguments/__init__.py:84-86)"
                            if tuple(cfg["sets"]) == ("sh", "mask", "orientation") else "l1")}

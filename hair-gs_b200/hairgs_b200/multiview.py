@@ -12,12 +12,21 @@ import torch
 import torch.distributed as dist
 
 
-def shard_views(n_views, world_size, rank):
+def shard_views(n_views, world_size, rank, costs=None):
     """View i goes to rank i mod world_size (round-robin).  Every rank gets at least one view so that
-    collectives stay matched when n_views < world_size (the extra ranks repeat a view with zero weight)."""
+    collectives stay matched when n_views < world_size (the extra ranks repeat a view with zero weight).
+
+    costs (optional, one number per view, identical on every rank — e.g. the view's tile-instance count N): the views
+    are first ordered by decreasing cost and then dealt round-robin, so the world_size views that meet in one lock-step
+    iteration cost about the same and the per-step max over ranks stays close to the mean."""
     if not (0 <= rank < world_size):
         raise ValueError(f"rank {rank} outside world of {world_size}")
-    mine = list(range(rank, n_views, world_size))
+    order = list(range(n_views))
+    if costs is not None:
+        if len(costs) != n_views:
+            raise ValueError("one cost per view")
+        order.sort(key=lambda v: (-float(costs[v]), v))
+    mine = order[rank::world_size]
     weights = [1.0] * len(mine)
     if not mine:
         mine, weights = [rank % max(n_views, 1)], [0.0]

@@ -93,3 +93,16 @@ def test_bucket_attach_accumulates_autograd_in_place():
     assert torch.allclose(bucket.view("a"), torch.full((5, 3), 2.0))
     assert torch.allclose(bucket.view("b"), 2 * params["b"].detach())
     assert bucket.flat.data_ptr() == params["a"].grad.data_ptr()
+
+
+def test_shard_views_cost_sorted():
+    """Views of similar cost meet in the same lock-step iteration; every view is dealt exactly once."""
+    costs = [5, 1, 9, 3, 7, 2, 8, 4]
+    world = 4
+    dealt = [multiview.shard_views(len(costs), world, r, costs=costs)[0] for r in range(world)]
+    assert sorted(v for d in dealt for v in d) == list(range(len(costs)))
+    step0 = sorted(costs[d[0]] for d in dealt)
+    step1 = sorted(costs[d[1]] for d in dealt)
+    assert step0 == [5, 7, 8, 9] and step1 == [1, 2, 3, 4]
+    with pytest.raises(ValueError):
+        multiview.shard_views(3, 2, 0, costs=[1, 2])
