@@ -25,6 +25,21 @@
  *                           <- GeometryState/ImageState/BinningState::fromChunk + required<T>()
  *                              rasterizer_impl.cu:155-194, rasterizer_impl.h:22-71 (internal ABI of
  *                              the reference; ours is laid out differently)
+ *
+ * Entry points for the callers either side of the rasterizer (paths relative to the
+ * Hair-GS repository root).  The reference implements these in Python/torch, so there is no C
+ * interface to cite; each replaces the torch code at the lines given:
+ *
+ *   hgs_strands_forward_stage_a/_b, hgs_strands_backward
+ *                           <- HairGaussianModel getters scene/hair_gaussian_model.py:134-206 +
+ *                              the three render() calls of one iteration loss/losses.py:245-248,
+ *                              311-312, train.py:146-155
+ *   hgs_weighted_l1         <- l1_loss loss/losses.py:16-17
+ *   hgs_hair_image_loss     <- loss_function's image terms loss/losses.py:319-346 (ssim :43-84,
+ *                              orientation_loss_rast :224-289, mask_loss_rast :292-316)
+ *   hgs_adam_step           <- torch.optim.Adam as configured at scene/gaussian_model.py:250,
+ *                              stepped at train.py:203-204
+ *   hgs_densify_stats       <- update_densification_stats scene/gaussian_model.py:675-682
  */
 #ifndef HAIRGS_RAST_H_
 #define HAIRGS_RAST_H_
