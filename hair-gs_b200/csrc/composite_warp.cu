@@ -18,8 +18,9 @@
 //    gives the candidates, which are broadcast through a 1.5 KB per-warp shared-memory slab.  Skipped instances
 //    are exactly those for which every pixel of the warp would take the reference's `continue`
 //    (power>0 or alpha<1/255), so outputs are unchanged; list positions still advance;
-//  * backward: gradients of a (warp, instance) pair are reduced with a transposing shuffle tree
-//    (V + 5 shuffles instead of 5 V), then 6+C lanes issue one red.global.add each.
+//  * backward: candidates are compacted into a per-warp queue and processed 8 at a time in two phases (lanes = pixels
+//    for the recurrence, lanes = candidate x pixel-quarter for the sums), one lane per candidate issues the
+//    red.global.add's — see the comment above composite_bwd_kernel.
 #include "hgs_common.cuh"
 
 namespace hgs {
@@ -239,77 +240,6 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restr
             g_fwd_stats[tile * 8 + warp] = make_uint4(st_chunks, st_cand, st_blend, ndone | ((uint32_t)nchunks << 8));
     }
 }
-
-// Sum V per-lane values across the warp with a transposing tree: after the call, lane l holds the
-// warp total of value index (l >> 2) & (VP-1) where VP = next pow2 >= V (VP <= 8 -> index l>>2).
-template <int VP>
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[VP], uint32_t lane) {
-    static_assert(VP == 8 || VP == 16, "VP");
-    // level 0 (xor 16): keep lower half of the indices if bit4 clear, upper half otherwise
-    if (VP == 16) {
-        const bool up = lane & 16;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float send = up ? v[k] : v[k + 8];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-            v[k] = (up ? v[k + 8] : v[k]) + recv;
-        }
-        // now 8 live values: indices (bit4 ? 8 : 0) + k ; continue with xor 8, 4, 2 on 8 -> 1
-        {
-            const bool u2 = lane & 8;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float send = u2 ? v[k] : v[k + 4];
-                const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
-                v[k] = (u2 ? v[k + 4] : v[k]) + recv;
-            }
-        }
-        {
-            const bool u3 = lane & 4;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const float send = u3 ? v[k] : v[k + 2];
-                const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
-                v[k] = (u3 ? v[k + 2] : v[k]) + recv;
-            }
-        }
-        {
-            const bool u4 = lane & 2;
-            const float send = u4 ? v[0] : v[1];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
-            v[0] = (u4 ? v[1] : v[0]) + recv;
-        }
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-        return v[0];  // lane l holds index: bit4*8 + bit3*4 + bit2*2 + bit1  == (l >> 1) & 15
-    } else {
-        const bool up = lane & 16;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float send = up ? v[k] : v[k + 4];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-            v[k] = (up ? v[k + 4] : v[k]) + recv;
-        }
-        {
-            const bool u2 = lane & 8;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const float send = u2 ? v[k] : v[k + 2];
-                const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
-                v[k] = (u2 ? v[k + 2] : v[k]) + recv;
-            }
-        }
-        {
-            const bool u3 = lane & 4;
-            const float send = u3 ? v[0] : v[1];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
-            v[0] = (u3 ? v[1] : v[0]) + recv;
-        }
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-        return v[0];  // lane l holds index (l >> 2) & 7
-    }
-}
-
 
 // Backward compositor.  Per warp (8x4 pixels), back to front over the tile list:
 //   1. chunks of 32 instances are culled against the warp's pixel block exactly like the forward; surviving
