@@ -113,6 +113,10 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restr
     __shared__ float4 s_hi[8][32];
     __shared__ float4 s_col[8][32 * (CS / 4)];
 
+    // <= 4 channels (the reference's RGB pass): colour * alpha * T exactly as forward.cu:357, so pixels stay bit-equal
+    // to the reference build; the fused 7-channel pass has no reference counterpart and folds alpha * T first
+    // (one multiply instead of C per blend, ~1 ulp per term).
+    constexpr bool kExactOrder = C <= 4;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t horizontal_blocks = (W + HGS_TILE - 1) / HGS_TILE;
     const uint32_t tile = tile_order[blockIdx.x];
@@ -200,8 +204,9 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restr
                             done = true;
                         } else {
                             const float* col = reinterpret_cast<const float*>(&s_col[warp][j0 * (CS / 4)]);
+                            const float w = alpha0 * T;
 #pragma unroll
-                            for (int ch = 0; ch < C; ++ch) Cacc[ch] += col[ch] * alpha0 * T;
+                            for (int ch = 0; ch < C; ++ch) Cacc[ch] += kExactOrder ? col[ch] * alpha0 * T : col[ch] * w;
                             T = test_T;
                             last_contributor = pos_base + (uint32_t)j0;
                             st_blend++;
@@ -213,8 +218,9 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restr
                             done = true;
                         } else {
                             const float* col = reinterpret_cast<const float*>(&s_col[warp][j1 * (CS / 4)]);
+                            const float w = alpha1 * T;
 #pragma unroll
-                            for (int ch = 0; ch < C; ++ch) Cacc[ch] += col[ch] * alpha1 * T;
+                            for (int ch = 0; ch < C; ++ch) Cacc[ch] += kExactOrder ? col[ch] * alpha1 * T : col[ch] * w;
                             T = test_T;
                             last_contributor = pos_base + (uint32_t)j1;
                             st_blend++;
@@ -307,12 +313,10 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_kernel(
     if (total == 0) return;
     const int nchunks = (total + 31) >> 5;
 
-    float accum_rec[C], dL_dpixel[C];
+    float dL_dpixel[C];
+    float acc_dot = 0.f;  // <colour accumulated behind the current instance, dL/dpixel>
 #pragma unroll
-    for (int ch = 0; ch < C; ++ch) {
-        accum_rec[ch] = 0.f;
-        dL_dpixel[ch] = inside ? dL_dpixels[(size_t)ch * H * W + pix_id] : 0.f;
-    }
+    for (int ch = 0; ch < C; ++ch) dL_dpixel[ch] = inside ? dL_dpixels[(size_t)ch * H * W + pix_id] : 0.f;
     {
         float tmp[8];
 #pragma unroll
@@ -354,16 +358,18 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_kernel(
             const float rcp = 1.f / om;
             T = T * rcp;
             const float dchannel_dcolor = alpha * T;
-            float dL_dalpha = 0.0f;
+            // The reference keeps one running colour per channel (accum_rec, :972-977) and sums
+            // (c - accum_rec) * dL/dpixel over the channels.  dL/dpixel is fixed for the pixel, so the same quantity is
+            // carried as ONE scalar: with d = <c, dL/dpixel>, acc_dot = <accum_rec, dL/dpixel> obeys the same linear
+            // recurrence acc_dot' = alpha * d + (1 - alpha) * acc_dot.  C FMAs + 3 ops instead of 4 C.
             const float* col = reinterpret_cast<const float*>(&ws.q_col[slot * (CS / 4)]);
+            float d = 0.f;
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-                const float cc = col[ch];
-                dL_dalpha += (cc - accum_rec[ch]) * dL_dpixel[ch];
-                // colour accumulated behind the NEXT (nearer) instance; the reference performs this same update
-                // lazily at the start of the next iteration from (last_alpha, last_color) (:972-973)
-                accum_rec[ch] = alpha * cc + om * accum_rec[ch];
-            }
+            for (int ch = 0; ch < C; ++ch) d += col[ch] * dL_dpixel[ch];
+            float dL_dalpha = d - acc_dot;
+            // colour accumulated behind the NEXT (nearer) instance; the reference performs this update lazily at the
+            // start of the next iteration from (last_alpha, last_color)
+            acc_dot = alpha * d + om * acc_dot;
             dL_dalpha *= T;
             dL_dalpha += (-T_final * rcp) * bg_dot_dpixel;
             ws.slab[g * 33 + lane] = make_float4(G, dL_dalpha, dchannel_dcolor, 0.f);
