@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restr
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
     bool done = !inside;
     const float wx0 = (float)bx, wx1 = (float)(bx + 7), wy0 = (float)by, wy1 = (float)(by + 3);
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
     const uint2 range = ranges[tile];
     const int total = (int)(range.y - range.x);
@@ -169,24 +170,25 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restr
             st_chunks++;
             st_cand += __popc(bits);
             if (bits) {
+                // candidates are written to the slab COMPACTED (list order kept), the lane they came from rides in the
+                // slot of the no longer needed cull extent: the blend loop is then a plain counted loop over
+                // consecutive slots instead of a find-first-set scan of the ballot
+                const uint32_t ncand = __popc(bits);
                 if (cand) {
-                    s_lo[warp][lane] = lo;
-                    s_hi[warp][lane] = hi;
-                    s_col[warp][lane * (CS / 4)] = c0;
-                    if (CS > 4) s_col[warp][lane * (CS / 4) + 1] = c1;
+                    const uint32_t slot = __popc(bits & lt_mask);
+                    s_lo[warp][slot] = lo;
+                    s_hi[warp][slot] = make_float4(hi.x, hi.y, __uint_as_float(lane), 0.f);
+                    s_col[warp][slot * (CS / 4)] = c0;
+                    if (CS > 4) s_col[warp][slot * (CS / 4) + 1] = c1;
                 }
                 __syncwarp();
                 const uint32_t pos_base = (uint32_t)(c * 32) + 1u;
                 // Two candidates per trip: their evaluate parts (distance, power, expf, alpha) do not depend on the
                 // transmittance chain, so issuing them together gives every warp two independent expf chains to
-                // overlap — the kernel's duration is set by the single warp with the most candidates
-                // (profiles/r1_fused_step.md), i.e. by per-warp latency, not by throughput.
-                while (bits) {
-                    const int j0 = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    const bool two = bits != 0;
-                    const int j1 = two ? __ffs(bits) - 1 : j0;
-                    bits &= bits - 1;
+                // overlap.
+                for (uint32_t j0 = 0; j0 < ncand; j0 += 2) {
+                    const bool two = j0 + 1 < ncand;
+                    const uint32_t j1 = two ? j0 + 1 : j0;
                     const float4 glo0 = s_lo[warp][j0], ghi0 = s_hi[warp][j0];
                     const float4 glo1 = s_lo[warp][j1], ghi1 = s_hi[warp][j1];
                     const float2 d0 = make_float2(glo0.x - pixf.x, glo0.y - pixf.y);
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restr
 #pragma unroll
                             for (int ch = 0; ch < C; ++ch) Cacc[ch] += kExactOrder ? col[ch] * alpha0 * T : col[ch] * w;
                             T = test_T;
-                            last_contributor = pos_base + (uint32_t)j0;
+                            last_contributor = pos_base + __float_as_uint(ghi0.z);
                             st_blend++;
                         }
                     }
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restr
 #pragma unroll
                             for (int ch = 0; ch < C; ++ch) Cacc[ch] += kExactOrder ? col[ch] * alpha1 * T : col[ch] * w;
                             T = test_T;
-                            last_contributor = pos_base + (uint32_t)j1;
+                            last_contributor = pos_base + __float_as_uint(ghi1.z);
                             st_blend++;
                         }
                     }
