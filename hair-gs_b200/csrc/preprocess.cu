@@ -226,7 +226,7 @@ __device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long 
 }
 
 template <bool kStrand>
-__global__ void __launch_bounds__(kPreprocThreads) preprocess_fwd_kernel(const PreArgs a) {
+__global__ void __launch_bounds__(kPreprocThreads, 6) preprocess_fwd_kernel(const PreArgs a) {
     const int idx = (int)(blockIdx.x * kPreprocThreads + threadIdx.x);
 
     uint32_t touched = 0;
@@ -496,7 +496,7 @@ __device__ __forceinline__ float3 dnormvdv3(const float3 v, const float3 dv) {  
 }
 
 template <bool kStrand>
-__global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreBwdArgs a) {
+__global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs a) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.P) return;
     const bool has_sh = (a.shs != nullptr) && a.M > 0;

@@ -10,7 +10,8 @@ from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libhairgs_rast.so")
+# HGS_LIBRARY: alternative build of the same library (A/B kernel experiments); default is the in-tree build
+LIB_PATH = os.environ.get("HGS_LIBRARY") or os.path.join(os.path.dirname(_HERE), "lib", "libhairgs_rast.so")
 
 HGS_MAX_CHANNELS = 8
 
