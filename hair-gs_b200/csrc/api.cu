@@ -81,6 +81,8 @@ int launch_hair_image_loss(const hgs_hair_loss&, cudaStream_t);
 int launch_adam_flat(long long, float*, float*, float*, float*, int, const int64_t*, const float*, int, float, float, float,
                      float, int, cudaStream_t);
 int launch_densify_stats(int, const int*, const float*, int, int*, float*, float*, float*, cudaStream_t);
+int launch_merge_candidates(const MergeArgs&, bool, int*, const long long*, int*, int*, float*, cudaStream_t);
+int launch_merge_greedy(long long, const int*, const int*, const int*, unsigned char*, unsigned char*, cudaStream_t);
 size_t knn_bytes(int P);
 int launch_knn(int P, const float* points, float* out, void* ws, cudaStream_t s);
 
@@ -378,6 +380,38 @@ int hgs_densify_stats(int32_t P, const int32_t* radii, const float* dL_dmean2D, 
     }
     return launch_densify_stats(P, radii, dL_dmean2D, grad_stride, nullptr, max_radii2D, xyz_gradient_accum, denom,
                                 (cudaStream_t)stream);
+}
+
+static int merge_args(MergeArgs& a, int32_t K, const float* points, const float* dirs, const int32_t* global_id,
+                      const int32_t* other_end, double radius, double dir_th, int32_t bidirectional, int32_t max_num_nn) {
+    if (K < 0 || !(radius >= 0.0) || (K > 0 && (!points || !dirs || !global_id || !other_end))) {
+        set_error("bad merge search args"); return HGS_ERR_INVALID;
+    }
+    a = MergeArgs{K, points, dirs, global_id, other_end, radius * radius, dir_th, bidirectional, max_num_nn};
+    return HGS_OK;
+}
+
+int hgs_merge_count(int32_t K, const float* points, const float* dirs, const int32_t* global_id, const int32_t* other_end,
+                    double radius, double dir_th, int32_t bidirectional, int32_t max_num_nn, int32_t* counts, void* stream) {
+    MergeArgs a;
+    if (int e = merge_args(a, K, points, dirs, global_id, other_end, radius, dir_th, bidirectional, max_num_nn)) return e;
+    if (K > 0 && !counts) { set_error("bad merge search args"); return HGS_ERR_INVALID; }
+    return launch_merge_candidates(a, false, counts, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int hgs_merge_fill(int32_t K, const float* points, const float* dirs, const int32_t* global_id, const int32_t* other_end,
+                   double radius, double dir_th, int32_t bidirectional, int32_t max_num_nn, const int64_t* offsets,
+                   int32_t* p1, int32_t* p2, float* dist, void* stream) {
+    MergeArgs a;
+    if (int e = merge_args(a, K, points, dirs, global_id, other_end, radius, dir_th, bidirectional, max_num_nn)) return e;
+    if (K > 0 && (!offsets || !p1 || !p2 || !dist)) { set_error("bad merge search args"); return HGS_ERR_INVALID; }
+    return launch_merge_candidates(a, true, nullptr, (const long long*)offsets, p1, p2, dist, (cudaStream_t)stream);
+}
+
+int hgs_merge_greedy(int64_t n, const int32_t* p1, const int32_t* p2, const int32_t* other_end_of, uint8_t* flags,
+                     uint8_t* keep, void* stream) {
+    if (n < 0 || (n > 0 && (!p1 || !p2 || !other_end_of || !flags || !keep))) { set_error("bad merge_greedy args"); return HGS_ERR_INVALID; }
+    return launch_merge_greedy(n, p1, p2, other_end_of, flags, keep, (cudaStream_t)stream);
 }
 
 size_t hgs_knn_bytes(int32_t P) { return knn_bytes(P); }

@@ -274,4 +274,17 @@ __device__ __forceinline__ float4 ldg_stream4(const float4* p) {
     return r;
 }
 
+// arguments of the strand endpoint merge search (merge.cu)
+struct MergeArgs {
+    int K;
+    const float* points;        // [K,3] positions of the strand ends considered
+    const float* dirs;          // [K,3] unit direction end -> its neighbouring joint
+    const int* global_id;       // [K]   endpoint id of each strand end
+    const int* other_end;       // [K]   endpoint id of the other end of the same strand (root <-> tip)
+    double r2;                  // ball radius squared (cKDTree compares squared distances in double)
+    double dir_th;              // cos(angle threshold); the float32 dot product is compared in double like numpy
+    int bidirectional;
+    int max_num_nn;             // <= 0: unlimited
+};
+
 }  // namespace hgs

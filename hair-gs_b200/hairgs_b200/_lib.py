@@ -116,6 +116,14 @@ def load():
                                   c_float, c_float, c_float, c_float, c_int32, c_void_p]
     lib.hgs_densify_stats.restype = c_int
     lib.hgs_densify_stats.argtypes = [c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.hgs_merge_count.restype = c_int
+    lib.hgs_merge_count.argtypes = [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_double, ctypes.c_double, c_int32,
+                                    c_int32, c_void_p, c_void_p]
+    lib.hgs_merge_fill.restype = c_int
+    lib.hgs_merge_fill.argtypes = [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_double, ctypes.c_double, c_int32,
+                                   c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.hgs_merge_greedy.restype = c_int
+    lib.hgs_merge_greedy.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.hgs_debug_set_stats.restype = c_int
     lib.hgs_debug_set_stats.argtypes = [c_void_p]
     lib.hgs_profile_enable.restype = c_int

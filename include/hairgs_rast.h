@@ -40,6 +40,9 @@
  *   hgs_adam_step           <- torch.optim.Adam as configured at scene/gaussian_model.py:250,
  *                              stepped at train.py:203-204
  *   hgs_densify_stats       <- update_densification_stats scene/gaussian_model.py:675-682
+ *   hgs_merge_count/_fill/_greedy
+ *                           <- compute_endpoint_pair_to_merge scene/hair_gaussian_model.py:1205-1362
+ *                              (scipy.spatial.cKDTree.query_ball_point + Python loops)
  */
 #ifndef HAIRGS_RAST_H_
 #define HAIRGS_RAST_H_
@@ -247,6 +250,27 @@ int hgs_adam_step(int64_t n, float* param, float* grad, float* exp_avg, float* e
  * dL_dmean2D has grad_stride floats per Gaussian (3 for viewspace_points.grad). */
 int hgs_densify_stats(int32_t P, const int32_t* radii, const float* dL_dmean2D, int32_t grad_stride,
                       float* max_radii2D, float* xyz_gradient_accum, float* denom, void* stream);
+
+/* Strand endpoint merge search: HairGaussianModel.compute_endpoint_pair_to_merge,
+ * scene/hair_gaussian_model.py:1205-1362, without the host cKDTree and the per-point Python loops.
+ * The K strand ends considered are given by position, unit direction towards their neighbouring joint, endpoint id and the
+ * endpoint id of the other end of their strand.  A pair (i, j) is a candidate when |p_i - p_j| <= radius (double
+ * arithmetic like cKDTree), j != i, j is not the other end of i's strand and <dir_j, -dir_i> >= dir_th (absolute value if
+ * bidirectional); per i at most max_num_nn candidates in ascending j are kept (<= 0: all).
+ *   hgs_merge_count: counts[i] = number of candidates of end i.
+ *   hgs_merge_fill:  writes end i's candidates at offsets[i] (exclusive scan of counts): p1 = id of i, p2 = id of j,
+ *                    dist = float32 norm of the float32 difference (np.linalg.norm, :1321-1324).
+ *   hgs_merge_greedy: pairs sorted by ascending dist -> keep[r] in {0,1} after remove_duplicate_endpoint_rows (:711-726)
+ *                    and remove_complementary_rows (:1237-1255).  other_end_of[id] = other strand end of endpoint id or
+ *                    -1; flags: one zeroed byte per endpoint id (scratch). */
+int hgs_merge_count(int32_t K, const float* points, const float* dirs, const int32_t* global_id,
+                    const int32_t* other_end, double radius, double dir_th, int32_t bidirectional,
+                    int32_t max_num_nn, int32_t* counts, void* stream);
+int hgs_merge_fill(int32_t K, const float* points, const float* dirs, const int32_t* global_id,
+                   const int32_t* other_end, double radius, double dir_th, int32_t bidirectional,
+                   int32_t max_num_nn, const int64_t* offsets, int32_t* p1, int32_t* p2, float* dist, void* stream);
+int hgs_merge_greedy(int64_t n, const int32_t* p1, const int32_t* p2, const int32_t* other_end_of,
+                     uint8_t* flags, uint8_t* keep, void* stream);
 
 /* Mean squared distance to the 3 nearest neighbours of every point (distCUDA2).
  * workspace: hgs_knn_bytes(P) bytes of device scratch. */
