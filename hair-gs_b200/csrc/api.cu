@@ -68,7 +68,7 @@ int launch_strand_preprocess_bwd(const hgs_raster_params*, const hgs_strand_inpu
                                  const hgs_strand_grads*, cudaStream_t);
 int launch_view_geom(int, const hgs_raster_params*, const hgs_raster_inputs*, const GeomLayout&, void*, cudaStream_t);
 int launch_emit_keys(int, const GeomLayout&, const uint2*, uint64_t*, uint32_t*, uint32_t, uint32_t, cudaStream_t);
-int launch_sort_pairs(int64_t, const uint32_t*, int, uint64_t* [2], uint32_t* [2], void*, int*, cudaStream_t);
+int launch_sort_pairs(int64_t, const uint32_t*, int, uint64_t* [2], uint32_t* [2], void*, int*, cudaStream_t, GeomHeader*, int, int);
 int launch_finalize_sorted(int, int64_t, const uint32_t*, const uint64_t*, const uint32_t*, const GeomLayout&,
                            const BinningLayout&, uint2*,
                            uint32_t*, size_t, cudaStream_t);
@@ -105,9 +105,14 @@ static int validate(const hgs_raster_params* prm, const hgs_raster_inputs* in, b
     return HGS_OK;
 }
 
+// bits of the depth part of the sort key: 32 (the reference's key, rasterizer_impl.cu:300-308) unless the caller passes a
+// smaller range hint (see KeyXform in binning.cu)
+static inline int depth_bits_for(const hgs_raster_params* prm) {
+    return (prm->sort_depth_bits >= 1 && prm->sort_depth_bits < 32) ? prm->sort_depth_bits : 32;
+}
 static inline int end_bit_for(const hgs_raster_params* prm) {
     const uint32_t gx = (prm->width + HGS_TILE - 1) / HGS_TILE, gy = (prm->height + HGS_TILE - 1) / HGS_TILE;
-    return 32 + tile_id_bits(gx * gy);  // rasterizer_impl.cu:300-308
+    return depth_bits_for(prm) + tile_id_bits(gx * gy);
 }
 
 }  // namespace hgs
@@ -182,7 +187,7 @@ int hgs_forward_stage_a(const hgs_raster_params* prm, const hgs_raster_inputs* i
 int hgs_forward_read_num_rendered(const void* geom_ws, int32_t P, uint32_t* n_pinned_host, void* stream) {
     (void)P;
     const GeomHeader* h = (const GeomHeader*)geom_ws;
-    return check_cuda(cudaMemcpyAsync(n_pinned_host, &h->num_rendered, 2 * sizeof(uint32_t) + 4, cudaMemcpyDeviceToHost,
+    return check_cuda(cudaMemcpyAsync(n_pinned_host, &h->num_rendered, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                       (cudaStream_t)stream), "read num_rendered");
 }
 
@@ -196,11 +201,14 @@ static int stage_b_impl(const hgs_raster_params* prm, const float* background, v
     BinningLayout b = carve_binning(binning_ws, N, prm->channels);
     const uint32_t gx = (prm->width + HGS_TILE - 1) / HGS_TILE, gy = (prm->height + HGS_TILE - 1) / HGS_TILE;
 
-    if (int e = launch_emit_keys(N > 0 ? prm->P : 0, g, g.rects, b.keys[0], b.vals[0], gx, (uint32_t)N, s)) return e;
+    // the unsorted pairs go into the ping-pong buffer from which the sort's passes end in buffer 0, whatever their number
+    const int start = sort_passes(end_bit_for(prm)) & 1;
+    if (int e = launch_emit_keys(N > 0 ? prm->P : 0, g, g.rects, b.keys[start], b.vals[start], gx, (uint32_t)N, s)) return e;
     if (int e = stage_check("emit_keys", prm->debug, s)) return e;
     int res = 0;
     const uint32_t* n_ptr = &g.hdr->num_rendered;  // live instance count stays on the device; N is only the capacity
-    if (int e = launch_sort_pairs(N, n_ptr, end_bit_for(prm), b.keys, b.vals, b.sort_ws, &res, s)) return e;
+    if (int e = launch_sort_pairs(N, n_ptr, end_bit_for(prm), b.keys, b.vals, b.sort_ws, &res, s, g.hdr, depth_bits_for(prm),
+                                  start)) return e;
     if (int e = stage_check("sort", prm->debug, s)) return e;
     if (int e = launch_finalize_sorted(prm->channels, N, n_ptr, b.keys[res], b.vals[res], g, b, im.ranges, im.tile_order, (size_t)gx * gy, s)) return e;
     if (int e = stage_check("finalize_sorted", prm->debug, s)) return e;
@@ -260,7 +268,7 @@ int hgs_strands_backward(const hgs_raster_params* prm, const hgs_strand_inputs* 
     GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels);
     ImageLayout im = carve_image((void*)image_ws, prm->width, prm->height);
     BinningLayout b = carve_binning((void*)binning_ws, R, prm->channels);
-    const int res = sort_passes(end_bit_for(prm)) & 1;
+    const int res = 0;  // the sorted pairs always end in ping-pong buffer 0 (stage_b_impl)
     const size_t Pz = (size_t)P;
     if (gr->dL_dconic == gr->dL_dmean2D + 3 * Pz && gr->dL_dopacity == gr->dL_dconic + 4 * Pz &&
         gr->dL_dcolor == gr->dL_dopacity + Pz) {
@@ -318,7 +326,7 @@ int hgs_rasterize_backward(const hgs_raster_params* prm, const hgs_raster_inputs
     GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels);
     ImageLayout im = carve_image((void*)image_ws, prm->width, prm->height);
     BinningLayout b = carve_binning((void*)binning_ws, R, prm->channels);
-    const int res = sort_passes(end_bit_for(prm)) & 1;
+    const int res = 0;  // the sorted pairs always end in ping-pong buffer 0 (stage_b_impl)
 
     // accumulation targets of the compositor (the only arrays that need clearing)
     const size_t Pz = (size_t)P;
@@ -430,7 +438,7 @@ int hgs_sort_pairs(int64_t n, int end_bit, uint64_t* keys_in, uint32_t* vals_in,
     uint64_t* keys[2] = {keys_in, keys_out};
     uint32_t* vals[2] = {vals_in, vals_out};
     int res = 0;
-    if (int e = launch_sort_pairs(n, nullptr, end_bit, keys, vals, workspace, &res, s)) return e;
+    if (int e = launch_sort_pairs(n, nullptr, end_bit, keys, vals, workspace, &res, s, nullptr, 32, 0)) return e;
     if (res == 0) {
         if (int e = check_cuda(cudaMemcpyAsync(keys_out, keys_in, (size_t)n * 8, cudaMemcpyDeviceToDevice, s), "copy keys")) return e;
         if (int e = check_cuda(cudaMemcpyAsync(vals_out, vals_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, s), "copy vals")) return e;
@@ -470,7 +478,7 @@ int64_t hgs_state_view(int what, const hgs_raster_params* prm, const hgs_raster_
         case HGS_VIEW_KEYS_SORTED: case HGS_VIEW_POINT_LIST: {
             if (N > 0 && !binning_ws) { set_error("null binning workspace"); return HGS_ERR_INVALID; }
             BinningLayout b = carve_binning((void*)binning_ws, capacity, prm->channels);
-            const int res = sort_passes(end_bit_for(prm)) & 1;
+            const int res = 0;  // the sorted pairs always end in ping-pong buffer 0 (stage_b_impl)
             if (what == HGS_VIEW_KEYS_SORTED) return d2d(b.keys[res], (size_t)N * 8);
             return d2d(b.vals[res], (size_t)N * 4);
         }

@@ -93,16 +93,43 @@ __device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
 // One read of the keys, all digit histograms at once.
 // The element count lives on the device (n_ptr, clamped to the buffer capacity) so that the host never has
 // to wait for it before launching; n_ptr == nullptr means "exactly cap elements".
+// Depth-range compaction of the rasterizer's keys (tile << 32 | depth bits).  All visible depths lie in
+// [dmin, dmax] (GeomHeader, reduced by tile_scan); sorting (tile << rb | depth - dmin) orders the pairs exactly like
+// the full key as long as dmax - dmin < 2^rb, and needs ceil((tile_bits + rb) / 8) passes instead of
+// ceil((tile_bits + 32) / 8).  The keys in memory stay the reference's; only the digit extraction sees the compacted
+// value.  rb comes from the host (a hint from earlier views); if the range does not fit, bit 1 of hdr->overflow is
+// raised and the caller repeats the stage with rb = 32.  rb == 32 with dmin == 0 is the identity (hgs_sort_pairs).
+struct KeyXform {
+    uint32_t dmin, dmask;
+    int rb;
+    __device__ __forceinline__ uint64_t operator()(uint64_t k) const {
+        const uint32_t d = min((uint32_t)k - dmin, dmask);
+        return ((k >> 32) << rb) | d;
+    }
+};
+
+__device__ __forceinline__ KeyXform load_key_xform(const GeomHeader* range_hdr, int rb) {
+    KeyXform x;
+    x.rb = rb;
+    x.dmask = rb >= 32 ? 0xffffffffu : ((1u << rb) - 1u);
+    x.dmin = (range_hdr != nullptr && rb < 32) ? ~range_hdr->depth_min_inv : 0u;
+    return x;
+}
+
 __global__ void __launch_bounds__(256) radix_histogram_kernel(const uint64_t* __restrict__ keys, uint32_t cap,
                                                               const uint32_t* __restrict__ n_ptr, int passes,
-                                                              uint32_t* __restrict__ ghist) {
+                                                              uint32_t* __restrict__ ghist, GeomHeader* range_hdr, int rb) {
     const uint32_t n = n_ptr ? min(*n_ptr, cap) : cap;
+    const KeyXform xf = load_key_xform(range_hdr, rb);
+    if (range_hdr != nullptr && rb < 32 && blockIdx.x == 0 && threadIdx.x == 0 && n > 0) {
+        if (((range_hdr->depth_max - xf.dmin) >> rb) != 0) atomicOr(&range_hdr->overflow, 2u);
+    }
     __shared__ uint32_t s_hist[kMaxPasses * kRadix];
     for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint64_t k = keys[i];
+        const uint64_t k = xf(keys[i]);
         for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p * kRadix + (uint32_t)((k >> (8 * p)) & 0xffu)], 1u);
     }
     __syncthreads();
@@ -145,12 +172,13 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
     const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, uint32_t cap, const uint32_t* __restrict__ n_ptr, int shift,
     const uint32_t* __restrict__ ghist /*[256]*/,
-    uint32_t* __restrict__ status /*[ntiles*256]*/, uint32_t* __restrict__ ticket) {
+    uint32_t* __restrict__ status /*[ntiles*256]*/, uint32_t* __restrict__ ticket, const GeomHeader* range_hdr, int rb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
 
     const uint32_t n = n_ptr ? min(*n_ptr, cap) : cap;
     if (blockIdx.x * (uint32_t)kSortTile >= n) return;  // tile beyond the live range (grid is sized by capacity)
+    const KeyXform xf = load_key_xform(range_hdr, rb);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     (void)ticket;  // blocks are dispatched in index order: predecessors of a tile are always running or done
 #pragma unroll
@@ -178,7 +206,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
     uint32_t* wh = sm.warp_hist[warp];
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t d = (uint32_t)(key[r] >> shift) & 0xffu;
+        const uint32_t d = (uint32_t)(xf(key[r]) >> shift) & 0xffu;
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const uint32_t lrank = __popc(peers & lt_mask);
         const int leader = __ffs(peers) - 1;
@@ -219,7 +247,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
     //      overlaps the predecessors' chain latency instead of waiting behind the look-back ------------------------
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t d = (uint32_t)(key[r] >> shift) & 0xffu;
+        const uint32_t d = (uint32_t)(xf(key[r]) >> shift) & 0xffu;
         const uint32_t pos = sm.excl[d] + wh[d] + rank[r];
         sm.keys[pos] = key[r];
         sm.vals[pos] = val[r];
@@ -260,7 +288,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
         const uint32_t li = tid + k * kSortThreads;
         if (li < nvalid) {
             const uint64_t kk = sm.keys[li];
-            const uint32_t d = (uint32_t)(kk >> shift) & 0xffu;
+            const uint32_t d = (uint32_t)(xf(kk) >> shift) & 0xffu;
             const uint32_t gi = sm.gbase[d] + li;
             keys_out[gi] = kk;
             vals_out[gi] = sm.vals[li];
@@ -282,18 +310,20 @@ int launch_emit_keys(int P, const GeomLayout& g, const uint2* rects, uint64_t* k
 
 // Sorts n pairs on key bits [0, end_bit).  keys[0]/vals[0] hold the input; returns in *result_buf
 // which ping-pong buffer (0/1) holds the sorted output.
+// range_hdr / depth_bits: depth-range compaction for the rasterizer's keys (see KeyXform); nullptr / 32 sorts the keys as
+// they are.  end_bit counts bits of the COMPACTED key.  start_buf: which ping-pong buffer holds the input.
 int launch_sort_pairs(int64_t n, const uint32_t* n_ptr, int end_bit, uint64_t* keys[2], uint32_t* vals[2], void* sort_ws,
-                      int* result_buf,
-                      cudaStream_t s) {
+                      int* result_buf, cudaStream_t s, GeomHeader* range_hdr, int depth_bits, int start_buf) {
     // the sorted data always ends in buffer (passes & 1), also for the trivial sizes
     const int passes = sort_passes(end_bit);
     if (passes > kMaxPasses) { set_error("end_bit %d too large", end_bit); return HGS_ERR_INVALID; }
-    *result_buf = passes & 1;
+    *result_buf = (start_buf ^ passes) & 1;
     if (n <= 0) return HGS_OK;
     if ((n == 1 && n_ptr == nullptr) || end_bit <= 0) {
         if (passes & 1) {
-            if (int e = check_cuda(cudaMemcpyAsync(keys[1], keys[0], (size_t)n * 8, cudaMemcpyDeviceToDevice, s), "copy keys")) return e;
-            if (int e = check_cuda(cudaMemcpyAsync(vals[1], vals[0], (size_t)n * 4, cudaMemcpyDeviceToDevice, s), "copy vals")) return e;
+            const int a = start_buf & 1, b = a ^ 1;
+            if (int e = check_cuda(cudaMemcpyAsync(keys[b], keys[a], (size_t)n * 8, cudaMemcpyDeviceToDevice, s), "copy keys")) return e;
+            if (int e = check_cuda(cudaMemcpyAsync(vals[b], vals[a], (size_t)n * 4, cudaMemcpyDeviceToDevice, s), "copy vals")) return e;
         }
         return HGS_OK;
     }
@@ -315,15 +345,15 @@ int launch_sort_pairs(int64_t n, const uint32_t* n_ptr, int end_bit, uint64_t* k
     const int hblocks = (int)(hb < 148 * 8 ? hb : 148 * 8);
     {
         StageScope prof(HGS_STAGE_SORT_HISTOGRAM, s);
-        radix_histogram_kernel<<<hblocks, 256, 0, s>>>(keys[0], nn, n_ptr, passes, L.hist);
+        radix_histogram_kernel<<<hblocks, 256, 0, s>>>(keys[start_buf & 1], nn, n_ptr, passes, L.hist, range_hdr, depth_bits);
     }
     if (int e = check_cuda(cudaGetLastError(), "radix_histogram launch")) return e;
-    int cur = 0;
+    int cur = start_buf & 1;
     for (int p = 0; p < passes; ++p) {
         StageScope prof(HGS_STAGE_SORT_ONESWEEP, s);
         onesweep_pass_kernel<<<(unsigned)L.ntiles, kSortThreads, sizeof(OnesweepSmem), s>>>(
             keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], nn, n_ptr, 8 * p, L.hist + p * kRadix,
-            L.status + (size_t)p * L.ntiles * kRadix, L.tickets + p);
+            L.status + (size_t)p * L.ntiles * kRadix, L.tickets + p, range_hdr, depth_bits);
         if (int e = check_cuda(cudaGetLastError(), "onesweep launch")) return e;
         cur ^= 1;
     }

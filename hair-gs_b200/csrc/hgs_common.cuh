@@ -42,8 +42,10 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a = kAlign) { return
 struct GeomHeader {            // first 256 B of the geometry workspace
     uint32_t num_rendered;     // total instance count N (written by the last preprocess block)
     uint32_t block_ticket;     // dynamic block id for the in-kernel chained scan
-    uint32_t overflow;         // set when N would exceed 2^31-1
-    uint32_t pad[61];
+    uint32_t overflow;         // bit 0: N would exceed 2^31-1; bit 1: the depth range did not fit the sort's depth bits
+    uint32_t depth_max;        // max over visible Gaussians of the depth's bit pattern (tile_scan)
+    uint32_t depth_min_inv;    // max of ~bits, i.e. ~min (so that the zero fill of the header is the identity)
+    uint32_t pad[59];
 };
 
 // One 32-byte record per Gaussian: everything the compositors need besides colour, in one sector.

@@ -10,7 +10,7 @@
 
 namespace hgs {
 
-int launch_sort_pairs(int64_t, const uint32_t*, int, uint64_t* [2], uint32_t* [2], void*, int*, cudaStream_t);
+int launch_sort_pairs(int64_t, const uint32_t*, int, uint64_t* [2], uint32_t* [2], void*, int*, cudaStream_t, GeomHeader*, int, int);
 
 static constexpr int kBox = 32;
 
@@ -221,7 +221,7 @@ int launch_knn(int P, const float* points, float* out, void* ws, cudaStream_t s)
     knn_morton_kernel<<<nb, 256, 0, s>>>(P, points, k.bounds, k.keys[0], k.vals[0]);
     if (int e = check_cuda(cudaGetLastError(), "knn morton launch")) return e;
     int res = 0;
-    if (int e = launch_sort_pairs(P, nullptr, 30, k.keys, k.vals, k.sort_ws, &res, s)) return e;
+    if (int e = launch_sort_pairs(P, nullptr, 30, k.keys, k.vals, k.sort_ws, &res, s, nullptr, 32, 0)) return e;
     knn_gather_kernel<<<nb, 256, 0, s>>>(P, points, k.vals[res], k.sorted);
     knn_box_kernel<<<(k.nbox * 32 + 255) / 256, 256, 0, s>>>(P, k.sorted, k.sorted, k.box_lo, k.box_hi);
     knn_box_kernel<<<(k.nsbox * 32 + 255) / 256, 256, 0, s>>>(k.nbox, k.box_lo, k.box_hi, k.sbox_lo, k.sbox_hi);

@@ -347,10 +347,12 @@ static constexpr int kScanItems = 16;
 static constexpr int kScanTile = kScanThreads * kScanItems;
 
 __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(int P, const uint32_t* __restrict__ touched,
+                                                                 const uint32_t* __restrict__ depth_bits,
                                                                  uint32_t* __restrict__ offsets,
                                                                  unsigned long long* __restrict__ scan_state,
                                                                  GeomHeader* __restrict__ hdr, uint32_t nblocks) {
     __shared__ uint32_t s_warp_sum[kScanThreads / 32];
+    __shared__ uint32_t s_warp_dmax[kScanThreads / 32], s_warp_dmin_inv[kScanThreads / 32];
     __shared__ unsigned long long s_block_excl;
     const int tid = threadIdx.x;
     const uint32_t bid = blockIdx.x;
@@ -368,6 +370,26 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(int P, const ui
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k) v[k] = (base + k < P) ? touched[base + k] : 0u;
     }
+    // depth range of the visible Gaussians (positive floats: the bit patterns order like the values).  The sort strips
+    // the common offset and the unused high bits from its keys (binning.cu), which can save a whole pass.
+    uint32_t dmax = 0, dmin_inv = 0;
+    if (base + kScanItems <= P) {
+#pragma unroll
+        for (int q = 0; q < kScanItems / 4; ++q) {
+            const uint4 t = reinterpret_cast<const uint4*>(depth_bits + base)[q];
+            const uint32_t d[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (v[4 * q + e] > 0) { dmax = max(dmax, d[e]); dmin_inv = max(dmin_inv, ~d[e]); }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k)
+            if (base + k < P && v[k] > 0) { const uint32_t d = depth_bits[base + k]; dmax = max(dmax, d); dmin_inv = max(dmin_inv, ~d); }
+    }
+    dmax = __reduce_max_sync(0xffffffffu, dmax);
+    dmin_inv = __reduce_max_sync(0xffffffffu, dmin_inv);
+    if (lane == 0) { s_warp_dmax[warp] = dmax; s_warp_dmin_inv[warp] = dmin_inv; }
 #pragma unroll
     for (int k = 1; k < kScanItems; ++k) v[k] += v[k - 1];
     uint32_t incl = v[kScanItems - 1];
@@ -384,6 +406,15 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(int P, const ui
         const uint32_t x = s_warp_sum[w];
         if ((uint32_t)w < warp) warp_excl += x;
         block_total += x;
+    }
+    if (warp == 1 && lane < kScanThreads / 32) {
+        const uint32_t m = (1u << (kScanThreads / 32)) - 1u;
+        const uint32_t bmax = __reduce_max_sync(m, s_warp_dmax[lane]);
+        const uint32_t bmin_inv = __reduce_max_sync(m, s_warp_dmin_inv[lane]);
+        if (lane == 0 && bmin_inv != 0) {  // the block has a visible Gaussian
+            atomicMax(&hdr->depth_max, bmax);
+            atomicMax(&hdr->depth_min_inv, bmin_inv);
+        }
     }
     if (warp == 0) {
         unsigned long long excl = 0;
@@ -920,7 +951,8 @@ __global__ void view_cov3d_kernel(int P, const float* __restrict__ scales, const
 static int launch_tile_scan(int P, const GeomLayout& g, cudaStream_t s) {
     const uint32_t nb = (uint32_t)((P + kScanTile - 1) / kScanTile);
     StageScope prof(HGS_STAGE_TILE_SCAN, s);
-    tile_scan_kernel<<<nb, kScanThreads, 0, s>>>(P, g.tiles_touched, g.offsets, g.scan_state, g.hdr, nb);
+    tile_scan_kernel<<<nb, kScanThreads, 0, s>>>(P, g.tiles_touched, reinterpret_cast<const uint32_t*>(g.depths), g.offsets,
+                                                 g.scan_state, g.hdr, nb);
     return check_cuda(cudaGetLastError(), "tile_scan launch");
 }
 

@@ -16,6 +16,7 @@ from hairgs_b200 import _lib as L
 NUM_CHANNELS = 3
 SYNC_FREE = True        # False: size the binning workspace exactly, after a blocking read-back (reference behaviour)
 _capacity_hint = {}     # (device, P, H, W) -> instance capacity to try first
+_depth_bits_hint = {}   # (device, P, H, W) -> sort_depth_bits to try first (depth-range compaction of the sort keys)
 _pinned_pool = []
 _pinned_next = 0
 
@@ -28,11 +29,29 @@ def _next_capacity(old, n):
     return max(old or 0, want)
 
 
+def _tile_bits(H, W):
+    # tile_id_bits in csrc/hgs_common.cuh (the reference's getHigherMsb of the tile count, rasterizer_impl.cu:300)
+    return (((W + 15) // 16) * ((H + 15) // 16)).bit_length()
+
+
+def _depth_range_bits(host):
+    """Bits needed for (depth_max - depth_min) of the visible Gaussians, from the read-back words 3-4."""
+    dmax, dmin = int(host[3]) & 0xffffffff, (~int(host[4])) & 0xffffffff
+    return max(1, (dmax - dmin).bit_length()) if dmax >= dmin else 1
+
+
+def _next_depth_bits(H, W, need):
+    """Hint for the next call: as many depth bits as fit in the number of 8-bit passes `need` bits take anyway."""
+    tb = _tile_bits(H, W)
+    passes = (tb + need + 7) // 8
+    return min(32, passes * 8 - tb)
+
+
 def _pinned_triplet():
-    """Small ring of pinned int32[3] buffers for the async (num_rendered, -, overflow) read-back."""
+    """Small ring of pinned int32[8] buffers for the async (num_rendered, -, overflow, depth_max, ~depth_min) read-back."""
     global _pinned_next
     if len(_pinned_pool) < 64:
-        _pinned_pool.append(torch.zeros(3, dtype=torch.int32).pin_memory())
+        _pinned_pool.append(torch.zeros(8, dtype=torch.int32).pin_memory())
         return _pinned_pool[-1]
     _pinned_next = (_pinned_next + 1) % 64
     return _pinned_pool[_pinned_next]
@@ -100,6 +119,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         ready.record(torch.cuda.current_stream(dev))
         key = (dev.index, P, H, W)
         cap = _capacity_hint.get(key) if SYNC_FREE else None
+        prm.sort_depth_bits = _depth_bits_hint.get(key, 0) if SYNC_FREE else 0
         binning = None
         if cap is not None:
             binning = torch.empty((lib.hgs_binning_bytes(cap, C),), **u8)
@@ -108,15 +128,23 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                     "forward stage B")
         ready.synchronize()
         N, overflow = int(host[0]), int(host[2])
-        if overflow != 0 or N < 0:
+        if (overflow & 1) != 0 or N < 0:
             raise L.HgsError("instance count overflows int32")
-        if cap is None or N > cap:
-            binning = torch.empty((lib.hgs_binning_bytes(N, C),), **u8)
+        need = _depth_range_bits(host)
+        fits = prm.sort_depth_bits in (0, 32) or need <= prm.sort_depth_bits
+        if cap is None or N > cap or not fits:
+            if cap is None or N > cap:
+                binning = torch.empty((lib.hgs_binning_bytes(N, C),), **u8)
+                cap_b = N
+            else:
+                cap_b = cap
+            prm.sort_depth_bits = _next_depth_bits(H, W, need) if SYNC_FREE else 0
             L.check(lib.hgs_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
-                                            binning.data_ptr() if N > 0 else None, img.data_ptr(), N, radii.data_ptr(),
-                                            out_color.data_ptr(), stream), "forward stage B")
+                                            binning.data_ptr() if cap_b > 0 else None, img.data_ptr(), cap_b,
+                                            radii.data_ptr(), out_color.data_ptr(), stream), "forward stage B")
         # next guess: 25 % head-room, rounded up to the 4096-instance granularity hgs_binning_capacity inverts
         _capacity_hint[key] = _next_capacity(_capacity_hint.get(key), N)
+        _depth_bits_hint[key] = max(_depth_bits_hint.get(key, 0), _next_depth_bits(H, W, need))
     del keep
     return N, out_color, radii, geom, binning, img
 

@@ -23,7 +23,8 @@ HGS_MAX_CHANNELS = 8
 class RasterParams(ctypes.Structure):
     _fields_ = [("P", c_int32), ("D", c_int32), ("M", c_int32), ("width", c_int32), ("height", c_int32),
                 ("channels", c_int32), ("tan_fovx", c_float), ("tan_fovy", c_float),
-                ("scale_modifier", c_float), ("prefiltered", c_int32), ("debug", c_int32)]
+                ("scale_modifier", c_float), ("prefiltered", c_int32), ("debug", c_int32),
+                ("sort_depth_bits", c_int32)]
 
 
 class RasterInputs(ctypes.Structure):
@@ -132,7 +133,7 @@ def load():
     lib.hgs_profile_collect.argtypes = [c_void_p, c_void_p]
     lib.hgs_stage_name.restype = c_char_p
     lib.hgs_stage_name.argtypes = [c_int]
-    if lib.hgs_abi_version() != 1:
+    if lib.hgs_abi_version() != 2:
         raise ImportError("libhairgs_rast.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -64,6 +64,7 @@ class _RasterizeStrands(torch.autograd.Function):
             ready.record(torch.cuda.current_stream(dev))
             key = (dev.index, P, H, W, 7)
             cap = _dgr._capacity_hint.get(key) if _dgr.SYNC_FREE else None
+            prm.sort_depth_bits = _dgr._depth_bits_hint.get(key, 0) if _dgr.SYNC_FREE else 0
             binning = None
             if cap is not None:
                 binning = torch.empty((lib.hgs_binning_bytes(cap, 7),), **u8)
@@ -72,15 +73,20 @@ class _RasterizeStrands(torch.autograd.Function):
                         "strands stage B")
             ready.synchronize()
             N, overflow = int(host[0]), int(host[2])
-            if overflow != 0 or N < 0:
+            if (overflow & 1) != 0 or N < 0:
                 raise L.HgsError("instance count overflows int32")
-            if cap is None or N > cap:
-                cap = N
-                binning = torch.empty((lib.hgs_binning_bytes(N, 7),), **u8)
+            need = _dgr._depth_range_bits(host)
+            fits = prm.sort_depth_bits in (0, 32) or need <= prm.sort_depth_bits
+            if cap is None or N > cap or not fits:
+                if cap is None or N > cap:
+                    cap = N
+                    binning = torch.empty((lib.hgs_binning_bytes(N, 7),), **u8)
+                prm.sort_depth_bits = _dgr._next_depth_bits(H, W, need) if _dgr.SYNC_FREE else 0
                 L.check(lib.hgs_strands_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
-                                                        binning.data_ptr() if N > 0 else None, img.data_ptr(), N,
+                                                        binning.data_ptr() if cap > 0 else None, img.data_ptr(), cap,
                                                         image.data_ptr(), stream), "strands stage B")
             _dgr._capacity_hint[key] = _dgr._next_capacity(_dgr._capacity_hint.get(key), N)
+            _dgr._depth_bits_hint[key] = max(_dgr._depth_bits_hint.get(key, 0), _dgr._next_depth_bits(H, W, need))
         ctx.settings, ctx.capacity, ctx.num_rendered = settings, cap, N
         ctx.save_for_backward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit, features, geom, binning, img)
         ctx.mark_non_differentiable(radii)

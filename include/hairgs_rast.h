@@ -54,7 +54,7 @@
 extern "C" {
 #endif
 
-#define HGS_ABI_VERSION 1
+#define HGS_ABI_VERSION 2
 #define HGS_TILE 16            /* BLOCK_X == BLOCK_Y == 16, cuda_rasterizer/config.h:16-17 */
 #define HGS_MAX_CHANNELS 8     /* colour channels per pass: 3 (reference) .. 8 (fused RGB+mask+orientation) */
 
@@ -80,6 +80,12 @@ typedef struct hgs_raster_params {
     float scale_modifier;
     int32_t prefiltered;    /* reference traps when a prefiltered point is culled; we report HGS_ERR_INVALID lazily via debug */
     int32_t debug;          /* synchronise + check after every stage (auxiliary.h:166-173) */
+    int32_t sort_depth_bits;/* 0 or 32: sort on the full 32 depth bits (reference key).  1..31: the caller asserts that the
+                             * bit patterns of all visible depths span less than 2^sort_depth_bits; the sort then drops
+                             * the unused high bits (fewer passes).  The range is known after stage A
+                             * (hgs_forward_read_num_rendered words 3-4): a caller that enqueued stage B on a hint must
+                             * check (depth_max - depth_min) >> sort_depth_bits == 0 and otherwise repeat stage B with 0
+                             * (the device also raises bit 1 of the overflow word).  Only read by the stage-B entries. */
 } hgs_raster_params;
 
 /* Device pointers of the per-Gaussian inputs (rasterizer.h:33-58 pointer arguments). */
@@ -175,7 +181,9 @@ int hgs_rasterize_forward(hgs_alloc_fn geom_alloc, void* geom_user,
 /* The same pass in three stream-ordered stages, for callers that own their workspaces and want to
  * overlap the instance-count read-back (no allocation, no implicit synchronisation):
  *   A  preprocess + tile-count scan; leaves num_rendered in the geometry workspace
- *   (read it with hgs_forward_read_num_rendered: async copy into pinned host memory)
+ *   (read it with hgs_forward_read_num_rendered: async copy of FIVE uint32 into pinned host memory:
+ *    num_rendered, -, overflow flags, depth_max, ~depth_min — the last two are the bit patterns bounding the depths of
+ *    the visible Gaussians, see hgs_raster_params.sort_depth_bits)
  *   B  key emission + (tile|depth) radix sort + tile ranges + compositing.  `capacity` is the number of
  *      instances binning_ws was sized for (hgs_binning_bytes(capacity, channels)); the live count is read from
  *      the geometry workspace ON THE DEVICE, so B may be enqueued before the host knows it.  If the count

@@ -25,11 +25,11 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(L.LIB_PATH)
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/hairgs_rast.h but not exported"
-    assert L.load().hgs_abi_version() == 1
+    assert L.load().hgs_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(L.RasterParams) == 11 * 4
+    assert ctypes.sizeof(L.RasterParams) == 12 * 4
     assert ctypes.sizeof(L.RasterInputs) == 11 * 8
     assert ctypes.sizeof(L.RasterGrads) == 9 * 8
 
