@@ -232,13 +232,26 @@ class Harness:
         self.fparams = {n: p for n, p in m.named_parameters() if p.numel() > 0}
         from hairgs_b200 import multiview
         self.fbucket = multiview.GradBucket({n: p.shape for n, p in self.fparams.items()}, self.dev)
+        self.fbucket.attach_to(self.fparams)
+        self.fsink = self._grad_sink()
+
+    def _grad_sink(self):
+        """The strand backward writes the parameter gradients straight into the slices of the flat bucket that the
+        parameters' .grad point at (fused.GradSink): no autograd accumulation kernels, no bucket clear."""
+        m = self.model
+        if m._features_rest.numel() != 0 or os.environ.get("HGS_BENCH_NO_SINK"):
+            return None     # features = cat(dc, rest): left to autograd
+        return self.fused_mod.GradSink({"endpoints": m._endpoints.grad, "width": m._width.grad, "opacity": m._opacity.grad,
+                                        "mask": m._mask.grad, "features": m._features_dc.grad})
 
     def step_resident_fused(self, it):
         cam = self.cams[self.my_views[it % len(self.my_views)]]
         m = self.model
-        self.fbucket.zero_()
-        self.fbucket.attach_to(self.fparams)
-        out = self.fused_mod.render_strands(cam, m, self.bg7)
+        if self.fsink is None:
+            self.fbucket.zero_()
+        else:
+            self.fsink.begin_step()
+        out = self.fused_mod.render_strands(cam, m, self.bg7, grad_sink=self.fsink)
         out["image7"].backward(self.dL7)
         self.fbucket.all_reduce()
         self.last_N = 0
@@ -251,8 +264,10 @@ class Harness:
         self.fused = fused
         self.opt_mode = optimizer
         if fused:
+            from hairgs_b200 import fused as fused_mod
             from hairgs_b200.fused import render_strands
             from hairgs_b200 import losses
+            self.fused_mod = fused_mod
             self.render_strands = render_strands
             self.weighted_l1 = losses.weighted_l1
             self.hair_image_loss = losses.hair_image_loss
@@ -282,6 +297,7 @@ class Harness:
                 for p in self.params:
                     p.grad = None
                 self.opt = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+        self.esink = self._grad_sink() if fused else None
         if getattr(self, "copy_stream", None) is not None:
             self._prefetched = -1
             return
@@ -330,7 +346,9 @@ class Harness:
         cam = Camera(base.image_width, base.image_height, base.FoVx, base.FoVy, cd[0:16].view(4, 4), cd[16:32].view(4, 4),
                      cd[32:35])
         tgt = self.tgt_dev[slot]
-        if self.opt_mode is None:
+        if self.esink is not None:
+            self.esink.begin_step()
+        elif self.opt_mode is None:
             self.flat_grad.zero_()
         m = self.model
         loss = None
@@ -338,11 +356,11 @@ class Harness:
         if self.fused and self.hair_loss:
             # ONE fused pass: strand parameterisation + 7 channels (hairgs_b200.fused.render_strands), then Hair-GS's
             # image loss (l1 + d-ssim + BCE mask + orientation, loss/losses.py:319-346) as one fused op
-            out = self.render_strands(cam, m, self.bg7)
+            out = self.render_strands(cam, m, self.bg7, grad_sink=self.esink)
             loss, _ = self.hair_image_loss(out["image7"], tgt[0:3], tgt[3], tgt[4], tgt[5],
                                            self.view_rot[it % len(self.my_views)], orient_mask=tgt[3] > 0.5, **lam)
         elif self.fused:
-            out = self.render_strands(cam, m, self.bg7)
+            out = self.render_strands(cam, m, self.bg7, grad_sink=self.esink)
             loss = self.weighted_l1(out["image7"], tgt, self.w7)
         elif self.hair_loss:
             # the reference's composition: three render() calls (loss/losses.py:245-248, 311-312, train.py:146-155) and
@@ -359,7 +377,8 @@ class Harness:
         if self.world > 1:
             torch.distributed.all_reduce(self.opt.grads.flat if self.opt_mode == "flat" else self.flat_grad)
         if self.opt_mode == "flat":
-            self.opt.step(grad_scale=1.0 / self.world)   # clears the gradient bucket too
+            # the sink overwrites the bucket on the next step, so the optimiser kernel need not clear it
+            self.opt.step(grad_scale=1.0 / self.world, zero_grad=self.esink is None)
         elif self.opt_mode == "torch":
             self.opt.step()
             self.opt.zero_grad(set_to_none=True)

@@ -263,7 +263,8 @@ int hgs_strands_backward(const hgs_raster_params* prm, const hgs_strand_inputs* 
         !gr->dL_dwidth || !gr->dL_dopacity_logit || !gr->dL_dmask_logit || !gr->dL_dfeatures) { set_error("missing gradient output pointer"); return HGS_ERR_INVALID; }
     if (!geom_ws || !image_ws || !dL_dpix || (R > 0 && !binning_ws)) { set_error("null workspace"); return HGS_ERR_INVALID; }
     const int P = prm->P;
-    if (int e = check_cuda(cudaMemsetAsync(gr->dL_dendpoints, 0, (size_t)in->num_endpoints * 3 * 4, s), "memset dL_dendpoints")) return e;
+    if (!gr->accumulate)
+        if (int e = check_cuda(cudaMemsetAsync(gr->dL_dendpoints, 0, (size_t)in->num_endpoints * 3 * 4, s), "memset dL_dendpoints")) return e;
     if (P == 0) return HGS_OK;
     GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels);
     ImageLayout im = carve_image((void*)image_ws, prm->width, prm->height);

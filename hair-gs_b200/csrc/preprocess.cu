@@ -514,6 +514,7 @@ struct PreBwdArgs {
     float* dL_dwidth;             // [P]
     float* dL_dopacity_logit;     // [P]
     float* dL_dmask_logit;        // [P]
+    int accumulate;               // strand entry: add to the gradient outputs instead of overwriting them
 };
 
 __device__ __forceinline__ float3 dnormvdv3(const float3 v, const float3 dv) {  // auxiliary.h:107-117
@@ -531,6 +532,10 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.P) return;
     const bool has_sh = (a.shs != nullptr) && a.M > 0;
+    // gradient outputs of the strand entry are either written (every element exactly once) or, when the caller sinks
+    // several views into one bucket, added to what is there
+    const bool acc_out = kStrand && a.accumulate;
+    auto put = [acc_out](float* p, float v) { *p = acc_out ? *p + v : v; };
     const bool has_sr = !kStrand && (a.scales != nullptr);
 
     // start every input stream before the visibility test
@@ -556,10 +561,12 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
 
     if (kStrand) {
         if (!(a.tiles_touched[idx] > 0)) {
-            a.dL_dwidth[idx] = 0.f;
-            a.dL_dopacity_logit[idx] = 0.f;
-            a.dL_dmask_logit[idx] = 0.f;
-            for (int i = 0; i < a.M * 3; ++i) a.dL_dsh[(size_t)idx * a.M * 3 + i] = 0.f;
+            if (!a.accumulate) {
+                a.dL_dwidth[idx] = 0.f;
+                a.dL_dopacity_logit[idx] = 0.f;
+                a.dL_dmask_logit[idx] = 0.f;
+                for (int i = 0; i < a.M * 3; ++i) a.dL_dsh[(size_t)idx * a.M * 3 + i] = 0.f;
+            }
             return;
         }
     } else if (!(a.radii[idx] > 0)) {
@@ -711,15 +718,15 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
         float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
         int written = 1;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) dsh[0 * 3 + c] = kSH_C0 * dRGB[c];
+        for (int c = 0; c < 3; ++c) put(dsh + (0 * 3 + c), kSH_C0 * dRGB[c]);
         if (a.D > 0) {
             written = 4;
             const float d1 = -kSH_C1 * y, d2 = kSH_C1 * z, d3 = -kSH_C1 * x;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                dsh[1 * 3 + c] = d1 * dRGB[c];
-                dsh[2 * 3 + c] = d2 * dRGB[c];
-                dsh[3 * 3 + c] = d3 * dRGB[c];
+                put(dsh + (1 * 3 + c), d1 * dRGB[c]);
+                put(dsh + (2 * 3 + c), d2 * dRGB[c]);
+                put(dsh + (3 * 3 + c), d3 * dRGB[c]);
                 dRGBdx[c] = -kSH_C1 * sh[3 * 3 + c];
                 dRGBdy[c] = -kSH_C1 * sh[1 * 3 + c];
                 dRGBdz[c] = kSH_C1 * sh[2 * 3 + c];
@@ -732,11 +739,11 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
                 const float d7 = kSH_C2[3] * xz, d8 = kSH_C2[4] * (xx - yy);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    dsh[4 * 3 + c] = d4 * dRGB[c];
-                    dsh[5 * 3 + c] = d5 * dRGB[c];
-                    dsh[6 * 3 + c] = d6 * dRGB[c];
-                    dsh[7 * 3 + c] = d7 * dRGB[c];
-                    dsh[8 * 3 + c] = d8 * dRGB[c];
+                    put(dsh + (4 * 3 + c), d4 * dRGB[c]);
+                    put(dsh + (5 * 3 + c), d5 * dRGB[c]);
+                    put(dsh + (6 * 3 + c), d6 * dRGB[c]);
+                    put(dsh + (7 * 3 + c), d7 * dRGB[c]);
+                    put(dsh + (8 * 3 + c), d8 * dRGB[c]);
                     dRGBdx[c] += kSH_C2[0] * y * sh[4 * 3 + c] + kSH_C2[2] * 2.f * -x * sh[6 * 3 + c] +
                                  kSH_C2[3] * z * sh[7 * 3 + c] + kSH_C2[4] * 2.f * x * sh[8 * 3 + c];
                     dRGBdy[c] += kSH_C2[0] * x * sh[4 * 3 + c] + kSH_C2[1] * z * sh[5 * 3 + c] +
@@ -755,13 +762,13 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
                     const float d15 = kSH_C3[6] * x * (xx - 3.f * yy);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        dsh[9 * 3 + c] = d9 * dRGB[c];
-                        dsh[10 * 3 + c] = d10 * dRGB[c];
-                        dsh[11 * 3 + c] = d11 * dRGB[c];
-                        dsh[12 * 3 + c] = d12 * dRGB[c];
-                        dsh[13 * 3 + c] = d13 * dRGB[c];
-                        dsh[14 * 3 + c] = d14 * dRGB[c];
-                        dsh[15 * 3 + c] = d15 * dRGB[c];
+                        put(dsh + (9 * 3 + c), d9 * dRGB[c]);
+                        put(dsh + (10 * 3 + c), d10 * dRGB[c]);
+                        put(dsh + (11 * 3 + c), d11 * dRGB[c]);
+                        put(dsh + (12 * 3 + c), d12 * dRGB[c]);
+                        put(dsh + (13 * 3 + c), d13 * dRGB[c]);
+                        put(dsh + (14 * 3 + c), d14 * dRGB[c]);
+                        put(dsh + (15 * 3 + c), d15 * dRGB[c]);
                         dRGBdx[c] += (kSH_C3[0] * sh[9 * 3 + c] * 3.f * 2.f * xy + kSH_C3[1] * sh[10 * 3 + c] * yz +
                                       kSH_C3[2] * sh[11 * 3 + c] * -2.f * xy + kSH_C3[3] * sh[12 * 3 + c] * -3.f * 2.f * xz +
                                       kSH_C3[4] * sh[13 * 3 + c] * (-3.f * xx + 4.f * zz - yy) +
@@ -779,7 +786,7 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
         }
         // coefficients above the active degree: defined zeros (reference: memset)
         for (int k = written; k < a.M; ++k) {
-            dsh[k * 3 + 0] = 0.f; dsh[k * 3 + 1] = 0.f; dsh[k * 3 + 2] = 0.f;
+            put(dsh + (k * 3 + 0), 0.f); put(dsh + (k * 3 + 1), 0.f); put(dsh + (k * 3 + 2), 0.f);
         }
         const float3 dL_ddir = make_float3(dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2],
                                            dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2],
@@ -788,7 +795,7 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
         dmean.x += dsm.x;
         dmean.y += dsm.y;
         dmean.z += dsm.z;
-    } else if (a.dL_dsh) {
+    } else if (a.dL_dsh && !a.accumulate) {
         for (int i = 0; i < a.M * 3; ++i) a.dL_dsh[(size_t)idx * a.M * 3 + i] = 0.f;
     }
     if (kStrand) {
@@ -808,7 +815,7 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
         // scale_modifier), and Hair-GS's autograd then chains that through exp()/norm(): reproduced here so both entries
         // train identically for scaling_modifier != 1 (they coincide at the training value 1.0).
         (void)mod;
-        a.dL_dwidth[idx] = dL_db * 2.f * sg.syz * sg.ew;  // "dL_dscale_y + dL_dscale_z" = dL_db * 2 syz, times dexp(w)/dw
+        put(a.dL_dwidth + idx, dL_db * 2.f * sg.syz * sg.ew);  // "dL_dscale_y + dL_dscale_z" = dL_db * 2 syz, times dexp(w)/dw
         // sx = max(dist/2*k, 1e-7)*mod
         const bool sx_live = sg.dist * 0.5f * kDistToScale > kMinVal;
         const float dL_ddist = sx_live ? dL_da * 2.f * sg.sx * (0.5f * kDistToScale) : 0.f;
@@ -831,8 +838,8 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
         atomicAdd(a.dL_dendpoints + 3 * i1 + 1, 0.5f * dmean.y + dL_ddiff.y);
         atomicAdd(a.dL_dendpoints + 3 * i1 + 2, 0.5f * dmean.z + dL_ddiff.z);
         const float o = sigmoidf_(a.opacity_logit[idx]), m = sigmoidf_(a.mask_logit[idx]);
-        a.dL_dopacity_logit[idx] = a.dL_dopacity[idx] * o * (1.f - o);
-        a.dL_dmask_logit[idx] = dcol[3] * m * (1.f - m);
+        put(a.dL_dopacity_logit + idx, a.dL_dopacity[idx] * o * (1.f - o));
+        put(a.dL_dmask_logit + idx, dcol[3] * m * (1.f - m));
         return;
     }
     a.dL_dmean3D[3 * idx] = dmean.x;
@@ -1021,6 +1028,7 @@ int launch_preprocess_bwd(const hgs_raster_params* prm, const hgs_raster_inputs*
     a.scales = in->scales; a.rotations = in->rotations; a.cov3D_precomp = in->cov3D_precomp;
     a.viewmatrix = in->viewmatrix; a.projmatrix = in->projmatrix; a.cam_pos = in->cam_pos;
     a.dL_dmean2D = gr->dL_dmean2D; a.dL_dconic = gr->dL_dconic; a.dL_dcolor = gr->dL_dcolor;
+    a.accumulate = 0;
     a.dL_dmean3D = gr->dL_dmean3D; a.dL_dcov3D = gr->dL_dcov3D; a.dL_dsh = gr->dL_dsh;
     a.dL_dscale = gr->dL_dscale; a.dL_drot = gr->dL_drot;
     a.tiles_touched = g.tiles_touched; a.endpoints = nullptr; a.pairs = nullptr; a.width = nullptr;
@@ -1048,6 +1056,7 @@ int launch_strand_preprocess_bwd(const hgs_raster_params* prm, const hgs_strand_
     a.width = in->width; a.opacity_logit = in->opacity_logit; a.mask_logit = in->mask_logit;
     a.dL_dopacity = gr->dL_dopacity; a.dL_dendpoints = gr->dL_dendpoints; a.dL_dwidth = gr->dL_dwidth;
     a.dL_dopacity_logit = gr->dL_dopacity_logit; a.dL_dmask_logit = gr->dL_dmask_logit;
+    a.accumulate = gr->accumulate ? 1 : 0;
     StageScope prof(HGS_STAGE_PREPROCESS_BWD, s);
     preprocess_bwd_kernel<true><<<(prm->P + 255) / 256, 256, 0, s>>>(a);
     return check_cuda(cudaGetLastError(), "strand preprocess_bwd launch");

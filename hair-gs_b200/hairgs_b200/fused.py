@@ -103,36 +103,66 @@ class _RasterizeStrands(torch.autograd.Function):
             dpix = L.f32c(grad_image, "grad_image", dev)
             acc = torch.empty((P * 15,), **f32)  # mean2D 3 | conic 4 | opacity 1 | colour 7 : one memset in the library
             d_mean2D = acc[:3 * P].view(P, 3)
-            out = torch.empty((3 * E + 3 * P + 3 * M * P,), **f32)
-            d_end = out[:3 * E].view(E, 3)
-            d_width = out[3 * E:3 * E + P].view(P, 1)
-            d_opac = out[3 * E + P:3 * E + 2 * P].view(P, 1)
-            d_mask = out[3 * E + 2 * P:3 * E + 3 * P].view(P, 1)
-            d_feat = out[3 * E + 3 * P:].view(P, M, 3)
+            sink = ctx.settings.get("grad_sink")
+            if sink is None:
+                out = torch.empty((3 * E + 3 * P + 3 * M * P,), **f32)
+                d_end = out[:3 * E].view(E, 3)
+                d_width = out[3 * E:3 * E + P].view(P, 1)
+                d_opac = out[3 * E + P:3 * E + 2 * P].view(P, 1)
+                d_mask = out[3 * E + 2 * P:3 * E + 3 * P].view(P, 1)
+                d_feat = out[3 * E + 3 * P:].view(P, M, 3)
+                accumulate = 0
+            else:
+                # the kernel deposits the parameter gradients straight into the caller's tensors (slices of a flat
+                # gradient bucket): no autograd AccumulateGrad adds, no bucket clear before the first view
+                d_end, d_width, d_opac, d_mask, d_feat = (sink.tensors[k] for k in ("endpoints", "width", "opacity", "mask",
+                                                                                     "features"))
+                for t, n in ((d_end, 3 * E), (d_width, P), (d_opac, P), (d_mask, P), (d_feat, 3 * M * P)):
+                    if t.numel() != n or t.dtype != torch.float32 or t.device != dev or not t.is_contiguous():
+                        raise L.HgsError("grad_sink: tensors must be contiguous float32 on the render device, shaped like "
+                                         "the parameters")
+                accumulate = 1 if sink.accumulate else 0
+                sink.accumulate = True      # later views of the same optimiser step add to the first
             grads = L.StrandGrads(dL_dmean2D=acc.data_ptr(), dL_dconic=acc[3 * P:].data_ptr(),
                                   dL_dopacity=acc[7 * P:].data_ptr(), dL_dcolor=acc[8 * P:].data_ptr(),
                                   dL_dendpoints=d_end.data_ptr(), dL_dwidth=d_width.data_ptr(),
                                   dL_dopacity_logit=d_opac.data_ptr(), dL_dmask_logit=d_mask.data_ptr(),
-                                  dL_dfeatures=d_feat.data_ptr())
+                                  dL_dfeatures=d_feat.data_ptr(), accumulate=accumulate)
             L.check(lib.hgs_strands_backward(ctypes.byref(prm), ctypes.byref(inp), int(ctx.capacity), geom.data_ptr(),
                                              L.ptr(binning), img.data_ptr(), dpix.data_ptr(), ctypes.byref(grads),
                                              L.stream_ptr(dev)), "strands backward")
+        if sink is not None:
+            return (None, None, None, None, None, None, d_mean2D, None)
         return (d_end, None, d_width.view_as(width), d_opac.view_as(opacity_logit), d_mask.view_as(mask_logit), d_feat,
                 d_mean2D, None)
 
 
+class GradSink:
+    """Where the strand backward deposits the parameter gradients instead of returning them through autograd:
+    tensors = {"endpoints": [E,3], "width": [P,1], "opacity": [P,1], "mask": [P,1], "features": [P,M,3]} — typically the
+    slices of a multiview.GradBucket / FlatAdam gradient buffer that the parameters' .grad already point at.  The first
+    backward after begin_step() overwrites them (no clear needed), later ones add."""
+
+    def __init__(self, tensors):
+        self.tensors = tensors
+        self.accumulate = False
+
+    def begin_step(self):
+        self.accumulate = False
+
+
 def rasterize_strands(endpoints, endpoint_pairs, width, opacity_logit, mask_logit, features, means2D, *, image_height,
                       image_width, tanfovx, tanfovy, bg, scale_modifier, viewmatrix, projmatrix, sh_degree, campos,
-                      debug=False):
+                      debug=False, grad_sink=None):
     """-> (image[7,H,W] = rgb | mask | orientation, radii[P])."""
     settings = dict(image_height=image_height, image_width=image_width, tanfovx=tanfovx, tanfovy=tanfovy, bg=bg,
                     scale_modifier=scale_modifier, viewmatrix=viewmatrix, projmatrix=projmatrix, sh_degree=sh_degree,
-                    campos=campos, debug=debug)
+                    campos=campos, debug=debug, grad_sink=grad_sink)
     return _RasterizeStrands.apply(endpoints, endpoint_pairs, width, opacity_logit, mask_logit, features, means2D,
                                    settings)
 
 
-def render_strands(viewpoint_camera, pc, bg_color, scaling_modifier=1.0, debug=False):
+def render_strands(viewpoint_camera, pc, bg_color, scaling_modifier=1.0, debug=False, grad_sink=None):
     """One-pass counterpart of the three render() calls of a Hair-GS Stage-III iteration.  `pc` is a
     HairGaussianModel-like object (hairgs_b200.models.StrandModel): _endpoints, endpoint_pairs, _width, _opacity, _mask,
     get_features, active_sh_degree.  bg_color: [7].  Returns render / mask / orientation images plus the usual
@@ -149,6 +179,6 @@ def render_strands(viewpoint_camera, pc, bg_color, scaling_modifier=1.0, debug=F
         tanfovx=math.tan(viewpoint_camera.FoVx * 0.5), tanfovy=math.tan(viewpoint_camera.FoVy * 0.5), bg=bg_color,
         scale_modifier=scaling_modifier, viewmatrix=viewpoint_camera.world_view_transform,
         projmatrix=viewpoint_camera.full_proj_transform, sh_degree=pc.active_sh_degree,
-        campos=viewpoint_camera.camera_center, debug=debug)
+        campos=viewpoint_camera.camera_center, debug=debug, grad_sink=grad_sink)
     return {"render": image[0:3], "mask": image[3:4], "orientation": image[4:7], "image7": image,
             "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii}

@@ -148,6 +148,8 @@ typedef struct hgs_strand_grads {
     float* dL_dopacity_logit; /* [P] */
     float* dL_dmask_logit;    /* [P] */
     float* dL_dfeatures;      /* [P,M,3] */
+    int32_t accumulate;       /* 0: the five parameter gradients above are overwritten (every element written once);
+                               * 1: they are ADDED to (several views sunk into one gradient bucket) */
 } hgs_strand_grads;
 
 int hgs_strands_forward_stage_a(const hgs_raster_params* prm, const hgs_strand_inputs* in, void* geom_ws,
