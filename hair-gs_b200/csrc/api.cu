@@ -76,6 +76,7 @@ int launch_composite_fwd(int, const ImageLayout&, const BinningLayout&, int, int
 int launch_composite_bwd(int, const ImageLayout&, const BinningLayout&, const uint32_t*, int, int, const float*,
                          const float*, const hgs_raster_grads*, cudaStream_t);
 int set_fwd_stats(void* dev_ptr);
+int set_composite_blocks(int mode);
 int launch_weighted_l1(int, long long, const float*, const float*, const float*, float*, float*, cudaStream_t);
 int launch_hair_image_loss(const hgs_hair_loss&, cudaStream_t);
 int launch_adam_flat(long long, float*, float*, float*, float*, int, const int64_t*, const float*, int, float, float, float,
@@ -122,6 +123,8 @@ using namespace hgs;
 extern "C" {
 
 int hgs_debug_set_stats(void* dev_ptr) { return set_fwd_stats(dev_ptr); }
+
+int hgs_debug_set_composite_blocks(int mode) { return set_composite_blocks(mode); }
 
 int hgs_profile_enable(int on) {
     g_prof_on = on != 0;

@@ -23,6 +23,9 @@
 //    red.global.add's — see the comment above composite_bwd_kernel.
 #include "hgs_common.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace hgs {
 
 // optional per-(tile,warp) work statistics of the forward compositor (debug; set through hgs_debug_set_stats)
@@ -233,6 +236,217 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const uint2* __restr
                 if (__all_sync(0xffffffffu, done)) break;
             }
         }
+    }
+
+    if (inside) {
+        final_T[pix_id] = T;
+        n_contrib[pix_id] = last_contributor;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) out_color[(size_t)ch * H * W + pix_id] = Cacc[ch] + T * bg_color[ch];
+    }
+    if (g_fwd_stats != nullptr) {
+        st_blend = __reduce_add_sync(0xffffffffu, st_blend);
+        const uint32_t ndone = __popc(__ballot_sync(0xffffffffu, done && inside));
+        if (lane == 0)
+            g_fwd_stats[tile * 8 + warp] = make_uint4(st_chunks, st_cand, st_blend, ndone | ((uint32_t)nchunks << 8));
+    }
+}
+
+// Forward compositor, half-warp edition.  Same walk as composite_fwd_kernel, but the warp's 8x4 pixel block is treated
+// as TWO 4x4 blocks (lanes 0-15 / 16-31): every chunk is culled against both, each half owns a small ring of compacted
+// candidates, and in one trip of the blend loop the two halves work on DIFFERENT instances.  Hair Gaussians reach ~2 px
+// from their centre, so a 4x4 block rejects many instances that the 8x4 block must keep: on cfg3 the blend loop runs
+// 34 % fewer trips (CPU model of the cull and of the queue policy: tools/block_shape_study.py).  Candidates carry over
+// from chunk to chunk, so the trips are always full pairs; the rings are drained in step as long as both halves have
+// work, and one-sided only when a ring could not take the next chunk.  A pixel still sees exactly the instances, in
+// list order, that can reach it, so pixels / final_T / n_contrib are unchanged bit for bit.
+template <int CS>
+struct FwdHalfSmem {
+    static constexpr int QN = 40;  // ring capacity per half: 32 new + <= 8 carried over
+    float4 q_lo[2][QN];
+    float4 q_hi[2][QN];            // (conic.c, opacity, list position + 1 as bits, -)
+    float4 q_col[2][QN * (CS / 4)];
+};
+
+template <int C, int CS>
+__global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __restrict__ ranges,
+                                                                 const uint32_t* __restrict__ tile_order, int W, int H,
+                                                                 const float4* __restrict__ pk_lo,
+                                                                 const float4* __restrict__ pk_hi,
+                                                                 const float4* __restrict__ pk_col,
+                                                                 const float* __restrict__ bg_color,
+                                                                 float* __restrict__ final_T,
+                                                                 uint32_t* __restrict__ n_contrib,
+                                                                 float* __restrict__ out_color) {
+    using WS = FwdHalfSmem<CS>;
+    constexpr uint32_t QN = WS::QN;
+    __shared__ WS s_ws[8];
+
+    constexpr bool kExactOrder = C <= 4;  // see composite_fwd_kernel
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t half = lane >> 4, hl = lane & 15;
+    WS& ws = s_ws[warp];
+    const uint32_t horizontal_blocks = (W + HGS_TILE - 1) / HGS_TILE;
+    const uint32_t tile = tile_order[blockIdx.x];
+    const uint32_t X0 = (tile % horizontal_blocks) * HGS_TILE, Y0 = (tile / horizontal_blocks) * HGS_TILE;
+    const uint32_t bx = X0 + (warp & 1) * 8, by = Y0 + (warp >> 1) * 4;
+    // lane = half * 16 + row * 4 + column: a warp-wide store still covers 4 rows x 32 contiguous bytes
+    const uint32_t px = bx + half * 4 + (hl & 3), py = by + (hl >> 2);
+    const uint32_t pix_id = W * py + px;
+    const float2 pixf = make_float2((float)px, (float)py);
+    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+    bool done = !inside;
+    const float ax0 = (float)bx, ax1 = (float)(bx + 3), bx0 = (float)(bx + 4), bx1 = (float)(bx + 7);
+    const float wy0 = (float)by, wy1 = (float)(by + 3);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    const uint2 range = ranges[tile];
+    const int total = (int)(range.y - range.x);
+    const int nchunks = (total + 31) >> 5;
+
+    float T = 1.0f;
+    uint32_t last_contributor = 0;
+    float Cacc[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) Cacc[ch] = 0.f;
+    uint32_t st_chunks = 0, st_cand = 0, st_blend = 0;
+
+    const float4* my_lo = ws.q_lo[half];
+    const float4* my_hi = ws.q_hi[half];
+    const float4* my_col = ws.q_col[half];
+    uint32_t head_a = 0, cnt_a = 0, head_b = 0, cnt_b = 0;  // warp-uniform ring state
+
+    // blends the first ta / tb queued candidates of the two halves, max(ta, tb) trips, two candidates per trip
+    // (independent expf chains, as in composite_fwd_kernel); a half that has run out re-reads a slot, predicated off
+    auto run = [&](const uint32_t ta, const uint32_t tb) {
+        const uint32_t my_n = half ? tb : ta;
+        const uint32_t my_head = half ? head_b : head_a;
+        const uint32_t ntrip = max(ta, tb);
+        st_cand += ntrip;
+        for (uint32_t j0 = 0; j0 < ntrip; j0 += 2) {
+            const bool act0 = j0 < my_n, act1 = j0 + 1 < my_n;
+            uint32_t i0 = my_head + (act0 ? j0 : 0u);
+            i0 = i0 >= QN ? i0 - QN : i0;
+            uint32_t i1 = act1 ? i0 + 1 : i0;
+            i1 = i1 >= QN ? i1 - QN : i1;
+            const float4 glo0 = my_lo[i0], ghi0 = my_hi[i0];
+            const float4 glo1 = my_lo[i1], ghi1 = my_hi[i1];
+            const float2 d0 = make_float2(glo0.x - pixf.x, glo0.y - pixf.y);
+            const float2 d1 = make_float2(glo1.x - pixf.x, glo1.y - pixf.y);
+            const float power0 = -0.5f * (glo0.z * d0.x * d0.x + ghi0.x * d0.y * d0.y) - glo0.w * d0.x * d0.y;
+            const float power1 = -0.5f * (glo1.z * d1.x * d1.x + ghi1.x * d1.y * d1.y) - glo1.w * d1.x * d1.y;
+            const float alpha0 = min(0.99f, ghi0.y * exp(power0));
+            const float alpha1 = min(0.99f, ghi1.y * exp(power1));
+            // same skip rules as forward.cu:336-345, evaluated as predicates
+            const bool ok0 = act0 && !(power0 > 0.0f) && !(alpha0 < 1.0f / 255.0f);
+            const bool ok1 = act1 && !(power1 > 0.0f) && !(alpha1 < 1.0f / 255.0f);
+            if (ok0 && !done) {
+                const float test_T = T * (1 - alpha0);
+                if (test_T < 0.0001f) {
+                    done = true;
+                } else {
+                    const float* col = reinterpret_cast<const float*>(&my_col[i0 * (CS / 4)]);
+                    const float w = alpha0 * T;
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) Cacc[ch] += kExactOrder ? col[ch] * alpha0 * T : col[ch] * w;
+                    T = test_T;
+                    last_contributor = __float_as_uint(ghi0.z);
+                    st_blend++;
+                }
+            }
+            if (ok1 && !done) {
+                const float test_T = T * (1 - alpha1);
+                if (test_T < 0.0001f) {
+                    done = true;
+                } else {
+                    const float* col = reinterpret_cast<const float*>(&my_col[i1 * (CS / 4)]);
+                    const float w = alpha1 * T;
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) Cacc[ch] += kExactOrder ? col[ch] * alpha1 * T : col[ch] * w;
+                    T = test_T;
+                    last_contributor = __float_as_uint(ghi1.z);
+                    st_blend++;
+                }
+            }
+        }
+        head_a += ta;
+        head_a = head_a >= QN ? head_a - QN : head_a;
+        cnt_a -= ta;
+        head_b += tb;
+        head_b = head_b >= QN ? head_b - QN : head_b;
+        cnt_b -= tb;
+        __syncwarp();  // the slots just consumed may be overwritten by the next push
+    };
+
+    if (!__all_sync(0xffffffffu, done) && nchunks > 0) {
+        float4 nlo = make_float4(0, 0, 0, 0), nhi = make_float4(0, 0, 0, 0), nc0 = make_float4(0, 0, 0, 0),
+               nc1 = make_float4(0, 0, 0, 0);
+        if ((int)lane < total) {
+            const size_t i = (size_t)range.x + lane;
+            nlo = pk_lo[i];
+            nhi = pk_hi[i];
+            nc0 = pk_col[i * (CS / 4)];
+            if (CS > 4) nc1 = pk_col[i * (CS / 4) + 1];
+        }
+        bool all_done = false;
+        for (int c = 0; c < nchunks; ++c) {
+            const float4 lo = nlo, hi = nhi, c0 = nc0, c1 = nc1;
+            const bool have = c * 32 + (int)lane < total;
+            if (c + 1 < nchunks) {  // prefetch the next chunk while this one is blended
+                const int p = (c + 1) * 32 + (int)lane;
+                if (p < total) {
+                    const size_t i = (size_t)range.x + p;
+                    nlo = pk_lo[i];
+                    nhi = pk_hi[i];
+                    nc0 = pk_col[i * (CS / 4)];
+                    if (CS > 4) nc1 = pk_col[i * (CS / 4) + 1];
+                }
+            }
+            // culled only when a comparison is TRUE, so NaNs keep the instance (the reference would evaluate it)
+            const float xl = lo.x - hi.z, xr = lo.x + hi.z;
+            const bool in_rows = have && !(lo.y - hi.w > wy1 || lo.y + hi.w < wy0);
+            const bool cand_a = in_rows && !(xl > ax1 || xr < ax0);
+            const bool cand_b = in_rows && !(xl > bx1 || xr < bx0);
+            const uint32_t bits_a = __ballot_sync(0xffffffffu, cand_a);
+            const uint32_t bits_b = __ballot_sync(0xffffffffu, cand_b);
+            st_chunks++;
+            if (!(bits_a | bits_b)) continue;
+            // push: each half's candidates go to ITS ring compacted (list order kept); the list position rides in the
+            // slot of the no longer needed cull extent
+            const float4 hi_tag = make_float4(hi.x, hi.y, __uint_as_float((uint32_t)(c * 32) + lane + 1u), 0.f);
+            if (cand_a) {
+                uint32_t slot = head_a + cnt_a + __popc(bits_a & lt_mask);
+                slot = slot >= QN ? slot - QN : slot;
+                ws.q_lo[0][slot] = lo;
+                ws.q_hi[0][slot] = hi_tag;
+                ws.q_col[0][slot * (CS / 4)] = c0;
+                if (CS > 4) ws.q_col[0][slot * (CS / 4) + 1] = c1;
+            }
+            if (cand_b) {
+                uint32_t slot = head_b + cnt_b + __popc(bits_b & lt_mask);
+                slot = slot >= QN ? slot - QN : slot;
+                ws.q_lo[1][slot] = lo;
+                ws.q_hi[1][slot] = hi_tag;
+                ws.q_col[1][slot * (CS / 4)] = c0;
+                if (CS > 4) ws.q_col[1][slot * (CS / 4) + 1] = c1;
+            }
+            cnt_a += __popc(bits_a);
+            cnt_b += __popc(bits_b);
+            __syncwarp();
+            // drain in step while both halves have a pair; one-sided only as far as the next push needs room
+            const uint32_t both = min(cnt_a, cnt_b) & ~1u;
+            if (both) run(both, both);
+            const uint32_t hi_cnt = max(cnt_a, cnt_b);
+            if (hi_cnt > QN - 32) {
+                const uint32_t over = (hi_cnt - (QN - 32) + 1u) & ~1u;
+                run(min(cnt_a, over), min(cnt_b, over));
+            }
+            if (__all_sync(0xffffffffu, done)) {
+                all_done = true;
+                break;
+            }
+        }
+        if (!all_done && (cnt_a | cnt_b)) run(cnt_a, cnt_b);
     }
 
     if (inside) {
@@ -500,6 +714,277 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_kernel(
     if (qcount > 0) process_group(qcount);
 }
 
+// Backward compositor, half-warp edition (see composite_fwd_half_kernel for the motivation): the warp's 8x4 pixels are
+// two 4x4 blocks with their own candidate rings.  A group is processed when BOTH rings hold 8 candidates (or one of
+// them could not take the next chunk):
+//   phase 1 (lanes = pixels): each half runs the recurrence over ITS up to 8 candidates, the two halves working on
+//            different instances in the same trip; (G, dL/dalpha, alpha*T) is parked per (half, candidate, pixel);
+//   phase 2 (lanes = half x candidate x pixel-octet): every lane sums its candidate's gradient terms over the
+//            contributing pixels of its octet, ONE shuffle level folds the two octets, and 16 lanes (one per queued
+//            candidate of either half) issue the red.global.adds.
+// cfg3, CPU model of the queue policy (tools/block_shape_study.py): 26 % fewer phase-1 trips than the 8x4 kernel; an
+// instance that reaches both halves is accumulated by both (1.3x the candidates, each over 16 instead of 32 pixels).
+template <int CS>
+struct BwdHalfSmem {
+    static constexpr int QN = 40;   // ring capacity per half: 32 new + <= 8 carried over
+    static constexpr int GR = 8;    // candidates per half and group
+    float4 q_lo[2][QN];
+    float4 q_hi[2][QN];             // (conic.c, opacity, list position as bits, Gaussian id as bits)
+    float4 q_col[2][QN * (CS / 4)];
+    float2 slab_gd[GR * 33];        // [candidate slot g][lane] (G, dL/dalpha): slot g of half A in lanes 0-15, of half B
+    float slab_w[GR * 33];          // in lanes 16-31; alpha * T.  Row stride 33 -> conflict-free in both phases
+    float4 dpix[32 * (CS / 4)];     // dL/dpixel of the warp's 32 pixels (indexed by lane)
+    uint32_t vmask[GR];             // bits 0-15: pixels of half A that candidate g of half A reached; 16-31: half B
+};
+
+template <int C, int CS>
+__global__ void __launch_bounds__(256, 3) composite_bwd_half_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
+    const uint32_t* __restrict__ point_list, int W, int H,
+    const float* __restrict__ bg_color, const float4* __restrict__ pk_lo, const float4* __restrict__ pk_hi,
+    const float4* __restrict__ pk_col, const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
+    const float* __restrict__ dL_dpixels, float* __restrict__ dL_dmean2D /*[P,3]*/,
+    float* __restrict__ dL_dconic /*[P,4]*/, float* __restrict__ dL_dopacity /*[P]*/,
+    float* __restrict__ dL_dcolors /*[P,C]*/) {
+    using WS = BwdHalfSmem<CS>;
+    constexpr uint32_t QN = WS::QN, GR = WS::GR;
+    extern __shared__ __align__(16) unsigned char bwd_smem_raw[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t half = lane >> 4, hl = lane & 15;
+    WS& ws = reinterpret_cast<WS*>(bwd_smem_raw)[warp];
+
+    const uint32_t horizontal_blocks = (W + HGS_TILE - 1) / HGS_TILE;
+    const uint32_t tile = tile_order[blockIdx.x];
+    const uint32_t X0 = (tile % horizontal_blocks) * HGS_TILE, Y0 = (tile / horizontal_blocks) * HGS_TILE;
+    const uint32_t bx = X0 + (warp & 1) * 8, by = Y0 + (warp >> 1) * 4;
+    const uint32_t px = bx + half * 4 + (hl & 3), py = by + (hl >> 2);
+    const uint32_t pix_id = W * py + px;
+    const float2 pixf = make_float2((float)px, (float)py);
+    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+    const float ax0 = (float)bx, wy0 = (float)by;
+
+    const uint2 range = ranges[tile];
+
+    const float T_final = inside ? final_Ts[pix_id] : 0;
+    float T = T_final;
+    const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
+
+    // nothing at list position >= the half's largest last_contributor can contribute to its 16 pixels
+    int total_mine = last_contributor;
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) total_mine = max(total_mine, __shfl_xor_sync(0xffffffffu, total_mine, o));
+    const int total_other = __shfl_xor_sync(0xffffffffu, total_mine, 16);
+    const int total_a = half ? total_other : total_mine, total_b = half ? total_mine : total_other;
+    const int total = max(total_a, total_b);
+    if (total == 0) return;
+    const int nchunks = (total + 31) >> 5;
+
+    float dL_dpixel[C];
+    float acc_dot = 0.f;  // <colour accumulated behind the current instance, dL/dpixel>
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) dL_dpixel[ch] = inside ? dL_dpixels[(size_t)ch * H * W + pix_id] : 0.f;
+    {
+        float tmp[8];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) tmp[ch] = ch < C ? dL_dpixel[ch] : 0.f;
+        ws.dpix[lane * (CS / 4)] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+        if (CS > 4) ws.dpix[lane * (CS / 4) + 1] = make_float4(tmp[4], tmp[5], tmp[6], tmp[7]);
+    }
+    float bg_dot_dpixel = 0;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) bg_dot_dpixel += bg_color[ch] * dL_dpixel[ch];
+    const float ddelx_dx = 0.5 * W;
+    const float ddely_dy = 0.5 * H;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    // phase-2 role of this lane: candidate my_g of half `half`, pixels [my_o * 8, my_o * 8 + 8) of that half
+    const uint32_t my_g = lane & 7, my_o = (lane >> 3) & 1;
+
+    const float4* my_lo = ws.q_lo[half];
+    const float4* my_hi = ws.q_hi[half];
+    const float4* my_col = ws.q_col[half];
+    uint32_t head_a = 0, cnt_a = 0, head_b = 0, cnt_b = 0;  // warp-uniform ring state
+
+    auto process_group = [&](const uint32_t na, const uint32_t nb) {
+        const uint32_t my_n = half ? nb : na;
+        const uint32_t my_head = half ? head_b : head_a;
+        const uint32_t ntrip = max(na, nb);
+        // ---- phase 1: lanes = pixels, each half over its own candidates in list order ---------------------------
+        auto evaluate = [&](uint32_t slot, float& G, float& alpha) -> bool {
+            const float4 glo = my_lo[slot];
+            const float4 ghi = my_hi[slot];
+            const int pos = __float_as_int(ghi.z);
+            bool valid = pos < last_contributor;  // false for outside pixels (last_contributor == 0)
+            const float2 d = make_float2(glo.x - pixf.x, glo.y - pixf.y);
+            const float power = -0.5f * (glo.z * d.x * d.x + ghi.x * d.y * d.y) - glo.w * d.x * d.y;
+            if (power > 0.0f) valid = false;
+            G = exp(power);
+            alpha = min(0.99f, ghi.y * G);
+            if (alpha < 1.0f / 255.0f) valid = false;
+            return valid;
+        };
+        // recurrence step of backward_distwar.cu:960-991 for one contributing (pixel, candidate) pair; see
+        // composite_bwd_kernel for the scalar form of the colour recurrence
+        auto recur = [&](uint32_t g, uint32_t slot, float G, float alpha) {
+            const float om = 1.f - alpha;
+            const float rcp = 1.f / om;
+            T = T * rcp;
+            const float dchannel_dcolor = alpha * T;
+            const float* col = reinterpret_cast<const float*>(&my_col[slot * (CS / 4)]);
+            float d = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) d += col[ch] * dL_dpixel[ch];
+            float dL_dalpha = d - acc_dot;
+            acc_dot = alpha * d + om * acc_dot;
+            dL_dalpha *= T;
+            dL_dalpha += (-T_final * rcp) * bg_dot_dpixel;
+            const uint32_t si = g * 33 + lane;
+            ws.slab_gd[si] = make_float2(G, dL_dalpha);
+            ws.slab_w[si] = dchannel_dcolor;
+        };
+        for (uint32_t g = 0; g < ntrip; g += 2) {
+            const bool act0 = g < my_n, act1 = g + 1 < my_n;
+            uint32_t slot0 = my_head + (act0 ? g : 0u);
+            slot0 = slot0 >= QN ? slot0 - QN : slot0;
+            uint32_t slot1 = act1 ? slot0 + 1 : slot0;
+            slot1 = slot1 >= QN ? slot1 - QN : slot1;
+            float G0, a0, G1, a1;
+            const bool v0 = evaluate(slot0, G0, a0) && act0;
+            const bool v1 = evaluate(slot1, G1, a1) && act1;
+            const uint32_t vm0 = __ballot_sync(0xffffffffu, v0);
+            const uint32_t vm1 = __ballot_sync(0xffffffffu, v1);
+            if (lane == 0) {
+                ws.vmask[g] = vm0;
+                if (g + 1 < GR) ws.vmask[g + 1] = vm1;
+            }
+            if (v0) recur(g, slot0, G0, a0);
+            if (v1) recur(g + 1, slot1, G1, a1);
+        }
+        __syncwarp();
+        // ---- phase 2: lanes = (half, candidate my_g, pixel octet my_o) ------------------------------------------
+        float acc[6 + C];
+#pragma unroll
+        for (int k = 0; k < 6 + C; ++k) acc[k] = 0.f;
+        uint32_t my_vm = 0;
+        uint32_t slot = my_head + my_g;
+        slot = slot >= QN ? slot - QN : slot;
+        if (my_g < my_n) {
+            my_vm = (ws.vmask[my_g] >> (half * 16)) & 0xffffu;
+            uint32_t m = (my_vm >> (my_o * 8)) & 0xffu;
+            if (m) {
+                const float4 glo = my_lo[slot];
+                const float4 ghi = my_hi[slot];
+                const float hx0 = ax0 + (float)(half * 4);
+                while (m) {
+                    const uint32_t p = my_o * 8 + (uint32_t)__ffs(m) - 1u;  // pixel of this half, row-major 4x4
+                    m &= m - 1;
+                    const uint32_t si = my_g * 33 + half * 16 + p;
+                    const float2 r = ws.slab_gd[si];  // (G, dL_dalpha)
+                    const float rw = ws.slab_w[si];   // alpha * T
+                    const float dx = glo.x - (hx0 + (float)(p & 3)), dy = glo.y - (wy0 + (float)(p >> 2));
+                    const float dL_dG = ghi.y * r.y;
+                    const float gdx = r.x * dx, gdy = r.x * dy;
+                    acc[0] += dL_dG * (-gdx * glo.z - gdy * glo.w);
+                    acc[1] += dL_dG * (-gdy * ghi.x - gdx * glo.w);
+                    acc[2] += gdx * dx * dL_dG;
+                    acc[3] += gdx * dy * dL_dG;
+                    acc[4] += gdy * dy * dL_dG;
+                    acc[5] += r.x * r.y;
+                    const float* dp = reinterpret_cast<const float*>(&ws.dpix[(half * 16 + p) * (CS / 4)]);
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) acc[6 + ch] += rw * dp[ch];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6 + C; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
+        if (my_o == 0 && my_vm != 0) {
+            const uint32_t gid = __float_as_uint(my_hi[slot].w);
+            atomicAdd(dL_dmean2D + 3 * (size_t)gid, acc[0] * ddelx_dx);
+            atomicAdd(dL_dmean2D + 3 * (size_t)gid + 1, acc[1] * ddely_dy);
+            atomicAdd(dL_dconic + 4 * (size_t)gid, -0.5f * acc[2]);
+            atomicAdd(dL_dconic + 4 * (size_t)gid + 1, -0.5f * acc[3]);
+            atomicAdd(dL_dconic + 4 * (size_t)gid + 3, -0.5f * acc[4]);
+            atomicAdd(dL_dopacity + gid, acc[5]);
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) atomicAdd(dL_dcolors + (size_t)gid * C + ch, acc[6 + ch]);
+        }
+        head_a += na;
+        head_a = head_a >= QN ? head_a - QN : head_a;
+        cnt_a -= na;
+        head_b += nb;
+        head_b = head_b >= QN ? head_b - QN : head_b;
+        cnt_b -= nb;
+        __syncwarp();
+    };
+
+    // back to front: lane l of chunk c holds list position total-1-(c*32+l)
+    float4 nlo = make_float4(0, 0, 0, 0), nhi = make_float4(0, 0, 0, 0), nc0 = make_float4(0, 0, 0, 0),
+           nc1 = make_float4(0, 0, 0, 0);
+    uint32_t nid = 0;
+    {
+        const int pos = total - 1 - (int)lane;
+        if (pos >= 0) {
+            const size_t i = (size_t)range.x + pos;
+            nlo = pk_lo[i];
+            nhi = pk_hi[i];
+            nc0 = pk_col[i * (CS / 4)];
+            if (CS > 4) nc1 = pk_col[i * (CS / 4) + 1];
+            nid = point_list[i];
+        }
+    }
+    __syncwarp();
+    for (int c = 0; c < nchunks; ++c) {
+        const float4 lo = nlo, hi = nhi, c0 = nc0, c1 = nc1;
+        const uint32_t id = nid;
+        const int my_pos = total - 1 - c * 32 - (int)lane;
+        const bool have = my_pos >= 0;
+        if (c + 1 < nchunks) {
+            const int pos = my_pos - 32;
+            if (pos >= 0) {
+                const size_t i = (size_t)range.x + pos;
+                nlo = pk_lo[i];
+                nhi = pk_hi[i];
+                nc0 = pk_col[i * (CS / 4)];
+                if (CS > 4) nc1 = pk_col[i * (CS / 4) + 1];
+                nid = point_list[i];
+            }
+        }
+        // extents relative to the warp's block origin, so the four block edges are immediates (the rounding of the
+        // extra subtraction, <= 2^-22 relative, is far inside the padding of the extents: preprocess.cu alpha_extent)
+        const float xl = (lo.x - hi.z) - ax0, xr = (lo.x + hi.z) - ax0;
+        const float yt = (lo.y - hi.w) - wy0, yb = (lo.y + hi.w) - wy0;
+        const bool in_rows = have && !(yt > 3.f || yb < 0.f);
+        const bool cand_a = in_rows && my_pos < total_a && !(xl > 3.f || xr < 0.f);
+        const bool cand_b = in_rows && my_pos < total_b && !(xl > 7.f || xr < 4.f);
+        const uint32_t bits_a = __ballot_sync(0xffffffffu, cand_a);
+        const uint32_t bits_b = __ballot_sync(0xffffffffu, cand_b);
+        if (!(bits_a | bits_b)) continue;
+        const float4 hi_tag = make_float4(hi.x, hi.y, __int_as_float(my_pos), __uint_as_float(id));
+        if (cand_a) {
+            uint32_t slot = head_a + cnt_a + __popc(bits_a & lt_mask);
+            slot = slot >= QN ? slot - QN : slot;
+            ws.q_lo[0][slot] = lo;
+            ws.q_hi[0][slot] = hi_tag;
+            ws.q_col[0][slot * (CS / 4)] = c0;
+            if (CS > 4) ws.q_col[0][slot * (CS / 4) + 1] = c1;
+        }
+        if (cand_b) {
+            uint32_t slot = head_b + cnt_b + __popc(bits_b & lt_mask);
+            slot = slot >= QN ? slot - QN : slot;
+            ws.q_lo[1][slot] = lo;
+            ws.q_hi[1][slot] = hi_tag;
+            ws.q_col[1][slot * (CS / 4)] = c0;
+            if (CS > 4) ws.q_col[1][slot * (CS / 4) + 1] = c1;
+        }
+        cnt_a += __popc(bits_a);
+        cnt_b += __popc(bits_b);
+        __syncwarp();
+        while ((cnt_a >= GR && cnt_b >= GR) || cnt_a > QN - 32 || cnt_b > QN - 32)
+            process_group(min(cnt_a, GR), min(cnt_b, GR));
+    }
+    while (cnt_a | cnt_b) process_group(min(cnt_a, GR), min(cnt_b, GR));
+}
+
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
@@ -510,6 +995,28 @@ struct PackedView {
 };
 
 static PackedView packed_view(const BinningLayout& b) { return PackedView{b.pk_lo, b.pk_hi, b.pk_col}; }
+
+// Pixel-block shape of the compositors: two 4x4 blocks per warp (default) or one 8x4 block per warp (the round-1 kernels,
+// kept for A/B measurements: profiles/r1_*).  Both produce identical outputs.  Selected by the environment variable
+// HGS_COMPOSITE_BLOCKS=8x4|4x4 or, overriding it, by hgs_debug_set_composite_blocks().
+static int g_blocks_override = 0;  // 0: environment / default, 1: 4x4 halves, 2: 8x4
+
+int set_composite_blocks(int mode) {
+    if (mode < 0 || mode > 2) {
+        set_error("composite block mode %d: expected 0 (default), 1 (4x4 halves) or 2 (8x4)", mode);
+        return HGS_ERR_INVALID;
+    }
+    g_blocks_override = mode;
+    return HGS_OK;
+}
+
+static bool composite_blocks_4x4() {
+    static const bool from_env = [] {
+        const char* e = getenv("HGS_COMPOSITE_BLOCKS");
+        return !(e != nullptr && strcmp(e, "8x4") == 0);
+    }();
+    return g_blocks_override ? g_blocks_override == 1 : from_env;
+}
 
 int launch_finalize_sorted(int channels, int64_t n, const uint32_t* n_ptr, const uint64_t* keys_sorted,
                            const uint32_t* point_list,
@@ -539,8 +1046,12 @@ static int launch_fwd_c(const ImageLayout& im, const BinningLayout& b, int W, in
     constexpr int CS = (C <= 4) ? 4 : 8;
     const PackedView p = packed_view(b);
     StageScope prof(HGS_STAGE_COMPOSITE_FWD, s);
-    composite_fwd_kernel<C, CS><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col, bg, im.final_T, im.n_contrib,
-                                                      out_color);
+    if (composite_blocks_4x4())
+        composite_fwd_half_kernel<C, CS><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col, bg, im.final_T,
+                                                               im.n_contrib, out_color);
+    else
+        composite_fwd_kernel<C, CS><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col, bg, im.final_T,
+                                                          im.n_contrib, out_color);
     return check_cuda(cudaGetLastError(), "composite_fwd launch");
 }
 
@@ -573,10 +1084,22 @@ static int launch_bwd_c(const ImageLayout& im, const BinningLayout& b, const uin
                                                     (int)smem), "composite_bwd smem attr")) return e;
         attr_set = true;
     }
+    const size_t smem_half = 8 * sizeof(BwdHalfSmem<CS>);
+    static bool attr_half_set = false;
+    if (!attr_half_set) {
+        if (int e = check_cuda(cudaFuncSetAttribute(composite_bwd_half_kernel<C, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)smem_half), "composite_bwd_half smem attr")) return e;
+        attr_half_set = true;
+    }
     StageScope prof(HGS_STAGE_COMPOSITE_BWD, s);
-    composite_bwd_kernel<C, CS><<<grid, 256, smem, s>>>(im.ranges, im.tile_order, point_list, W, H, bg, p.lo, p.hi, p.col, im.final_T,
-                                                      im.n_contrib, dL_dpix, gr->dL_dmean2D, gr->dL_dconic,
-                                                      gr->dL_dopacity, gr->dL_dcolor);
+    if (composite_blocks_4x4())
+        composite_bwd_half_kernel<C, CS><<<grid, 256, smem_half, s>>>(im.ranges, im.tile_order, point_list, W, H, bg, p.lo, p.hi,
+                                                                       p.col, im.final_T, im.n_contrib, dL_dpix, gr->dL_dmean2D,
+                                                                       gr->dL_dconic, gr->dL_dopacity, gr->dL_dcolor);
+    else
+        composite_bwd_kernel<C, CS><<<grid, 256, smem, s>>>(im.ranges, im.tile_order, point_list, W, H, bg, p.lo, p.hi, p.col,
+                                                             im.final_T, im.n_contrib, dL_dpix, gr->dL_dmean2D, gr->dL_dconic,
+                                                             gr->dL_dopacity, gr->dL_dcolor);
     return check_cuda(cudaGetLastError(), "composite_bwd launch");
 }
 

@@ -128,6 +128,8 @@ def load():
     lib.hgs_merge_greedy.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.hgs_debug_set_stats.restype = c_int
     lib.hgs_debug_set_stats.argtypes = [c_void_p]
+    lib.hgs_debug_set_composite_blocks.restype = c_int
+    lib.hgs_debug_set_composite_blocks.argtypes = [c_int]
     lib.hgs_profile_enable.restype = c_int
     lib.hgs_profile_enable.argtypes = [c_int]
     lib.hgs_profile_collect.restype = c_int

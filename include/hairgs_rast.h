@@ -341,6 +341,11 @@ enum hgs_stage {
 /* Debug: when dev_ptr != NULL the forward compositor writes one uint4 per (tile, warp):
  * (chunks walked, cull candidates, blends summed over lanes, pixels terminated | list chunks << 8). */
 int hgs_debug_set_stats(void* dev_ptr);
+/* Debug / measurement: pixel-block shape of the compositors (no reference counterpart: renderCUDA, forward.cu:261, and
+ * renderCUDABW_*, backward_distwar.cu:450-1014, have one thread per pixel of a 16x16 tile).  0 = default (environment
+ * variable HGS_COMPOSITE_BLOCKS=4x4|8x4, else 4x4), 1 = two 4x4 blocks per warp, 2 = one 8x4 block per warp.
+ * Outputs are identical in both modes. */
+int hgs_debug_set_composite_blocks(int mode);
 int hgs_profile_enable(int on);
 int hgs_profile_collect(double* ms, int64_t* launches);
 const char* hgs_stage_name(int stage);

@@ -30,6 +30,17 @@ def dev():
     return torch.device("cuda:0")
 
 
+@pytest.fixture(params=["4x4", "8x4"])
+def blocks(request):
+    """Runs the test once per pixel-block shape of the compositors (two 4x4 blocks per warp = default, one 8x4 block
+    per warp = the round-1 kernels); hgs_debug_set_composite_blocks, include/hairgs_rast.h."""
+    from hairgs_b200 import _lib
+    lib = _lib.load()
+    assert lib.hgs_debug_set_composite_blocks(1 if request.param == "4x4" else 2) == 0
+    yield request.param
+    assert lib.hgs_debug_set_composite_blocks(0) == 0
+
+
 def need_ref():
     C = refload.ref_dgr()
     if C is None:
@@ -70,7 +81,7 @@ def assert_forward_equal(vo, vr, co, cr, ro, rr, d, No, Nr):
 
 
 @pytest.mark.parametrize("name", CASE_NAMES)
-def test_forward_and_backward_vs_reference(name):
+def test_forward_and_backward_vs_reference(name, blocks):
     C = need_ref()
     d = _cases()[name]()
     No, co, ro, bo, vo = common.ours_forward(d)
@@ -115,7 +126,7 @@ def _load_gold(path):
 
 @pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLD, "*.npz")) if "knn" not in p and "loss_ref" not in p),
                          ids=lambda p: os.path.basename(p)[:-4])
-def test_golden_fixtures(path):
+def test_golden_fixtures(path, blocks):
     """No reference needed: the fixtures ARE the reference's outputs (generated by tests/golden/make_golden.py)."""
     import diff_gaussian_rasterization._C as ours_C
     d, z = _load_gold(path)
@@ -186,7 +197,7 @@ def test_empty_and_fully_culled():
 
 
 @pytest.mark.parametrize("P,W,H", [(1, 16, 16), (1, 1, 1), (7, 33, 17), (300, 2048, 16)])
-def test_tiny_and_odd_shapes(P, W, H):
+def test_tiny_and_odd_shapes(P, W, H, blocks):
     C = need_ref()
     d = common.blob_inputs(P, W, H, dev(), seed=30 + P, scale_mul=20.0)
     No, co, ro, bo, vo = common.ours_forward(d)
@@ -194,7 +205,7 @@ def test_tiny_and_odd_shapes(P, W, H):
     assert_forward_equal(vo, vr, co, cr, ro, rr, d, No, Nr)
 
 
-def test_multichannel_equals_separate_passes():
+def test_multichannel_equals_separate_passes(blocks):
     """One 7-channel pass (RGB + mask + orientation) == three 3-channel reference-shaped passes."""
     import diff_gaussian_rasterization._C as ours_C
     d = common.strand_inputs(500, 50, 320, 256, dev(), seed=6, colors="orientation")
@@ -396,7 +407,7 @@ def test_sync_free_capacity_paths():
 
 
 @pytest.mark.parametrize("M,D,mod,W,H", [(1, 0, 1.0, 384, 320), (4, 1, 0.8, 250, 190)], ids=["sh0", "sh1_mod0.8_ragged"])
-def test_fused_strands_equals_three_pass_dropin(M, D, mod, W, H):
+def test_fused_strands_equals_three_pass_dropin(M, D, mod, W, H, blocks):
     """SURVEY §8f N1+N2: render_strands() (one fused 7-channel pass, strand parameterisation inside the kernel) against
     the drop-in path Hair-GS runs today: torch getters + three render() calls + autograd.  Tolerances: pixels 1e-4 on all
     but a handful of pixels (a radius can flip by one where the closed-form covariance and the quaternion route round
@@ -733,3 +744,42 @@ def test_fused_strands_grad_sink_equals_autograd():
     (fused.render_strands(cams[1], m, bg7, grad_sink=sink)["image7"] * w7).sum().backward()
     for k in names:
         assert common.rel_err(sink.tensors[k], per_view[1][k]) <= 1e-5, k
+
+
+@pytest.mark.parametrize("channels", [3, 7])
+def test_block_shapes_agree(channels):
+    """The two compositor layouts (two 4x4 blocks per warp / one 8x4 block per warp) walk the same tile lists with a
+    different cull granularity: pixels, final_T and n_contrib must be bit-identical, gradients equal up to the order of
+    the floating-point sums.  Dense strands so that the candidate rings wrap, drain one-sided and terminate early."""
+    import diff_gaussian_rasterization._C as ours_C
+    from hairgs_b200 import _lib
+    lib = _lib.load()
+    d = common.strand_inputs(3000, 100, 512, 384, dev(), seed=11, colors="orientation")
+    P = d["means3D"].shape[0]
+    g = torch.Generator().manual_seed(5)
+    if channels == 7:
+        d["colors"] = torch.cat([torch.rand(P, 4, generator=g).to(dev()), d["colors"]], 1).contiguous()
+        d["background"] = torch.tensor([0.1, 0.2, 0.3, 0.0, 0.5, 0.5, 0.5], device=dev())
+    d["opacity"] = (0.05 + 0.94 * torch.rand(P, 1, generator=g)).to(dev())  # opaque enough for early termination
+    dL = torch.randn(channels, 384, 512, generator=g).to(dev())
+    out = {}
+    try:
+        for mode in (1, 2):
+            assert lib.hgs_debug_set_composite_blocks(mode) == 0
+            N, c, r, b, v = common.ours_forward(d)
+            v = {k: v[k].clone() for k in ("accum_alpha", "n_contrib")}
+            grads = ours_C.rasterize_gaussians_backward(*common.bwd_args(d, r, dL, b[0], N, b[1], b[2]))
+            out[mode] = (N, c.clone(), r.clone(), v, [x.clone() for x in grads])
+    finally:
+        assert lib.hgs_debug_set_composite_blocks(0) == 0
+    (N1, c1, r1, v1, g1), (N2, c2, r2, v2, g2) = out[1], out[2]
+    assert N1 == N2 and torch.equal(r1, r2)
+    assert common.bits_equal(c1, c2) == 0, "pixels differ between block shapes"
+    for k in ("accum_alpha", "n_contrib"):
+        assert common.bits_equal(v1[k], v2[k]) == 0, k
+    assert float((c1 != d["background"].view(-1, 1, 1)).float().mean()) > 0.2
+    for n, a, b_ in zip(GRAD_NAMES, g1, g2):
+        if a.numel():
+            assert torch.isfinite(a).all(), n
+            assert common.rel_err(a, b_) <= 1e-5, (n, common.rel_err(a, b_))
+    assert lib.hgs_debug_set_composite_blocks(3) != 0  # rejected, mode unchanged
