@@ -31,8 +31,11 @@ namespace hgs {
 // optional per-(tile,warp) work statistics of the forward compositor (debug; set through hgs_debug_set_stats)
 __device__ uint4* g_fwd_stats = nullptr;
 
+static bool g_fwd_stats_on = false;  // host mirror: the counting variant of the forward kernel is launched only then
+
 int set_fwd_stats(void* dev_ptr) {
     uint4* p = (uint4*)dev_ptr;
+    g_fwd_stats_on = p != nullptr;
     return check_cuda(cudaMemcpyToSymbol(g_fwd_stats, &p, sizeof(p)), "set stats pointer");
 }
 
@@ -268,7 +271,7 @@ struct FwdHalfSmem {
     float4 q_col[2][QN * (CS / 4)];
 };
 
-template <int C, int CS>
+template <int C, int CS, bool kStats>
 __global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __restrict__ ranges,
                                                                  const uint32_t* __restrict__ tile_order, int W, int H,
                                                                  const float4* __restrict__ pk_lo,
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __
         const uint32_t my_n = half ? tb : ta;
         const uint32_t my_head = half ? head_b : head_a;
         const uint32_t ntrip = max(ta, tb);
-        st_cand += ntrip;
+        if (kStats) st_cand += ntrip;
         for (uint32_t j0 = 0; j0 < ntrip; j0 += 2) {
             const bool act0 = j0 < my_n, act1 = j0 + 1 < my_n;
             uint32_t i0 = my_head + (act0 ? j0 : 0u);
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __
                     for (int ch = 0; ch < C; ++ch) Cacc[ch] += kExactOrder ? col[ch] * alpha0 * T : col[ch] * w;
                     T = test_T;
                     last_contributor = __float_as_uint(ghi0.z);
-                    st_blend++;
+                    if (kStats) st_blend++;
                 }
             }
             if (ok1 && !done) {
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __
                     for (int ch = 0; ch < C; ++ch) Cacc[ch] += kExactOrder ? col[ch] * alpha1 * T : col[ch] * w;
                     T = test_T;
                     last_contributor = __float_as_uint(ghi1.z);
-                    st_blend++;
+                    if (kStats) st_blend++;
                 }
             }
         }
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __
             const bool cand_b = in_rows && !(xl > bx1 || xr < bx0);
             const uint32_t bits_a = __ballot_sync(0xffffffffu, cand_a);
             const uint32_t bits_b = __ballot_sync(0xffffffffu, cand_b);
-            st_chunks++;
+            if (kStats) st_chunks++;
             if (!(bits_a | bits_b)) continue;
             // push: each half's candidates go to ITS ring compacted (list order kept); the list position rides in the
             // slot of the no longer needed cull extent
@@ -455,7 +458,7 @@ __global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) out_color[(size_t)ch * H * W + pix_id] = Cacc[ch] + T * bg_color[ch];
     }
-    if (g_fwd_stats != nullptr) {
+    if (kStats && g_fwd_stats != nullptr) {
         st_blend = __reduce_add_sync(0xffffffffu, st_blend);
         const uint32_t ndone = __popc(__ballot_sync(0xffffffffu, done && inside));
         if (lane == 0)
@@ -719,8 +722,8 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_kernel(
 // them could not take the next chunk):
 //   phase 1 (lanes = pixels): each half runs the recurrence over ITS up to 8 candidates, the two halves working on
 //            different instances in the same trip; (G, dL/dalpha, alpha*T) is parked per (half, candidate, pixel);
-//   phase 2 (lanes = half x candidate x pixel-octet): every lane sums its candidate's gradient terms over the
-//            contributing pixels of its octet, ONE shuffle level folds the two octets, and 16 lanes (one per queued
+//   phase 2 (lanes = half x candidate x column parity): every lane sums its candidate's gradient terms over the
+//            contributing pixels of its two columns, ONE shuffle level folds the two parities, and 16 lanes (one per queued
 //            candidate of either half) issue the red.global.adds.
 // cfg3, CPU model of the queue policy (tools/block_shape_study.py): 26 % fewer phase-1 trips than the 8x4 kernel; an
 // instance that reaches both halves is accumulated by both (1.3x the candidates, each over 16 instead of 32 pixels).
@@ -796,7 +799,7 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_half_kernel(
     const float ddelx_dx = 0.5 * W;
     const float ddely_dy = 0.5 * H;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    // phase-2 role of this lane: candidate my_g of half `half`, pixels [my_o * 8, my_o * 8 + 8) of that half
+    // phase-2 role of this lane: candidate my_g of half `half`, pixel columns my_o and my_o + 2 of that half
     const uint32_t my_g = lane & 7, my_o = (lane >> 3) & 1;
 
     const float4* my_lo = ws.q_lo[half];
@@ -860,7 +863,7 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_half_kernel(
             if (v1) recur(g + 1, slot1, G1, a1);
         }
         __syncwarp();
-        // ---- phase 2: lanes = (half, candidate my_g, pixel octet my_o) ------------------------------------------
+        // ---- phase 2: lanes = (half, candidate my_g, column parity my_o) ---------------------------------------
         float acc[6 + C];
 #pragma unroll
         for (int k = 0; k < 6 + C; ++k) acc[k] = 0.f;
@@ -869,13 +872,16 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_half_kernel(
         slot = slot >= QN ? slot - QN : slot;
         if (my_g < my_n) {
             my_vm = (ws.vmask[my_g] >> (half * 16)) & 0xffffu;
-            uint32_t m = (my_vm >> (my_o * 8)) & 0xffu;
+            // the candidate's two lanes take the even / the odd columns of the 4x4 block: a strand covers neighbouring
+            // pixels, so the contributing pixels split about evenly (rows 0-1 / 2-3 left 5.9 trips of this loop per
+            // group with 7 lanes active, profiles/r1_composite_half.md)
+            uint32_t m = my_vm & (0x5555u << my_o);
             if (m) {
                 const float4 glo = my_lo[slot];
                 const float4 ghi = my_hi[slot];
                 const float hx0 = ax0 + (float)(half * 4);
                 while (m) {
-                    const uint32_t p = my_o * 8 + (uint32_t)__ffs(m) - 1u;  // pixel of this half, row-major 4x4
+                    const uint32_t p = (uint32_t)__ffs(m) - 1u;  // pixel of this half, row-major 4x4
                     m &= m - 1;
                     const uint32_t si = my_g * 33 + half * 16 + p;
                     const float2 r = ws.slab_gd[si];  // (G, dL_dalpha)
@@ -1046,9 +1052,12 @@ static int launch_fwd_c(const ImageLayout& im, const BinningLayout& b, int W, in
     constexpr int CS = (C <= 4) ? 4 : 8;
     const PackedView p = packed_view(b);
     StageScope prof(HGS_STAGE_COMPOSITE_FWD, s);
-    if (composite_blocks_4x4())
-        composite_fwd_half_kernel<C, CS><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col, bg, im.final_T,
-                                                               im.n_contrib, out_color);
+    if (composite_blocks_4x4() && g_fwd_stats_on)
+        composite_fwd_half_kernel<C, CS, true><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col, bg,
+                                                                     im.final_T, im.n_contrib, out_color);
+    else if (composite_blocks_4x4())
+        composite_fwd_half_kernel<C, CS, false><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col, bg,
+                                                                      im.final_T, im.n_contrib, out_color);
     else
         composite_fwd_kernel<C, CS><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col, bg, im.final_T,
                                                           im.n_contrib, out_color);
