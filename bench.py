@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="e2e through the eager path only (no CUDA-graph replay)")
     ap.add_argument("--cpu-sample-views", type=int, default=2)
     return ap.parse_args()
 
@@ -257,12 +258,15 @@ class Harness:
         self.last_N = 0
 
     # ---- end-to-end step: render() + autograd, host<->device copies inside --------------------------
-    def setup_e2e(self, fused=False, optimizer=None):
+    def setup_e2e(self, fused=False, optimizer=None, graph=False):
         """optimizer: None (gradients only), "flat" (hairgs_b200.optim.FlatAdam: one launch over the flat bucket) or
-        "torch" (torch.optim.Adam(eps=1e-15) + zero_grad(set_to_none=True), scene/gaussian_model.py:250, train.py:203-204)."""
+        "torch" (torch.optim.Adam(eps=1e-15) + zero_grad(set_to_none=True), scene/gaussian_model.py:250, train.py:203-204).
+        graph: replay the view (render_strands + hair_image_loss + backward) as one CUDA graph
+        (hairgs_b200.graphs.GraphedStrandStep); the copies, the all-reduce and the optimiser stay outside the graph."""
         torch = self.torch
         self.fused = fused
         self.opt_mode = optimizer
+        self.graphed, self.graph_note = None, None
         if fused:
             from hairgs_b200 import fused as fused_mod
             from hairgs_b200.fused import render_strands
@@ -300,6 +304,7 @@ class Harness:
         self.esink = self._grad_sink() if fused else None
         if getattr(self, "copy_stream", None) is not None:
             self._prefetched = -1
+            self._setup_graph(graph)
             return
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         H, W = self.cfg["H"], self.cfg["W"]
@@ -319,6 +324,32 @@ class Harness:
         self.h2d_bytes = self.n_tgt * H * W * 4 + 35 * 4
         self.d2h_bytes = 4
         self._prefetched = -1
+        self._setup_graph(graph)
+
+    def _setup_graph(self, graph):
+        """Captures the fused view into CUDA graphs over the SAME double-buffered input slots the copy stream fills."""
+        if not (graph and self.fused and self.hair_loss and self.esink is not None):
+            return
+        torch = self.torch
+        try:
+            from hairgs_b200 import graphs
+            mine = [self.cams[v] for v in self.my_views]
+            cap, bits = graphs.measure_plan(self.model, mine, self.bg7)
+            c0 = mine[0]
+            g = graphs.GraphedStrandStep(self.model, self.esink, self.bg7, self.cfg["H"], self.cfg["W"], c0.FoVx, c0.FoVy,
+                                         cap, bits, lambdas=LOSS_LAMBDAS, cam_buf=self.cam_dev, tgt_buf=self.tgt_dev)
+            for slot in range(2):  # a real view in every slot before the warm-up / capture
+                k = slot % len(self.my_views)
+                self.tgt_dev[slot].copy_(self.targets_host[k])
+                self.cam_dev[slot].copy_(self.cam_host[k])
+            torch.cuda.synchronize(self.dev)
+            g.capture()
+            self.graphed = g
+            self.graph_note = f"one CUDA graph per input slot, plan: capacity {cap} instances, {bits} depth bits"
+        except Exception as e:  # stay measurable: fall back to the eager path and say so in the JSON line
+            self.graphed = None
+            self.graph_note = f"graph capture failed, eager path used: {type(e).__name__}: {e}"
+            torch.cuda.synchronize(self.dev)
 
     def _prefetch(self, it):
         """stage view `it` into slot it%2 on the copy stream (double-buffered data loader)."""
@@ -353,7 +384,10 @@ class Harness:
         m = self.model
         loss = None
         lam = LOSS_LAMBDAS
-        if self.fused and self.hair_loss:
+        if self.graphed is not None:
+            # the same view as the branch below, replayed as ONE graph launch (inputs: this slot's camera / targets)
+            loss = self.graphed.replay(slot)
+        elif self.fused and self.hair_loss:
             # ONE fused pass: strand parameterisation + 7 channels (hairgs_b200.fused.render_strands), then Hair-GS's
             # image loss (l1 + d-ssim + BCE mask + orientation, loss/losses.py:319-346) as one fused op
             out = self.render_strands(cam, m, self.bg7, grad_sink=self.esink)
@@ -373,7 +407,8 @@ class Harness:
                 out = self.render(cam, m, self.bg, override_color=colour_override(m, s))["render"]
                 term = (out - tgt[0:3]).abs().mean()
                 loss = term if loss is None else loss + term
-        loss.backward()
+        if self.graphed is None:
+            loss.backward()
         if self.world > 1:
             torch.distributed.all_reduce(self.opt.grads.flat if self.opt_mode == "flat" else self.flat_grad)
         if self.opt_mode == "flat":
@@ -590,6 +625,7 @@ def run():
 
     can_fuse = args.impl == "ours" and cfg["kind"] == "strands" and tuple(cfg["sets"]) == ("sh", "mask", "orientation")
     ms_res_3pass, ms_e2e_3pass = ms_res, None
+    ms_e2e_eager, graph_note = None, None
     h.setup_e2e(fused=False)
     ms_e2e = timed_loop(torch, h.step_e2e, args.steps, args.warmup, world, dev, flush)
     if can_fuse:
@@ -605,10 +641,22 @@ def run():
         launches_per_step = int(sum(launches))
         h.setup_e2e(fused=True)
         ms_e2e = timed_loop(torch, h.step_e2e, args.steps, args.warmup, world, dev, flush)
+        if h.hair_loss and not args.no_graph:
+            # the same step with the view replayed as one CUDA graph (the eager loop is host-bound: ~25 launches and
+            # ~0.9 ms of Python per view); eager number kept as e2e.value_eager
+            h.setup_e2e(fused=True, graph=True)
+            if h.graphed is not None:
+                ms_e2e_eager = ms_e2e
+                ms_e2e = timed_loop(torch, h.step_e2e, args.steps, args.warmup, world, dev, flush)
+                h.graphed.check()
+            graph_note = h.graph_note
     # the same e2e step with the optimiser included ("optimiser step excluded and also reported included");
     # runs last because it moves the parameters
-    h.setup_e2e(fused=can_fuse, optimizer="flat" if args.impl == "ours" else "torch")
+    h.setup_e2e(fused=can_fuse, optimizer="flat" if args.impl == "ours" else "torch",
+                graph=can_fuse and ms_e2e_eager is not None)
     ms_e2e_opt = timed_loop(torch, h.step_e2e, args.steps, args.warmup, world, dev, flush)
+    if h.graphed is not None:
+        h.graphed.check()
     clk = clocks.stop() if rank == 0 else None
     import diff_gaussian_rasterization as dgr
     dgr._RasterizeGaussians.backend = dgr._C
@@ -686,6 +734,14 @@ def run():
         line["e2e"]["api"] = ("hairgs_b200.fused.render_strands() + hairgs_b200.losses."
                               + ("hair_image_loss()" if h.hair_loss else "weighted_l1()") +
                               " + autograd, targets/camera prefetched from pinned host memory")
+        if graph_note is not None:
+            line["e2e"]["graph"] = graph_note
+        if ms_e2e_eager is not None:
+            line["e2e"]["api"] = ("hairgs_b200.graphs.GraphedStrandStep.replay(): render_strands() + hair_image_loss() + "
+                                  "backward captured as one CUDA graph per input slot; targets/camera copied from pinned "
+                                  "host memory into the slot every step, loss copied back; all-reduce / optimiser outside "
+                                  "the graph")
+            line["e2e"]["value_eager"] = round(views / (ms_e2e_eager / 1000.0), 2)
     line["n_gpus"] = world
     if args.impl == "reference":
         line["impl"] = "reference"

@@ -287,6 +287,13 @@ __global__ void __launch_bounds__(256) hair_pointwise_kernel(const HairLossArgs 
     const float count = a.terms[5];
     const float inv_count = count > 0.f ? 1.f / count : 0.f;
     const float kPi = 3.14159265358979323846f, kPi2 = 1.57079632679489661923f, eps = 1e-7f;
+    // world_view_transform[:3,:2]: by value, or from the camera's matrix on the device (graph replay: one graph, any view)
+    float r0 = a.view_rot[0], r1 = a.view_rot[1], r3 = a.view_rot[3], r4 = a.view_rot[4], r6 = a.view_rot[6],
+          r7 = a.view_rot[7];
+    if (a.view_matrix_dev != nullptr) {
+        const float* vm = a.view_matrix_dev;
+        r0 = vm[0]; r1 = vm[1]; r3 = vm[4]; r4 = vm[5]; r6 = vm[8]; r7 = vm[9];
+    }
     float bce_sum = 0.f, ori_sum = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
         // ---- mask: BCEWithLogits(x, z) = max(x,0) - x z + log(1 + exp(-|x|)), mean over pixels ----------------
@@ -299,8 +306,8 @@ __global__ void __launch_bounds__(256) hair_pointwise_kernel(const HairLossArgs 
         float gox = 0.f, goy = 0.f, goz = 0.f;
         if (orient_in_mask(a, i, ox, oy, oz)) {
             // view-space xy: o_world @ wvt[:3,:3]
-            const float vx = ox * a.view_rot[0] + oy * a.view_rot[3] + oz * a.view_rot[6];
-            const float vy = ox * a.view_rot[1] + oy * a.view_rot[4] + oz * a.view_rot[7];
+            const float vx = ox * r0 + oy * r3 + oz * r6;
+            const float vy = ox * r1 + oy * r4 + oz * r7;
             const float nrm = sqrtf(vx * vx + vy * vy);
             const float den = nrm + eps;
             const float pxn = vx / den;
@@ -324,9 +331,9 @@ __global__ void __launch_bounds__(256) hair_pointwise_kernel(const HairLossArgs 
             const float gdotv = g_px * vx + g_py * vy;
             const float k = nrm > 0.f ? gdotv / (den * den * nrm) : 0.f;
             const float g_vx = g_px / den - k * vx, g_vy = g_py / den - k * vy;
-            gox = g_vx * a.view_rot[0] + g_vy * a.view_rot[1];
-            goy = g_vx * a.view_rot[3] + g_vy * a.view_rot[4];
-            goz = g_vx * a.view_rot[6] + g_vy * a.view_rot[7];
+            gox = g_vx * r0 + g_vy * r1;
+            goy = g_vx * r3 + g_vy * r4;
+            goz = g_vx * r6 + g_vy * r7;
         }
         a.dL_dimage[4 * HW + i] = gox;
         a.dL_dimage[5 * HW + i] = goy;

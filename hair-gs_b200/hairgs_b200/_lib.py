@@ -136,7 +136,7 @@ def load():
     lib.hgs_profile_collect.argtypes = [c_void_p, c_void_p]
     lib.hgs_stage_name.restype = c_char_p
     lib.hgs_stage_name.argtypes = [c_int]
-    if lib.hgs_abi_version() != 2:
+    if lib.hgs_abi_version() != 3:
         raise ImportError("libhairgs_rast.so ABI version mismatch; rebuild")
     _lib = lib
     return lib
@@ -148,7 +148,7 @@ class HairLoss(ctypes.Structure):
                 ("gt_mask", c_void_p), ("gt_theta", c_void_p), ("confidence", c_void_p), ("orient_mask", c_void_p),
                 ("view_rot", ctypes.c_float * 9), ("bg_orient", ctypes.c_float * 3), ("l_l1", ctypes.c_float),
                 ("l_dssim", ctypes.c_float), ("l_mask", ctypes.c_float), ("l_orient", ctypes.c_float),
-                ("terms", c_void_p), ("scratch", c_void_p), ("dL_dimage", c_void_p)]
+                ("terms", c_void_p), ("scratch", c_void_p), ("dL_dimage", c_void_p), ("view_matrix_dev", c_void_p)]
 
 
 class HgsError(RuntimeError):

@@ -1,0 +1,172 @@
+"""CUDA-graph replay of one Hair-GS Stage-III training view (SURVEY.md §8f N1-N3 in one graph).
+
+The eager step — `fused.render_strands` -> `losses.hair_image_loss` -> `loss.backward()` — is ~25 kernel launches and
+~0.9 ms of Python / autograd bookkeeping per view; on cfg3 that is as long as the device work itself (0.94 ms), so the
+eager loop is host-bound (profiles/r1_e2e_host_time.txt).  The forward was built without host synchronisation for
+exactly this purpose: with a fixed *launch plan* (instance capacity and sort depth bits decided up front) nothing the
+host does depends on the view, and the whole view — strand parameterisation, binning, sort, both compositors, the image
+loss and every gradient down to the raw parameters — is captured once and replayed with one `cudaGraphLaunch`.
+
+What varies per view lives in device memory the caller fills between replays: the camera (world_view_transform,
+full_proj_transform, camera_center: 35 floats) and the six target planes.  The reference has no counterpart (its forward
+blocks on `num_rendered` mid-pass, rasterizer_impl.cu:281, which cannot be captured).
+
+Validation is deferred, never skipped: every replay copies (num_rendered, overflow, depth range) to pinned memory and
+the next use of the slot checks it against the plan (`HgsPlanError` if the view did not fit — its results were then
+computed on a truncated instance list and the caller must re-plan and redo that step).
+"""
+import math
+
+import torch
+
+from . import _lib as L
+from . import fused, losses
+from .scenes import Camera
+from diff_gaussian_rasterization import _C as _dgr
+
+
+class HgsPlanError(L.HgsError):
+    """A replayed view needed more instances or more depth bits than the captured launch plan provides."""
+
+
+class LaunchPlan:
+    """Fixed launch plan of the strand forward: capacity of the binning workspace (instances) and the sort's depth bits.
+    `host` is the pinned read-back target of hgs_forward_read_num_rendered."""
+
+    def __init__(self, capacity, depth_bits):
+        self.capacity, self.depth_bits = int(capacity), int(depth_bits)
+        self.host = torch.zeros(8, dtype=torch.int32).pin_memory()
+
+    def check(self):
+        """Call once the work that used this plan has completed.  Returns the view's instance count."""
+        N, overflow = int(self.host[0]), int(self.host[2])
+        if (overflow & 1) != 0 or N < 0:
+            raise HgsPlanError("instance count overflows int32")
+        if N > self.capacity:
+            raise HgsPlanError(f"view has {N} tile instances, the captured plan holds {self.capacity}")
+        need = _dgr._depth_range_bits(self.host)
+        if self.depth_bits not in (0, 32) and need > self.depth_bits:
+            raise HgsPlanError(f"view needs {need} depth bits in the sort keys, the captured plan compares {self.depth_bits}")
+        return N
+
+
+def measure_plan(model, cameras, bg7):
+    """(capacity, depth_bits) that fit every camera in `cameras` for the current parameters: one eager forward per camera
+    (no grad).  The eager path keeps, per (device, P, H, W), the largest instance count seen plus 25 % head-room and the
+    widest depth range rounded up to whole sort passes (diff_gaussian_rasterization._C hints); the plan is those."""
+    H, W = int(cameras[0].image_height), int(cameras[0].image_width)
+    key = (model._endpoints.device.index, int(model.endpoint_pairs.shape[0]), H, W, 7)
+    with torch.no_grad():
+        for cam in cameras:
+            fused.render_strands(cam, model, bg7)
+    return int(_dgr._capacity_hint[key]), int(_dgr._depth_bits_hint[key])
+
+
+class GraphedStrandStep:
+    """One training view as a CUDA graph: render_strands + hair_image_loss + backward into a fused.GradSink.
+
+        step = GraphedStrandStep(model, sink, bg7, H, W, fovx, fovy, capacity, depth_bits, lambdas=dict(...))
+        step.cam_buf[s].copy_(...); step.tgt_buf[s].copy_(...)      # fill every slot once with a real view
+        step.capture()
+        loop:  copy the view's camera (35 floats: world_view_transform | full_proj_transform | camera_center) and targets
+               (image[3] | mask | orientation field | confidence) into slot s, then
+               loss = step.replay(s)       # device scalar; parameter gradients are in the sink's tensors,
+                                           # step.mean2d_grad[s] / step.radii[s] feed the densification statistics
+
+    `slots` static input buffers (default 2) let the next view's host->device copies overlap the current replay; each
+    slot has its own graph (same kernels, different input addresses) sharing one memory pool.
+    """
+
+    def __init__(self, model, sink, bg7, H, W, fovx, fovy, capacity, depth_bits, lambdas=None, slots=2, cam_buf=None,
+                 tgt_buf=None):
+        dev = model._endpoints.device
+        if dev.type != "cuda":
+            raise L.HgsError("GraphedStrandStep needs a CUDA model: this rasterizer has no CPU path")
+        self.model, self.sink, self.bg7, self.dev = model, sink, bg7, dev
+        self.H, self.W, self.fovx, self.fovy = int(H), int(W), float(fovx), float(fovy)
+        self.lambdas = dict(lambdas or {})
+        # static inputs: the caller's own staging buffers (cam_buf / tgt_buf, one per slot) or fresh ones
+        self.cam_buf = list(cam_buf) if cam_buf is not None else [torch.zeros(35, device=dev) for _ in range(slots)]
+        self.tgt_buf = (list(tgt_buf) if tgt_buf is not None else
+                        [torch.zeros(6, self.H, self.W, device=dev) for _ in range(slots)])
+        slots = len(self.cam_buf)
+        for c, t in zip(self.cam_buf, self.tgt_buf):
+            if c.shape != (35,) or t.shape != (6, self.H, self.W) or c.device != dev or t.device != dev \
+                    or c.dtype != torch.float32 or t.dtype != torch.float32 or not t.is_contiguous():
+                raise L.HgsError("GraphedStrandStep: slot buffers must be float32 [35] and contiguous [6,H,W] on the model's "
+                                 "device")
+        self.plans = [LaunchPlan(capacity, depth_bits) for _ in range(slots)]
+        self.done = [None] * slots          # event after the slot's last replay
+        self.graphs, self.loss, self.terms = [], [], []
+        self.mean2d_grad, self.radii = [None] * slots, [None] * slots   # static outputs of each slot's graph
+        self.replays = 0
+
+    # the body that is captured.  It calls the forward, the loss and the backward directly (no autograd engine inside the
+    # capture: the engine synchronises with the streams on which the parameters' AccumulateGrad nodes were created, which
+    # are outside the capture whenever an eager autograd graph of the same parameters is still alive).
+    def _view(self, slot):
+        cd, tgt = self.cam_buf[slot], self.tgt_buf[slot]
+        wvt = cd[0:16].view(4, 4)
+        m = self.model
+        lam = self.lambdas
+        l_dssim = float(lam.get("lambda_dssim", 0.2))
+        weights = (max(0.0, 1.0 - l_dssim), l_dssim, float(lam.get("lambda_mask", 0.1)),
+                   float(lam.get("lambda_orientation", 0.1)))
+        settings = dict(image_height=self.H, image_width=self.W, tanfovx=math.tan(self.fovx * 0.5),
+                        tanfovy=math.tan(self.fovy * 0.5), bg=self.bg7, scale_modifier=1.0, viewmatrix=wvt,
+                        projmatrix=cd[16:32].view(4, 4), sh_degree=m.active_sh_degree, campos=cd[32:35], debug=False,
+                        grad_sink=self.sink, plan=self.plans[slot])
+        with torch.no_grad():
+            args = (m._endpoints, m.endpoint_pairs, m._width, m._opacity, m._mask, m.get_features)
+            image, radii, state = fused.strands_forward(*args, settings)
+            terms, dimage = losses.hair_image_loss_raw(image, tgt[0:3], tgt[3], tgt[4], tgt[5], tgt[3] > 0.5, wvt, weights,
+                                                       lam.get("bg_orient", (0.0, 0.0, 0.0)))
+            self.sink.begin_step()
+            grads = fused.strands_backward(*args, settings, state, dimage)
+        self.mean2d_grad[slot] = grads[5]      # screen-space mean gradients (densification statistics)
+        self.radii[slot] = radii
+        return terms[0], terms
+
+    def capture(self, warmup=2):
+        """Runs `warmup` eager views per slot on a side stream (lazy initialisation inside the library and autograd must not
+        happen during capture), then captures one graph per slot.  The slots must already hold a real view."""
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for slot in range(len(self.cam_buf)):
+                for _ in range(warmup):
+                    self._view(slot)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        for p in self.plans:
+            p.check()
+        pool = None
+        for slot in range(len(self.cam_buf)):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                loss, terms = self._view(slot)
+            pool = g.pool()
+            self.graphs.append(g)
+            self.loss.append(loss)
+            self.terms.append(terms)
+        return self
+
+    def replay(self, slot):
+        """Replays the view in `slot` on the current stream; returns the (static) device scalar of the loss.  Raises
+        HgsPlanError if the PREVIOUS replay of this slot did not fit the plan."""
+        ev = self.done[slot]
+        if ev is not None:
+            ev.synchronize()
+            self.plans[slot].check()
+        self.graphs[slot].replay()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self.done[slot] = ev
+        self.replays += 1
+        return self.loss[slot]
+
+    def check(self):
+        """Synchronises and validates the last replay of every slot."""
+        torch.cuda.synchronize(self.dev)
+        return [p.check() for p, ev in zip(self.plans, self.done) if ev is not None]

@@ -55,47 +55,65 @@ def l1_groups(groups, H, W, device):
 # ---------------------------------------------------------------------------------------------------------------------
 # Hair-GS image-space loss of one view (loss/losses.py:319-346, image terms), fused: hgs_hair_image_loss
 # ---------------------------------------------------------------------------------------------------------------------
+def hair_image_loss_raw(image7, gt_rgb, gt_mask, gt_theta, confidence, orient_mask, view_rot, lambdas, bg_orient):
+    """The fused loss without autograd: -> (terms[8], dL_dimage7[7,H,W]) for d(total)/d(image7); lambdas = (l1, dssim,
+    mask, orientation) weights.  See hair_image_loss for the arguments."""
+    lib = L.load()
+    if not image7.is_cuda:
+        raise L.HgsError("hair_image_loss: image7 must be a CUDA tensor (no CPU path)")
+    dev = image7.device
+    img = L.f32c(image7, "image7", dev)
+    if img.dim() != 3 or img.shape[0] != 7:
+        raise L.HgsError("hair_image_loss: image7 must be [7,H,W] (rgb | mask | orientation)")
+    H, W = img.shape[1], img.shape[2]
+    gt = L.f32c(gt_rgb, "gt_rgb", dev)
+    gm = L.f32c(gt_mask, "gt_mask", dev)
+    th = L.f32c(gt_theta, "gt_theta", dev)
+    cf = L.f32c(confidence, "confidence", dev)
+    if gt.shape != (3, H, W) or gm.shape != (H, W) or th.shape != (H, W) or cf.shape != (H, W):
+        raise L.HgsError("hair_image_loss: targets must be gt_rgb[3,H,W], gt_mask/gt_theta/confidence[H,W]")
+    om = None
+    if orient_mask is not None:
+        if orient_mask.shape != (H, W) or orient_mask.device != dev:
+            raise L.HgsError("hair_image_loss: orient_mask must be a [H,W] tensor on the image's device")
+        if orient_mask.dtype == torch.bool:
+            om = orient_mask.contiguous().view(torch.uint8)
+        else:
+            om = (orient_mask != 0).view(torch.uint8)
+    a = L.HairLoss()
+    a.height, a.width = H, W
+    a.image7, a.gt_rgb, a.gt_mask, a.gt_theta, a.confidence = (img.data_ptr(), gt.data_ptr(), gm.data_ptr(),
+                                                             th.data_ptr(), cf.data_ptr())
+    a.orient_mask = om.data_ptr() if om is not None else None
+    vm = None
+    if torch.is_tensor(view_rot):
+        # the camera's world_view_transform on the device: read by the kernel, nothing baked into the launch
+        if not view_rot.is_cuda or view_rot.device != dev or view_rot.dtype != torch.float32 or view_rot.numel() != 16:
+            raise L.HgsError("hair_image_loss: a tensor view_rot must be the [4,4] float32 world_view_transform on the "
+                             "image's device")
+        vm = view_rot.contiguous()
+        a.view_matrix_dev = vm.data_ptr()
+    else:
+        a.view_matrix_dev = None
+        for i, v in enumerate(view_rot):
+            a.view_rot[i] = float(v)
+    for i, v in enumerate(bg_orient):
+        a.bg_orient[i] = float(v)
+    a.l_l1, a.l_dssim, a.l_mask, a.l_orient = [float(v) for v in lambdas]
+    terms = torch.empty(8, dtype=torch.float32, device=dev)
+    scratch = torch.empty(9 * H * W, dtype=torch.float32, device=dev)
+    grad = torch.empty_like(img)
+    a.terms, a.scratch, a.dL_dimage = terms.data_ptr(), scratch.data_ptr(), grad.data_ptr()
+    with torch.cuda.device(dev):
+        L.check(lib.hgs_hair_image_loss(ctypes.byref(a), L.stream_ptr(dev)), "hair_image_loss")
+    return terms, grad
+
+
 class _HairImageLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image7, gt_rgb, gt_mask, gt_theta, confidence, orient_mask, view_rot, lambdas, bg_orient):
-        lib = L.load()
-        if not image7.is_cuda:
-            raise L.HgsError("hair_image_loss: image7 must be a CUDA tensor (no CPU path)")
-        dev = image7.device
-        img = L.f32c(image7, "image7", dev)
-        if img.dim() != 3 or img.shape[0] != 7:
-            raise L.HgsError("hair_image_loss: image7 must be [7,H,W] (rgb | mask | orientation)")
-        H, W = img.shape[1], img.shape[2]
-        gt = L.f32c(gt_rgb, "gt_rgb", dev)
-        gm = L.f32c(gt_mask, "gt_mask", dev)
-        th = L.f32c(gt_theta, "gt_theta", dev)
-        cf = L.f32c(confidence, "confidence", dev)
-        if gt.shape != (3, H, W) or gm.shape != (H, W) or th.shape != (H, W) or cf.shape != (H, W):
-            raise L.HgsError("hair_image_loss: targets must be gt_rgb[3,H,W], gt_mask/gt_theta/confidence[H,W]")
-        om = None
-        if orient_mask is not None:
-            if orient_mask.shape != (H, W) or orient_mask.device != dev:
-                raise L.HgsError("hair_image_loss: orient_mask must be a [H,W] tensor on the image's device")
-            if orient_mask.dtype == torch.bool:
-                om = orient_mask.contiguous().view(torch.uint8)
-            else:
-                om = (orient_mask != 0).view(torch.uint8)
-        a = L.HairLoss()
-        a.height, a.width = H, W
-        a.image7, a.gt_rgb, a.gt_mask, a.gt_theta, a.confidence = (img.data_ptr(), gt.data_ptr(), gm.data_ptr(),
-                                                                 th.data_ptr(), cf.data_ptr())
-        a.orient_mask = om.data_ptr() if om is not None else None
-        for i, v in enumerate(view_rot):
-            a.view_rot[i] = float(v)
-        for i, v in enumerate(bg_orient):
-            a.bg_orient[i] = float(v)
-        a.l_l1, a.l_dssim, a.l_mask, a.l_orient = [float(v) for v in lambdas]
-        terms = torch.empty(8, dtype=torch.float32, device=dev)
-        scratch = torch.empty(9 * H * W, dtype=torch.float32, device=dev)
-        grad = torch.empty_like(img)
-        a.terms, a.scratch, a.dL_dimage = terms.data_ptr(), scratch.data_ptr(), grad.data_ptr()
-        with torch.cuda.device(dev):
-            L.check(lib.hgs_hair_image_loss(ctypes.byref(a), L.stream_ptr(dev)), "hair_image_loss")
+        terms, grad = hair_image_loss_raw(image7, gt_rgb, gt_mask, gt_theta, confidence, orient_mask, view_rot, lambdas,
+                                          bg_orient)
         ctx.save_for_backward(grad)
         ctx.mark_non_differentiable(terms)
         return terms[0], terms
@@ -116,7 +134,9 @@ def hair_image_loss(image7, gt_rgb, gt_mask, gt_theta, confidence, view_rot, lam
     """loss, terms = the image-space part of Hair-GS's loss_function on the fused strand render.
 
     image7: [7,H,W] from rasterize_strands (rgb | mask logit | world orientation).  view_rot: view_rot_of(camera
-    .world_view_transform).  terms (no grad): [total, l1, dssim, mask, orientation, n_orientation_pixels, -, -].
+    .world_view_transform) — nine host floats — or camera.world_view_transform itself as a CUDA [4,4] tensor (the
+    kernel then reads the rotation from device memory: required inside a captured CUDA graph, hairgs_b200.graphs).
+    terms (no grad): [total, l1, dssim, mask, orientation, n_orientation_pixels, -, -].
     """
     lambdas = (max(0.0, 1.0 - lambda_dssim), lambda_dssim, lambda_mask, lambda_orientation)
     return _HairImageLoss.apply(image7, gt_rgb, gt_mask, gt_theta, confidence, orient_mask, view_rot, lambdas, bg_orient)

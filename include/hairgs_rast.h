@@ -54,7 +54,7 @@
 extern "C" {
 #endif
 
-#define HGS_ABI_VERSION 2
+#define HGS_ABI_VERSION 3
 #define HGS_TILE 16            /* BLOCK_X == BLOCK_Y == 16, cuda_rasterizer/config.h:16-17 */
 #define HGS_MAX_CHANNELS 8     /* colour channels per pass: 3 (reference) .. 8 (fused RGB+mask+orientation) */
 
@@ -241,6 +241,10 @@ typedef struct hgs_hair_loss {
     float* terms;
     float* scratch;
     float* dL_dimage;
+    const float* view_matrix_dev;   /* ABI v3, may be NULL: DEVICE pointer to camera.world_view_transform ([4,4] floats in
+                                     * torch's row-major layout, the tensor the rasterizer takes as `viewmatrix`); when set,
+                                     * the kernels read the rotation from it and ignore view_rot, so that one captured CUDA
+                                     * graph serves every view */
 } hgs_hair_loss;
 int hgs_hair_image_loss(const hgs_hair_loss* args, void* stream);
 

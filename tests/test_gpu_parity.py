@@ -783,3 +783,79 @@ def test_block_shapes_agree(channels):
             assert torch.isfinite(a).all(), n
             assert common.rel_err(a, b_) <= 1e-5, (n, common.rel_err(a, b_))
     assert lib.hgs_debug_set_composite_blocks(3) != 0  # rejected, mode unchanged
+
+
+def _graph_fixture(S=300, V=40, H=192, W=256):
+    from hairgs_b200 import fused, models, scenes
+    sc = scenes.strand_scene(S, V, seed=21).to(dev())
+    cams = scenes.orbit_cameras(4, W, H, device=dev())
+    g = torch.Generator(device="cuda").manual_seed(17)
+    tgts = []
+    for _ in cams:
+        t = torch.rand(6, H, W, generator=g, device=dev())
+        t[3] = (t[3] < 0.5).float()
+        t[4] *= math.pi
+        tgts.append(t)
+    names = {"endpoints": "_endpoints", "width": "_width", "opacity": "_opacity", "mask": "_mask", "features": "_features_dc"}
+    model = models.StrandModel(sc).to(dev())
+    sink = fused.GradSink({k: torch.zeros_like(getattr(model, n)) for k, n in names.items()})
+    return model, cams, tgts, sink, names
+
+
+def test_graphed_step_equals_eager():
+    """hairgs_b200.graphs.GraphedStrandStep: the captured view (render_strands + hair_image_loss + backward) replayed on
+    new cameras / targets gives the loss and the raw-parameter gradients of the eager path, and the device-side view
+    matrix of the loss equals the by-value one."""
+    from hairgs_b200 import fused, graphs, losses
+    model, cams, tgts, sink, names = _graph_fixture()
+    H, W = 192, 256
+    bg7 = torch.zeros(7, device=dev())
+    lam = dict(lambda_dssim=0.2, lambda_mask=0.01, lambda_orientation=100.0)
+    eager = []
+    for cam, t in zip(cams, tgts):
+        sink.begin_step()
+        out = fused.render_strands(cam, model, bg7, grad_sink=sink)
+        loss, terms = losses.hair_image_loss(out["image7"], t[0:3], t[3], t[4], t[5],
+                                             losses.view_rot_of(cam.world_view_transform.cpu()), orient_mask=t[3] > 0.5, **lam)
+        loss.backward()
+        eager.append((float(loss), terms.clone(), {k: v.clone() for k, v in sink.tensors.items()}))
+    cap, bits = graphs.measure_plan(model, cams, bg7)
+    step = graphs.GraphedStrandStep(model, sink, bg7, H, W, cams[0].FoVx, cams[0].FoVy, cap, bits, lambdas=lam)
+
+    def load(slot, i):
+        c = cams[i]
+        step.cam_buf[slot].copy_(torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1),
+                                            c.camera_center.reshape(-1)]))
+        step.tgt_buf[slot].copy_(tgts[i])
+
+    load(0, 0)
+    load(1, 1)
+    step.capture()
+    for it, i in enumerate((2, 0, 3, 1, 1, 2)):       # views the graphs were not captured on, both slots, repeats
+        slot = it % 2
+        load(slot, i)
+        loss = step.replay(slot)
+        torch.cuda.synchronize()
+        ref_loss, ref_terms, ref_grads = eager[i]
+        assert abs(float(loss) - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss)), (i, float(loss), ref_loss)
+        assert torch.allclose(step.terms[slot], ref_terms, rtol=1e-4, atol=1e-6)
+        for k in names:
+            assert common.rel_err(sink.tensors[k], ref_grads[k]) <= 1e-5, (i, k)
+    assert all(n > 0 for n in step.check())
+
+
+def test_graphed_step_detects_a_plan_that_does_not_fit():
+    """A view with more tile instances than the captured capacity must be reported, never silently truncated."""
+    from hairgs_b200 import graphs
+    model, cams, tgts, sink, names = _graph_fixture()
+    bg7 = torch.zeros(7, device=dev())
+    cap, bits = graphs.measure_plan(model, cams, bg7)
+    step = graphs.GraphedStrandStep(model, sink, bg7, 192, 256, cams[0].FoVx, cams[0].FoVy, 4096, bits)
+    for slot in range(2):
+        c = cams[slot]
+        step.cam_buf[slot].copy_(torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1),
+                                            c.camera_center.reshape(-1)]))
+        step.tgt_buf[slot].copy_(tgts[slot])
+    with pytest.raises(graphs.HgsPlanError):
+        step.capture()
+    assert cap > 4096
