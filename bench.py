@@ -236,6 +236,37 @@ class Harness:
         self.fbucket.attach_to(self.fparams)
         self.fsink = self._grad_sink()
 
+    def setup_fused_graph(self):
+        """The resident fused step as a CUDA-graph replay (hairgs_b200.graphs, dL/dimage given): same kernels, one launch."""
+        torch = self.torch
+        self.fgraph, self.fgraph_note = None, None
+        if self.fsink is None:
+            return
+        try:
+            from hairgs_b200 import graphs
+            mine = [self.cams[v] for v in self.my_views]
+            cap, bits = graphs.measure_plan(self.model, mine, self.bg7)
+            g = graphs.GraphedStrandStep(self.model, self.fsink, self.bg7, self.cfg["H"], self.cfg["W"], mine[0].FoVx,
+                                         mine[0].FoVy, cap, bits, dimage=self.dL7.contiguous())
+            self.cam_flat = [torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1),
+                                        c.camera_center.reshape(-1)]).contiguous() for c in mine]
+            for slot in range(2):
+                g.cam_buf[slot].copy_(self.cam_flat[slot % len(mine)])
+            torch.cuda.synchronize(self.dev)
+            g.capture()
+            self.fgraph = g
+            self.fgraph_note = f"CUDA-graph replay, plan: capacity {cap} instances, {bits} depth bits"
+        except Exception as e:
+            self.fgraph_note = f"graph capture failed, eager path used: {type(e).__name__}: {e}"
+            torch.cuda.synchronize(self.dev)
+
+    def step_resident_fused_graph(self, it):
+        slot = it % 2
+        # the view's camera is resident; 140 bytes device-to-device into the graph's input slot
+        self.fgraph.cam_buf[slot].copy_(self.cam_flat[it % len(self.cam_flat)], non_blocking=True)
+        self.fgraph.replay(slot)
+        self.fbucket.all_reduce()
+
     def _grad_sink(self):
         """The strand backward writes the parameter gradients straight into the slices of the flat bucket that the
         parameters' .grad point at (fused.GradSink): no autograd accumulation kernels, no bucket clear."""
@@ -626,6 +657,7 @@ def run():
     can_fuse = args.impl == "ours" and cfg["kind"] == "strands" and tuple(cfg["sets"]) == ("sh", "mask", "orientation")
     ms_res_3pass, ms_e2e_3pass = ms_res, None
     ms_e2e_eager, graph_note = None, None
+    ms_res_eager, res_graph_note = None, None
     h.setup_e2e(fused=False)
     ms_e2e = timed_loop(torch, h.step_e2e, args.steps, args.warmup, world, dev, flush)
     if can_fuse:
@@ -639,6 +671,13 @@ def run():
         launches = (ctypes.c_int64 * 16)()
         lib.hgs_profile_collect(None, launches)
         launches_per_step = int(sum(launches))
+        if not args.no_graph:
+            h.setup_fused_graph()
+            if h.fgraph is not None:
+                ms_res_eager = ms_res
+                ms_res = timed_loop(torch, h.step_resident_fused_graph, args.steps, args.warmup, world, dev, flush)
+                h.fgraph.check()
+            res_graph_note = h.fgraph_note
         h.setup_e2e(fused=True)
         ms_e2e = timed_loop(torch, h.step_e2e, args.steps, args.warmup, world, dev, flush)
         if h.hair_loss and not args.no_graph:
@@ -730,6 +769,10 @@ def run():
         config["path"] = ("fused strand entry: strand parameterisation + RGB/mask/orientation in ONE rasterization pass "
                           "(hairgs_b200.fused.render_strands); the three-pass drop-in path is reported as *_dropin_3pass")
         line["value_dropin_3pass"] = round(views / (ms_res_3pass / 1000.0), 2)
+        if res_graph_note is not None:
+            config["value_path"] = res_graph_note
+        if ms_res_eager is not None:
+            line["value_eager"] = round(views / (ms_res_eager / 1000.0), 2)
         line["e2e"]["value_dropin_3pass"] = round(views / (ms_e2e_3pass / 1000.0), 2)
         line["e2e"]["api"] = ("hairgs_b200.fused.render_strands() + hairgs_b200.losses."
                               + ("hair_image_loss()" if h.hair_loss else "weighted_l1()") +

@@ -78,18 +78,28 @@ class GraphedStrandStep:
     """
 
     def __init__(self, model, sink, bg7, H, W, fovx, fovy, capacity, depth_bits, lambdas=None, slots=2, cam_buf=None,
-                 tgt_buf=None):
+                 tgt_buf=None, dimage=None):
         dev = model._endpoints.device
         if dev.type != "cuda":
             raise L.HgsError("GraphedStrandStep needs a CUDA model: this rasterizer has no CPU path")
         self.model, self.sink, self.bg7, self.dev = model, sink, bg7, dev
         self.H, self.W, self.fovx, self.fovy = int(H), int(W), float(fovx), float(fovy)
         self.lambdas = dict(lambdas or {})
+        # dimage: a static [7,H,W] dL/dimage7 to back-propagate INSTEAD of the image loss (the caller's own loss gradient,
+        # or a fixed one for measurements); the target slots are then unused
+        if dimage is not None and (dimage.shape != (7, self.H, self.W) or dimage.dtype != torch.float32
+                                   or dimage.device != dev or not dimage.is_contiguous()):
+            raise L.HgsError("GraphedStrandStep: dimage must be a contiguous float32 [7,H,W] tensor on the model's device")
+        self.dimage = dimage
         # static inputs: the caller's own staging buffers (cam_buf / tgt_buf, one per slot) or fresh ones
         self.cam_buf = list(cam_buf) if cam_buf is not None else [torch.zeros(35, device=dev) for _ in range(slots)]
-        self.tgt_buf = (list(tgt_buf) if tgt_buf is not None else
-                        [torch.zeros(6, self.H, self.W, device=dev) for _ in range(slots)])
         slots = len(self.cam_buf)
+        if tgt_buf is not None:
+            self.tgt_buf = list(tgt_buf)
+        elif dimage is not None:
+            self.tgt_buf = [torch.zeros(6, self.H, self.W, device=dev)] * slots     # never read
+        else:
+            self.tgt_buf = [torch.zeros(6, self.H, self.W, device=dev) for _ in range(slots)]
         for c, t in zip(self.cam_buf, self.tgt_buf):
             if c.shape != (35,) or t.shape != (6, self.H, self.W) or c.device != dev or t.device != dev \
                     or c.dtype != torch.float32 or t.dtype != torch.float32 or not t.is_contiguous():
@@ -98,7 +108,7 @@ class GraphedStrandStep:
         self.plans = [LaunchPlan(capacity, depth_bits) for _ in range(slots)]
         self.done = [None] * slots          # event after the slot's last replay
         self.graphs, self.loss, self.terms = [], [], []
-        self.mean2d_grad, self.radii = [None] * slots, [None] * slots   # static outputs of each slot's graph
+        self.mean2d_grad, self.radii, self.image = [None] * slots, [None] * slots, [None] * slots  # static outputs
         self.replays = 0
 
     # the body that is captured.  It calls the forward, the loss and the backward directly (no autograd engine inside the
@@ -119,12 +129,16 @@ class GraphedStrandStep:
         with torch.no_grad():
             args = (m._endpoints, m.endpoint_pairs, m._width, m._opacity, m._mask, m.get_features)
             image, radii, state = fused.strands_forward(*args, settings)
-            terms, dimage = losses.hair_image_loss_raw(image, tgt[0:3], tgt[3], tgt[4], tgt[5], tgt[3] > 0.5, wvt, weights,
-                                                       lam.get("bg_orient", (0.0, 0.0, 0.0)))
+            if self.dimage is not None:
+                terms, dimage = torch.zeros(8, device=self.dev), self.dimage
+            else:
+                terms, dimage = losses.hair_image_loss_raw(image, tgt[0:3], tgt[3], tgt[4], tgt[5], tgt[3] > 0.5, wvt,
+                                                           weights, lam.get("bg_orient", (0.0, 0.0, 0.0)))
             self.sink.begin_step()
             grads = fused.strands_backward(*args, settings, state, dimage)
         self.mean2d_grad[slot] = grads[5]      # screen-space mean gradients (densification statistics)
         self.radii[slot] = radii
+        self.image[slot] = image
         return terms[0], terms
 
     def capture(self, warmup=2):
