@@ -65,7 +65,7 @@ def parse_args():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="e2e through the eager path only (no CUDA-graph replay)")
-    ap.add_argument("--cpu-sample-views", type=int, default=2)
+    ap.add_argument("--cpu-sample-views", type=int, default=6)
     return ap.parse_args()
 
 

@@ -158,7 +158,9 @@ class GraphedStrandStep:
         pool = None
         for slot in range(len(self.cam_buf)):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
+            # thread_local: calls of OTHER host threads (e.g. the NCCL watchdog of a multi-GPU job) must not invalidate
+            # the capture; the captured body itself runs on this thread only (no autograd worker threads)
+            with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
                 loss, terms = self._view(slot)
             pool = g.pool()
             self.graphs.append(g)
