@@ -4,11 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg5|cfg1]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-Metric (BASELINE.json): training views/s of fwd+bwd rasterization.  A *step* is one camera view per GPU rendered
-the way Hair-GS trains on it (train.py:146-155, loss/losses.py:341-346): every colour set of the workload
-(cfg3: SH-RGB, mask, strand orientation) is rasterized forward and backward, the Gaussian-parameter gradients are
-accumulated into one flat fp32 bucket, and with N > 1 GPUs the bucket is all-reduced over NCCL (views shard over
-ranks, one process per GPU, no other data-path collective: weak scaling).
+Metric (BASELINE.json): training views/s of fwd+bwd rasterization.  A *step* is one batch of camera views,
+--views-per-step (default 8) per GPU — 8 GPUs x 8 views is the 64-view batch of BASELINE configs[3], SURVEY 8(e) — each
+rendered the way Hair-GS trains on it (train.py:146-155, loss/losses.py:341-346): every colour set of the workload
+(cfg3: SH-RGB, mask, strand orientation) is rasterized forward and backward, the Gaussian-parameter gradients of the
+step's views accumulate in one flat fp32 bucket, and with N > 1 GPUs the bucket is all-reduced over NCCL ONCE per step
+(views shard over ranks, one process per GPU, no other data-path collective: weak scaling, per-GPU work fixed).
 
   value  — device-resident: Gaussian inputs, cameras and dL/dimage already in HBM, the `_C` entry points of the
            drop-in called directly (through the C ABI of libhairgs_rast.so).
@@ -66,6 +67,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="e2e through the eager path only (no CUDA-graph replay)")
     ap.add_argument("--cpu-sample-views", type=int, default=6)
+    ap.add_argument("--views-per-step", type=int, default=8,
+                    help="views each rank renders per step (one gradient all-reduce / optimiser step per step); "
+                         "8 views x 8 GPUs = the 64-view batch of BASELINE configs[3]")
     return ap.parse_args()
 
 
@@ -143,9 +147,10 @@ def colour_override(model, which):
 class Harness:
     """Everything both arms share; `backend` is the `_C`-shaped extension module under test."""
 
-    def __init__(self, cfg, dev, backend, world, rank):
+    def __init__(self, cfg, dev, backend, world, rank, views_per_step=1):
         import torch
         self.torch, self.cfg, self.dev, self.C, self.world, self.rank = torch, cfg, dev, backend, world, rank
+        self.vps = max(1, int(views_per_step))
         self.model, self.cams = build_workload(cfg, dev)
         from hairgs_b200 import multiview
         self.bg = torch.zeros(3, device=dev)
@@ -197,9 +202,14 @@ class Harness:
 
     # ---- device-resident step: direct _C calls ------------------------------------------------------
     def step_resident(self, it):
-        torch, C, cfg, i = self.torch, self.C, self.cfg, self.inputs
-        cam = self.cams[self.my_views[it % len(self.my_views)]]
         b = self.bucket.zero_()
+        for k in range(self.vps):
+            self._resident_view(it * self.vps + k, b)
+        b.all_reduce()  # one collective per step; no-op on a single rank
+
+    def _resident_view(self, vi, b):
+        torch, C, cfg, i = self.torch, self.C, self.cfg, self.inputs
+        cam = self.cams[self.my_views[vi % len(self.my_views)]]
         for s in cfg["sets"]:
             col = self.colours[s]
             sh = i["sh"] if col is None else self.empty
@@ -218,7 +228,6 @@ class Harness:
             else:
                 b.accumulate("colour_" + s, gcol)
             self.last_N = N
-        b.all_reduce()  # one collective per step; no-op on a single rank
 
     # ---- device-resident fused step: strand parameterisation + 7 channels in one pass ------------------
     def setup_fused(self):
@@ -261,10 +270,12 @@ class Harness:
             torch.cuda.synchronize(self.dev)
 
     def step_resident_fused_graph(self, it):
-        slot = it % 2
-        # the view's camera is resident; 140 bytes device-to-device into the graph's input slot
-        self.fgraph.cam_buf[slot].copy_(self.cam_flat[it % len(self.cam_flat)], non_blocking=True)
-        self.fgraph.replay(slot)
+        for k in range(self.vps):
+            vi = it * self.vps + k
+            slot = vi % 2
+            # the view's camera is resident; 140 bytes device-to-device into the graph's input slot
+            self.fgraph.cam_buf[slot].copy_(self.cam_flat[vi % len(self.cam_flat)], non_blocking=True)
+            self.fgraph.replay(slot, accumulate=k > 0)
         self.fbucket.all_reduce()
 
     def _grad_sink(self):
@@ -277,14 +288,15 @@ class Harness:
                                         "mask": m._mask.grad, "features": m._features_dc.grad})
 
     def step_resident_fused(self, it):
-        cam = self.cams[self.my_views[it % len(self.my_views)]]
         m = self.model
         if self.fsink is None:
             self.fbucket.zero_()
         else:
-            self.fsink.begin_step()
-        out = self.fused_mod.render_strands(cam, m, self.bg7, grad_sink=self.fsink)
-        out["image7"].backward(self.dL7)
+            self.fsink.begin_step()      # the first view of the step overwrites the bucket, the others add
+        for k in range(self.vps):
+            cam = self.cams[self.my_views[(it * self.vps + k) % len(self.my_views)]]
+            out = self.fused_mod.render_strands(cam, m, self.bg7, grad_sink=self.fsink)
+            out["image7"].backward(self.dL7)
         self.fbucket.all_reduce()
         self.last_N = 0
 
@@ -352,8 +364,8 @@ class Harness:
         self.copy_done = [torch.cuda.Event() for _ in range(2)]
         self.slot_free = [torch.cuda.Event() for _ in range(2)]
         self.loss_host = torch.zeros(1).pin_memory()
-        self.h2d_bytes = self.n_tgt * H * W * 4 + 35 * 4
-        self.d2h_bytes = 4
+        self.h2d_bytes = self.vps * (self.n_tgt * H * W * 4 + 35 * 4)
+        self.d2h_bytes = self.vps * 4
         self._prefetched = -1
         self._setup_graph(graph)
 
@@ -394,6 +406,21 @@ class Harness:
         self._prefetched = it
 
     def step_e2e(self, it):
+        """One step = views_per_step views (each: H2D of its camera/targets, render, loss, backward, D2H of the loss), then ONE
+        gradient all-reduce and ONE optimiser step."""
+        torch = self.torch
+        for k in range(self.vps):
+            self._e2e_view(it * self.vps + k, first=k == 0)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.opt.grads.flat if self.opt_mode == "flat" else self.flat_grad)
+        if self.opt_mode == "flat":
+            # the sink overwrites the bucket on the next step, so the optimiser kernel need not clear it
+            self.opt.step(grad_scale=1.0 / (self.world * self.vps), zero_grad=self.esink is None)
+        elif self.opt_mode == "torch":
+            self.opt.step()
+            self.opt.zero_grad(set_to_none=True)
+
+    def _e2e_view(self, it, first):
         torch, cfg = self.torch, self.cfg
         from hairgs_b200.scenes import Camera
         if self._prefetched < it:
@@ -408,16 +435,17 @@ class Harness:
         cam = Camera(base.image_width, base.image_height, base.FoVx, base.FoVy, cd[0:16].view(4, 4), cd[16:32].view(4, 4),
                      cd[32:35])
         tgt = self.tgt_dev[slot]
-        if self.esink is not None:
-            self.esink.begin_step()
-        elif self.opt_mode is None:
-            self.flat_grad.zero_()
+        if first:
+            if self.esink is not None:
+                self.esink.begin_step()      # the first view of the step overwrites the gradients, the others add
+            elif self.opt_mode is None:
+                self.flat_grad.zero_()
         m = self.model
         loss = None
         lam = LOSS_LAMBDAS
         if self.graphed is not None:
             # the same view as the branch below, replayed as ONE graph launch (inputs: this slot's camera / targets)
-            loss = self.graphed.replay(slot)
+            loss = self.graphed.replay(slot, accumulate=not first)
         elif self.fused and self.hair_loss:
             # ONE fused pass: strand parameterisation + 7 channels (hairgs_b200.fused.render_strands), then Hair-GS's
             # image loss (l1 + d-ssim + BCE mask + orientation, loss/losses.py:319-346) as one fused op
@@ -440,14 +468,6 @@ class Harness:
                 loss = term if loss is None else loss + term
         if self.graphed is None:
             loss.backward()
-        if self.world > 1:
-            torch.distributed.all_reduce(self.opt.grads.flat if self.opt_mode == "flat" else self.flat_grad)
-        if self.opt_mode == "flat":
-            # the sink overwrites the bucket on the next step, so the optimiser kernel need not clear it
-            self.opt.step(grad_scale=1.0 / self.world, zero_grad=self.esink is None)
-        elif self.opt_mode == "torch":
-            self.opt.step()
-            self.opt.zero_grad(set_to_none=True)
         self.slot_free[slot].record(cur)
         self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
 
@@ -622,7 +642,9 @@ def run():
     from hairgs_b200 import _lib as L
     lib = L.load()
 
-    h = Harness(cfg, dev, backend, world, rank)
+    h = Harness(cfg, dev, backend, world, rank, views_per_step=args.views_per_step)
+    config["views_per_step"] = (f"{h.vps} per rank ({h.vps * world}-view batch): gradients of the step's views accumulate in the "
+                                f"flat bucket, ONE all-reduce and ONE optimiser step per step")
     P, M, D = h.P, h.M, cfg["D"]
     HW = cfg["W"] * cfg["H"]
     T = ((cfg["W"] + 15) // 16) * ((cfg["H"] + 15) // 16)
@@ -700,7 +722,7 @@ def run():
     import diff_gaussian_rasterization as dgr
     dgr._RasterizeGaussians.backend = dgr._C
 
-    views = world * args.steps
+    views = world * args.steps * h.vps
     value = views / (ms_res / 1000.0)
     e2e_value = views / (ms_e2e / 1000.0)
 

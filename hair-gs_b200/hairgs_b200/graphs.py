@@ -78,7 +78,7 @@ class GraphedStrandStep:
     """
 
     def __init__(self, model, sink, bg7, H, W, fovx, fovy, capacity, depth_bits, lambdas=None, slots=2, cam_buf=None,
-                 tgt_buf=None, dimage=None):
+                 tgt_buf=None, dimage=None, accumulate_variant=True):
         dev = model._endpoints.device
         if dev.type != "cuda":
             raise L.HgsError("GraphedStrandStep needs a CUDA model: this rasterizer has no CPU path")
@@ -91,6 +91,8 @@ class GraphedStrandStep:
                                    or dimage.device != dev or not dimage.is_contiguous()):
             raise L.HgsError("GraphedStrandStep: dimage must be a contiguous float32 [7,H,W] tensor on the model's device")
         self.dimage = dimage
+        # also capture the view with the backward ADDING to the sink (gradient accumulation over the views of a batch)
+        self.accumulate_variant = bool(accumulate_variant)
         # static inputs: the caller's own staging buffers (cam_buf / tgt_buf, one per slot) or fresh ones
         self.cam_buf = list(cam_buf) if cam_buf is not None else [torch.zeros(35, device=dev) for _ in range(slots)]
         slots = len(self.cam_buf)
@@ -114,7 +116,7 @@ class GraphedStrandStep:
     # the body that is captured.  It calls the forward, the loss and the backward directly (no autograd engine inside the
     # capture: the engine synchronises with the streams on which the parameters' AccumulateGrad nodes were created, which
     # are outside the capture whenever an eager autograd graph of the same parameters is still alive).
-    def _view(self, slot):
+    def _view(self, slot, accumulate=False):
         cd, tgt = self.cam_buf[slot], self.tgt_buf[slot]
         wvt = cd[0:16].view(4, 4)
         m = self.model
@@ -134,7 +136,8 @@ class GraphedStrandStep:
             else:
                 terms, dimage = losses.hair_image_loss_raw(image, tgt[0:3], tgt[3], tgt[4], tgt[5], tgt[3] > 0.5, wvt,
                                                            weights, lam.get("bg_orient", (0.0, 0.0, 0.0)))
-            self.sink.begin_step()
+            # first view of an optimiser step: the backward OVERWRITES the sink; later views of the step add to it
+            self.sink.accumulate = bool(accumulate)
             grads = fused.strands_backward(*args, settings, state, dimage)
         self.mean2d_grad[slot] = grads[5]      # screen-space mean gradients (densification statistics)
         self.radii[slot] = radii
@@ -157,25 +160,35 @@ class GraphedStrandStep:
             p.check()
         pool = None
         for slot in range(len(self.cam_buf)):
-            g = torch.cuda.CUDAGraph()
-            # thread_local: calls of OTHER host threads (e.g. the NCCL watchdog of a multi-GPU job) must not invalidate
-            # the capture; the captured body itself runs on this thread only (no autograd worker threads)
-            with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
-                loss, terms = self._view(slot)
-            pool = g.pool()
-            self.graphs.append(g)
-            self.loss.append(loss)
-            self.terms.append(terms)
+            per_mode = []
+            for accumulate in ((False, True) if self.accumulate_variant else (False,)):
+                g = torch.cuda.CUDAGraph()
+                # thread_local: calls of OTHER host threads (e.g. the NCCL watchdog of a multi-GPU job) must not
+                # invalidate the capture; the captured body itself runs on this thread only (no autograd worker threads)
+                with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
+                    loss, terms = self._view(slot, accumulate)
+                pool = g.pool()
+                per_mode.append((g, loss, terms, self.mean2d_grad[slot], self.radii[slot], self.image[slot]))
+            self.graphs.append(per_mode)
+            self.loss.append(per_mode[0][1])
+            self.terms.append(per_mode[0][2])
         return self
 
-    def replay(self, slot):
-        """Replays the view in `slot` on the current stream; returns the (static) device scalar of the loss.  Raises
-        HgsPlanError if the PREVIOUS replay of this slot did not fit the plan."""
+    def replay(self, slot, accumulate=False):
+        """Replays the view in `slot` on the current stream; returns the (static) device scalar of the loss.
+        accumulate=False: first view of an optimiser step, the parameter gradients in the sink are overwritten;
+        accumulate=True: a later view of the same step, its gradients are added (needs accumulate_variant=True).
+        Raises HgsPlanError if the PREVIOUS replay of this slot did not fit the plan."""
         ev = self.done[slot]
         if ev is not None:
             ev.synchronize()
             self.plans[slot].check()
-        self.graphs[slot].replay()
+        if accumulate and not self.accumulate_variant:
+            raise L.HgsError("GraphedStrandStep was built without the accumulate variant (accumulate_variant=True)")
+        g, loss, terms, mean2d, radii, image = self.graphs[slot][1 if accumulate else 0]
+        self.loss[slot], self.terms[slot] = loss, terms
+        self.mean2d_grad[slot], self.radii[slot], self.image[slot] = mean2d, radii, image
+        g.replay()
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))
         self.done[slot] = ev

@@ -841,6 +841,15 @@ def test_graphed_step_equals_eager():
         assert torch.allclose(step.terms[slot], ref_terms, rtol=1e-4, atol=1e-6)
         for k in names:
             assert common.rel_err(sink.tensors[k], ref_grads[k]) <= 1e-5, (i, k)
+    # gradient accumulation over the views of one optimiser step: the first replay overwrites the sink, the second adds
+    load(0, 0)
+    load(1, 3)
+    step.replay(0)
+    step.replay(1, accumulate=True)
+    torch.cuda.synchronize()
+    for k in names:
+        assert common.rel_err(sink.tensors[k], eager[0][2][k] + eager[3][2][k]) <= 1e-5, k
+    assert abs(float(step.loss[1]) - eager[3][0]) <= 1e-5 * max(1.0, abs(eager[3][0]))
     assert all(n > 0 for n in step.check())
 
 
