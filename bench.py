@@ -538,6 +538,32 @@ def cpu_port_views_per_s(cfg, n_views):
     return n_views / dt, pyoracle.num_threads(), dt
 
 
+def cpu_torch_naive(cfg, max_tiles=96):
+    """The CPU baseline as BASELINE.json's north_star words it: the reference's torch-side preprocessing plus a naive torch
+    compositor (oracle/torch_baseline.py), forward + autograd backward of one colour set on a
+    bounded sample of tiles, extrapolated; a view renders len(cfg["sets"]) colour sets."""
+    import torch
+    from oracle import torch_baseline as tb
+    model, cams = build_workload(cfg, "cpu")
+    cam = cams[0]
+    with torch.no_grad():
+        d = dict(background=torch.zeros(3), means3D=model.get_xyz, colors=torch.Tensor([]), opacity=model.get_opacity,
+                 scales=model.get_scaling, rotations=model.get_rotation, scale_modifier=1.0, cov3D_precomp=torch.Tensor([]),
+                 viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, tan_fovx=cam.tanfovx,
+                 tan_fovy=cam.tanfovy, image_height=cfg["H"], image_width=cfg["W"], sh=model.get_features.contiguous(),
+                 degree=cfg["D"], campos=cam.camera_center)
+        d = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in d.items()}
+    strand = None
+    if cfg["kind"] == "strands":
+        strand = (model._endpoints.detach().clone(), model.endpoint_pairs, model._width.detach().clone())
+    torch.set_num_threads(os.cpu_count() or 1)
+    r = tb.time_view(d, strand=strand, max_tiles=max_tiles)
+    sets = len(cfg["sets"])
+    return {"value": round(1000.0 / (sets * r["ms_per_view"]), 5), "unit": "views/s", "cores": r["cores"],
+            "ms_per_colour_set": round(r["ms_per_view"], 1), "colour_sets_per_view": sets, "items_ms": r["items"],
+            "sample": r["sample"]}
+
+
 # ---------------------------------------------------------------------------------------------------
 def algorithmic_bytes(stage, P, N, HW, T, M, D, sh_mode, C=3):
     """SURVEY.md §8(d) compulsory traffic per launch of each stage."""
@@ -823,6 +849,12 @@ def run():
             line["cpu_baseline"] = {"value": round(vps, 4), "unit": "views/s", "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_sample_views} view(s) of {args.workload} (all colour sets, "
                                               f"fwd+bwd) through the OpenMP C port in oracle/, {dt:.1f} s"}
+            try:
+                # the baseline as the north_star words it (torch preprocessing + naive torch compositor), next to the
+                # much faster C port above
+                line["cpu_baseline"]["torch_naive"] = cpu_torch_naive(cfg)
+            except Exception as e:
+                line["cpu_baseline"]["torch_naive"] = {"unavailable": f"{type(e).__name__}: {e}"}
     if world > 1:
         torch.distributed.destroy_process_group()
     return line
