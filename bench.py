@@ -524,6 +524,7 @@ def cpu_port_views_per_s(cfg, n_views):
         sh = model.get_features.numpy()
     rng = np.random.default_rng(0)
     dL = rng.standard_normal((3, cfg["H"], cfg["W"])).astype(np.float32)
+    stats = None
     t0 = time.perf_counter()
     for v in range(n_views):
         cam = cams[v % len(cams)]
@@ -533,8 +534,18 @@ def cpu_port_views_per_s(cfg, n_views):
                      sh=sh if cols[s] is None else None, colors=cols[s])
             f = pyoracle.Forward(d)
             f.backward(dL)
+            if stats is None:
+                # what SURVEY 8(d) asks the generator to report about the synthetic scene (first sampled view)
+                r = f.array("ranges").astype(np.int64)
+                ln = r[:, 1] - r[:, 0]
+                stats = {"P": int(f.P), "num_rendered": int(f.N), "visible_fraction": round(float((f.radii > 0).mean()), 4),
+                         "non_empty_tiles": int((ln > 0).sum()), "tiles": int(ln.shape[0]),
+                         "mean_tile_list": round(float(ln[ln > 0].mean()) if (ln > 0).any() else 0.0, 1),
+                         "max_tile_list": int(ln.max()) if ln.size else 0,
+                         "median_radius_px": float(np.median(f.radii[f.radii > 0])) if (f.radii > 0).any() else 0.0}
             f.close()
     dt = time.perf_counter() - t0
+    cpu_port_views_per_s.scene_stats = stats
     return n_views / dt, pyoracle.num_threads(), dt
 
 
@@ -849,6 +860,8 @@ def run():
             line["cpu_baseline"] = {"value": round(vps, 4), "unit": "views/s", "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_sample_views} view(s) of {args.workload} (all colour sets, "
                                               f"fwd+bwd) through the OpenMP C port in oracle/, {dt:.1f} s"}
+            if getattr(cpu_port_views_per_s, "scene_stats", None):
+                config["scene_stats"] = cpu_port_views_per_s.scene_stats
             try:
                 # the baseline as the north_star words it (torch preprocessing + naive torch compositor), next to the
                 # much faster C port above
