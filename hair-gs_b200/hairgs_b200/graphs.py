@@ -56,8 +56,15 @@ def measure_plan(model, cameras, bg7):
     widest depth range rounded up to whole sort passes (diff_gaussian_rasterization._C hints); the plan is those."""
     H, W = int(cameras[0].image_height), int(cameras[0].image_width)
     key = (model._endpoints.device.index, int(model.endpoint_pairs.shape[0]), H, W, 7)
+    if not _dgr.SYNC_FREE:
+        raise L.HgsError("measure_plan needs the capacity hints of the sync-free forward (diff_gaussian_rasterization._C."
+                         "SYNC_FREE is off)")
+    if len(cameras) == 0:
+        raise L.HgsError("measure_plan: no cameras")
     with torch.no_grad():
         for cam in cameras:
+            if int(cam.image_height) != H or int(cam.image_width) != W:
+                raise L.HgsError("measure_plan: all cameras of one plan must have the same resolution")
             fused.render_strands(cam, model, bg7)
     return int(_dgr._capacity_hint[key]), int(_dgr._depth_bits_hint[key])
 
@@ -82,6 +89,11 @@ class GraphedStrandStep:
         dev = model._endpoints.device
         if dev.type != "cuda":
             raise L.HgsError("GraphedStrandStep needs a CUDA model: this rasterizer has no CPU path")
+        if sink is None or not all(k in sink.tensors for k in ("endpoints", "width", "opacity", "mask", "features")):
+            raise L.HgsError("GraphedStrandStep needs a fused.GradSink with endpoints / width / opacity / mask / features "
+                             "tensors: the captured backward writes the parameter gradients there")
+        if int(capacity) <= 0:
+            raise L.HgsError("GraphedStrandStep: capacity must be positive (see measure_plan)")
         self.model, self.sink, self.bg7, self.dev = model, sink, bg7, dev
         self.H, self.W, self.fovx, self.fovy = int(H), int(W), float(fovx), float(fovy)
         self.lambdas = dict(lambdas or {})

@@ -188,3 +188,31 @@ def test_fused_strand_entry_validation_without_gpu():
     assert lib.hgs_binning_capacity(lib.hgs_binning_bytes(12345, 3), 3, 12345) == 12345
     assert lib.hgs_binning_capacity(lib.hgs_binning_bytes(8 * 4096, 7), 7, 999) == 8 * 4096
     assert lib.hgs_binning_capacity(lib.hgs_binning_bytes(8 * 4096, 7) + 256, 7, 999) < 0
+
+
+def test_graph_replay_host_logic_without_gpu():
+    """hairgs_b200.graphs: no CPU path, and the deferred validation of a launch plan (pure host logic on the read-back
+    words: num_rendered, -, overflow, depth_max bits, ~depth_min bits)."""
+    from hairgs_b200 import fused, graphs, models
+    sc = scenes.strand_scene(5, 6, seed=1)
+    m = models.StrandModel(sc)
+    with pytest.raises(L.HgsError, match="no CPU path"):
+        graphs.GraphedStrandStep(m, None, torch.zeros(7), 32, 32, 1.0, 1.0, 4096, 32)
+
+    def plan(capacity, bits, n, overflow, dmax, dmin):
+        p = graphs.LaunchPlan.__new__(graphs.LaunchPlan)
+        p.capacity, p.depth_bits = capacity, bits
+        p.host = torch.tensor([n, 0, overflow, dmax, ~dmin, 0, 0, 0], dtype=torch.int64).to(torch.int32)
+        return p
+
+    lo, hi = 0x3E4CCCCD, 0x3F4CCCCD          # float bits of 0.2 and 0.8: a 2^24 range -> 25 bits
+    assert plan(1000, 25, 900, 0, hi, lo).check() == 900
+    assert plan(1000, 32, 1000, 0, hi, lo).check() == 1000
+    with pytest.raises(graphs.HgsPlanError, match="tile instances"):
+        plan(1000, 25, 1001, 0, hi, lo).check()
+    with pytest.raises(graphs.HgsPlanError, match="depth bits"):
+        plan(1000, 24, 900, 0, hi, lo).check()
+    with pytest.raises(graphs.HgsPlanError, match="int32"):
+        plan(1000, 25, 900, 1, hi, lo).check()
+    assert issubclass(graphs.HgsPlanError, L.HgsError)
+    assert fused.GradSink({}).accumulate is False
