@@ -21,7 +21,6 @@ import torch
 
 from . import _lib as L
 from . import fused, losses
-from .scenes import Camera
 from diff_gaussian_rasterization import _C as _dgr
 
 
