@@ -77,9 +77,8 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, const uint2* __re
 // ------------------------------------------------------------------------------------------------
 // radix sort
 // ------------------------------------------------------------------------------------------------
-static constexpr uint32_t kStFlagAgg = 1u << 30;
-static constexpr uint32_t kStFlagIncl = 2u << 30;
-static constexpr uint32_t kStValMask = (1u << 30) - 1;
+static constexpr uint32_t kStFlagAgg = 1u << 31;       // a tile's digit count has been published
+static constexpr uint32_t kStValMask = (1u << 24) - 1;  // counts are < 2^24 (<= 128 tiles x 4096 keys per group)
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
     uint32_t v;
@@ -172,19 +171,23 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
     const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, uint32_t cap, const uint32_t* __restrict__ n_ptr, int shift,
     const uint32_t* __restrict__ ghist /*[256]*/,
-    uint32_t* __restrict__ status /*[ntiles*256]*/, uint32_t* __restrict__ ticket, const GeomHeader* range_hdr, int rb) {
+    uint32_t* __restrict__ status /*[ntiles*256]*/, uint32_t* __restrict__ group /*[ngroups*256]*/, int group_shift,
+    uint32_t* __restrict__ ticket, const GeomHeader* range_hdr, int rb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
 
     const uint32_t n = n_ptr ? min(*n_ptr, cap) : cap;
-    if (blockIdx.x * (uint32_t)kSortTile >= n) return;  // tile beyond the live range (grid is sized by capacity)
-    const KeyXform xf = load_key_xform(range_hdr, rb);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    (void)ticket;  // blocks are dispatched in index order: predecessors of a tile are always running or done
+    // A tile's id is the order in which its block STARTED (one atomic per block), not blockIdx.x: the look-back below
+    // waits on words published by tiles with smaller ids, and CUDA gives no guarantee that blocks are dispatched in
+    // index order (MPS, preemption, concurrent graph branches) - with tickets every predecessor is running or done.
+    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
 #pragma unroll
     for (int w = 0; w < kSortThreads / 32; ++w) sm.warp_hist[w][tid] = 0;
     __syncthreads();
-    const uint32_t tile = blockIdx.x;
+    const uint32_t tile = sm.tile;
+    if (tile * (uint32_t)kSortTile >= n) return;  // tile beyond the live range (grid is sized by capacity)
+    const KeyXform xf = load_key_xform(range_hdr, rb);
     const uint32_t base = tile * kSortTile;
     const uint32_t nvalid = min((uint32_t)kSortTile, n - base);
 
@@ -225,10 +228,10 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
         sm.warp_hist[w][tid] = block_count;
         block_count += c;
     }
-    // publish as early as possible so successors' look-back does not stall on us
-    uint32_t* my_status = status + (size_t)tile * kRadix + tid;
-    if (tile == 0) st_relaxed_u32(my_status, kStFlagIncl | block_count);
-    else st_relaxed_u32(my_status, kStFlagAgg | block_count);
+    // publish as early as possible: the tile's own word and its contribution to its group's word (one arrival each)
+    st_relaxed_u32(status + (size_t)tile * kRadix + tid, kStFlagAgg | block_count);
+    const uint32_t my_group = tile >> group_shift, in_group = tile & ((1u << group_shift) - 1u);
+    atomicAdd(group + (size_t)my_group * kRadix + tid, (1u << 24) | block_count);
 
     // values: issue the loads now, they are consumed after the key scatter
     uint32_t val[kSortItems];
@@ -253,31 +256,35 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
         sm.vals[pos] = val[r];
     }
 
-    // ---- decoupled look-back: kLook predecessors per L2 round trip --------------------------------------------------
+    // ---- two-level look-back (see sort_group_shift): complete groups before mine + tiles before me in my group.
+    //      kLook words per L2 round trip; a word that is not there yet is simply read again -------------------------------
     uint32_t prev_sum = 0;
-    if (tile > 0) {
+    {
         constexpr int kLook = 16;
-        int t = (int)tile - 1;
-        bool found = false;
-        while (!found) {
+        const uint32_t full = 1u << group_shift;  // arrivals of a complete group (every predecessor group is complete)
+        for (uint32_t k0 = 0; k0 < my_group; k0 += kLook) {
             uint32_t w[kLook];
 #pragma unroll
             for (int k = 0; k < kLook; ++k)
-                w[k] = (t - k >= 0) ? ld_relaxed_u32(status + (size_t)(t - k) * kRadix + tid) : kStFlagIncl;
+                w[k] = (k0 + k < my_group) ? ld_relaxed_u32(group + (size_t)(k0 + k) * kRadix + tid) : (full << 24);
 #pragma unroll
             for (int k = 0; k < kLook; ++k) {
-                if (found) continue;
-                if ((w[k] >> 30) == 0) {  // predecessor not published yet: retry from it
-                    t -= k;
-                    goto next_round;
-                }
+                while ((w[k] >> 24) != full) w[k] = ld_relaxed_u32(group + (size_t)(k0 + k) * kRadix + tid);
                 prev_sum += w[k] & kStValMask;
-                if ((w[k] >> 30) == 2) found = true;
             }
-            t -= kLook;
-        next_round:;
         }
-        st_relaxed_u32(my_status, kStFlagIncl | ((prev_sum + block_count) & kStValMask));
+        const uint32_t first = tile - in_group;
+        for (uint32_t k0 = 0; k0 < in_group; k0 += kLook) {
+            uint32_t w[kLook];
+#pragma unroll
+            for (int k = 0; k < kLook; ++k)
+                w[k] = (k0 + k < in_group) ? ld_relaxed_u32(status + (size_t)(first + k0 + k) * kRadix + tid) : kStFlagAgg;
+#pragma unroll
+            for (int k = 0; k < kLook; ++k) {
+                while (!(w[k] & kStFlagAgg)) w[k] = ld_relaxed_u32(status + (size_t)(first + k0 + k) * kRadix + tid);
+                prev_sum += w[k] & kStValMask;
+            }
+        }
     }
     sm.gbase[tid] = gexcl + prev_sum - local_excl;
     __syncthreads();
@@ -332,14 +339,13 @@ int launch_sort_pairs(int64_t n, const uint32_t* n_ptr, int end_bit, uint64_t* k
         return HGS_ERR_OVERFLOW;
     }
     SortLayout L = carve_sort(sort_ws, n);
+    // hist, tickets and the group words of all passes are contiguous, then the tile words of the passes that run
     const size_t clear = (size_t)((char*)L.status - (char*)L.hist) + (size_t)passes * L.ntiles * kRadix * 4;
     if (int e = check_cuda(cudaMemsetAsync(L.hist, 0, clear, s), "memset sort ws")) return e;
-    static int smem_set = 0;
-    if (!smem_set) {
+    static std::atomic<unsigned long long> attr_done{0};  // function attributes are per device
+    if (first_call_on_device(attr_done))
         if (int e = check_cuda(cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)sizeof(OnesweepSmem)), "onesweep smem attr")) return e;
-        smem_set = 1;
-    }
     const uint32_t nn = (uint32_t)n;
     int64_t hb = (n + 256 * 8 - 1) / (256 * 8);
     const int hblocks = (int)(hb < 148 * 8 ? hb : 148 * 8);
@@ -353,7 +359,8 @@ int launch_sort_pairs(int64_t n, const uint32_t* n_ptr, int end_bit, uint64_t* k
         StageScope prof(HGS_STAGE_SORT_ONESWEEP, s);
         onesweep_pass_kernel<<<(unsigned)L.ntiles, kSortThreads, sizeof(OnesweepSmem), s>>>(
             keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], nn, n_ptr, 8 * p, L.hist + p * kRadix,
-            L.status + (size_t)p * L.ntiles * kRadix, L.tickets + p, range_hdr, depth_bits);
+            L.status + (size_t)p * L.ntiles * kRadix, L.group + (size_t)p * L.ngroups * kRadix, L.group_shift, L.tickets + p,
+            range_hdr, depth_bits);
         if (int e = check_cuda(cudaGetLastError(), "onesweep launch")) return e;
         cur ^= 1;
     }

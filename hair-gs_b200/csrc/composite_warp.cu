@@ -1087,18 +1087,13 @@ static int launch_bwd_c(const ImageLayout& im, const BinningLayout& b, const uin
     constexpr int CS = (C <= 4) ? 4 : 8;
     const PackedView p = packed_view(b);
     const size_t smem = 8 * sizeof(BwdWarpSmem<CS>);
-    static bool attr_set = false;
-    if (!attr_set) {
+    const size_t smem_half = 8 * sizeof(BwdHalfSmem<CS>);
+    static std::atomic<unsigned long long> attr_done{0};  // per template instance, per device
+    if (first_call_on_device(attr_done)) {
         if (int e = check_cuda(cudaFuncSetAttribute(composite_bwd_kernel<C, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)smem), "composite_bwd smem attr")) return e;
-        attr_set = true;
-    }
-    const size_t smem_half = 8 * sizeof(BwdHalfSmem<CS>);
-    static bool attr_half_set = false;
-    if (!attr_half_set) {
         if (int e = check_cuda(cudaFuncSetAttribute(composite_bwd_half_kernel<C, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)smem_half), "composite_bwd_half smem attr")) return e;
-        attr_half_set = true;
     }
     StageScope prof(HGS_STAGE_COMPOSITE_BWD, s);
     if (composite_blocks_4x4())

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
 #include "../../include/hairgs_rast.h"
 
 #define HGS_TILE_PIX (HGS_TILE * HGS_TILE)
@@ -17,6 +18,15 @@ namespace hgs {
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int stage_check(const char* stage, int debug, cudaStream_t s);
+
+// Per-device one-time initialisation (function attributes and the like are per device, and a process may drive
+// several): true exactly once per (flag word, current device); thread-safe.
+inline bool first_call_on_device(std::atomic<unsigned long long>& done) {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    return (done.fetch_or(bit) & bit) == 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Stage profiler: counts every kernel launch of the library and, when enabled through
@@ -124,11 +134,21 @@ static constexpr int kMaxPasses = 8;
 
 struct SortLayout {
     uint32_t* hist;     // [kMaxPasses * 256] global digit histograms -> exclusive offsets
-    uint32_t* tickets;  // [kMaxPasses] dynamic tile ids
-    uint32_t* status;   // [kMaxPasses * ntiles * 256] decoupled look-back words
+    uint32_t* tickets;  // [kMaxPasses] dynamic tile ids (a tile's id is the order in which its block STARTED)
+    uint32_t* status;   // [kMaxPasses * ntiles * 256] per-tile digit counts (flag in bit 31)
+    uint32_t* group;    // [kMaxPasses * ngroups * 256] per-group digit counts: arrivals << 24 | sum
     size_t bytes;
     size_t ntiles;
+    size_t ngroups;
+    int group_shift;    // tiles per group = 1 << group_shift
 };
+
+// Two-level look-back of the onesweep passes: tiles are grouped (32 / 64 / 128 per group, ~sqrt(ntiles)); a tile's
+// exclusive prefix is the sum of the complete groups before its own plus the tiles before it inside its group.  Every
+// word it reads is published by a tile right after its local ranking, so no tile ever waits for another tile's look-back
+// (the classic chained scan serialises ~ntiles/32 L2 round trips when the whole grid is one wave, which is what a
+// 1-2 M instance sort is on 148 SMs).
+__host__ __device__ inline int sort_group_shift(size_t ntiles) { return ntiles <= 1024 ? 5 : (ntiles <= 4096 ? 6 : 7); }
 
 __host__ __device__ inline SortLayout carve_sort(void* base, int64_t n) {
     SortLayout s;
@@ -136,8 +156,11 @@ __host__ __device__ inline SortLayout carve_sort(void* base, int64_t n) {
     size_t off = 0;
     s.ntiles = (size_t)((n + kSortTile - 1) / kSortTile);
     if (s.ntiles == 0) s.ntiles = 1;
+    s.group_shift = sort_group_shift(s.ntiles);
+    s.ngroups = (s.ntiles + ((size_t)1 << s.group_shift) - 1) >> s.group_shift;
     s.hist = (uint32_t*)(p + off);    off = align_up(off + (size_t)kMaxPasses * kRadix * 4);
     s.tickets = (uint32_t*)(p + off); off = align_up(off + (size_t)kMaxPasses * 4);
+    s.group = (uint32_t*)(p + off);   off = align_up(off + (size_t)kMaxPasses * s.ngroups * kRadix * 4);
     s.status = (uint32_t*)(p + off);  off = align_up(off + (size_t)kMaxPasses * s.ntiles * kRadix * 4);
     s.bytes = off;
     return s;
@@ -250,15 +273,6 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-
-// cp.async helpers (LDGSTS): 16-byte global -> shared copies without register staging.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // non-blocking prefetch of the cache line(s) holding [p, p+bytes): lets a thread start every input stream it will
 // need before the first data-dependent early-out (otherwise each cull test exposes one full DRAM latency)

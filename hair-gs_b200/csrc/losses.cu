@@ -88,7 +88,9 @@ static constexpr int kSsimStrip = 4;                        // outputs per threa
 static constexpr int kSsimTaps = 11;
 static constexpr int kSsimWin = kSsimStrip + kSsimTaps - 1; // 14 inputs feed 4 outputs
 
-__device__ __constant__ float kGauss11[11];  // normalised 11-tap Gaussian, sigma 1.5 (loss/losses.py:24-40)
+// normalised 11-tap Gaussian, sigma 1.5 (loss/losses.py:24-40): exp(-(x-5)^2 / 4.5) / sum, evaluated in float32.
+// A compile-time initialiser: valid on every device of the process and inside a stream capture (no lazy upload).
+__device__ __constant__ float kGauss11[11] = {0.00102838036f, 0.00759875868f, 0.0360007733f, 0.109360702f, 0.213005543f, 0.266011745f, 0.213005543f, 0.109360702f, 0.0360007733f, 0.00759875868f, 0.00102838036f};
 
 using HairLossArgs = hgs_hair_loss;
 
@@ -360,14 +362,6 @@ __global__ void hair_loss_finish_kernel(const HairLossArgs a) {
 }
 
 int launch_hair_image_loss(const HairLossArgs& a, cudaStream_t s) {
-    static bool init = false;
-    if (!init) {
-        float g[11], sum = 0.f;
-        for (int x = 0; x < 11; ++x) { g[x] = expf(-((x - 5) * (x - 5)) / (2.f * 1.5f * 1.5f)); sum += g[x]; }
-        for (int x = 0; x < 11; ++x) g[x] /= sum;
-        if (int e = check_cuda(cudaMemcpyToSymbol(kGauss11, g, sizeof(g)), "gaussian window")) return e;
-        init = true;
-    }
     if (int e = check_cuda(cudaMemsetAsync(a.terms, 0, 8 * sizeof(float), s), "memset loss terms")) return e;
     const long long HW = (long long)a.height * a.width;
     long long nb = (HW + 255) / 256;

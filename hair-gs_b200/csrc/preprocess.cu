@@ -57,6 +57,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 // reference builds on the torch side (utils/transform.py:69-86 + pytorch3d matrix_to_quaternion) never has to exist.
 struct StrandGeom {
     float3 mean, dhat, diff;
+    float3 ohat;  // orientation colour: diff/dist when dist >= 1e-7 (get_orientation :188-201 uses >=, get_rotation :147-165 >)
     float dist, sx, syz, ew;  // sx, syz include scale_modifier; ew = exp(width)
     bool collapsed;
 };
@@ -72,6 +73,8 @@ __device__ __forceinline__ StrandGeom strand_geom(const float* __restrict__ endp
     sg.collapsed = !(sg.dist > kMinVal);
     sg.dhat = sg.collapsed ? make_float3(1.f, 0.f, 0.f)
                            : make_float3(sg.diff.x / sg.dist, sg.diff.y / sg.dist, sg.diff.z / sg.dist);
+    sg.ohat = (sg.dist >= kMinVal) ? make_float3(sg.diff.x / sg.dist, sg.diff.y / sg.dist, sg.diff.z / sg.dist)
+                                   : make_float3(1.f, 0.f, 0.f);
     sg.sx = fmaxf(sg.dist * 0.5f * kDistToScale, kMinVal) * mod;
     sg.ew = expf(width[idx]);
     sg.syz = sg.ew * mod;
@@ -82,6 +85,18 @@ __device__ __forceinline__ void strand_cov3d(const StrandGeom& sg, float* cov3D)
     const float3 d = sg.dhat;
     cov3D[0] = b + c * d.x * d.x; cov3D[1] = c * d.x * d.y; cov3D[2] = c * d.x * d.z;
     cov3D[3] = b + c * d.y * d.y; cov3D[4] = c * d.y * d.z; cov3D[5] = b + c * d.z * d.z;
+}
+
+// Quaternion i of a [P,4] float array.  One 128-bit load when the array is 16-byte aligned (every torch allocation is),
+// four scalar loads otherwise: the reference reads glm::vec4 with 4-byte alignment, so a sliced / re-homed tensor (e.g. a
+// parameter living at an odd offset of a flat optimiser buffer) must work here too.
+__device__ __forceinline__ float4 load_quat(const float* __restrict__ q, int i) {
+    if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) return reinterpret_cast<const float4*>(q)[i];
+    return make_float4(q[4 * (size_t)i], q[4 * (size_t)i + 1], q[4 * (size_t)i + 2], q[4 * (size_t)i + 3]);
+}
+__device__ __forceinline__ void store_quat(float* __restrict__ q, int i, const float4 v) {
+    if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) { reinterpret_cast<float4*>(q)[i] = v; return; }
+    q[4 * (size_t)i] = v.x; q[4 * (size_t)i + 1] = v.y; q[4 * (size_t)i + 2] = v.z; q[4 * (size_t)i + 3] = v.w;
 }
 
 // Sigma = (S R)^T (S R) from scale and raw (un-normalised) quaternion (forward.cu:118-152).
@@ -271,7 +286,7 @@ __global__ void __launch_bounds__(kPreprocThreads, 6) preprocess_fwd_kernel(cons
                 cov3D = a.cov3D_precomp + (size_t)idx * 6;
             } else {
                 const float3 sc = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
-                const float4 rq = reinterpret_cast<const float4*>(a.rotations)[idx];
+                const float4 rq = load_quat(a.rotations, idx);
                 cov3d_from_scale_rot(sc, a.scale_modifier, rq, cov3D_local);
                 cov3D = cov3D_local;
             }
@@ -301,7 +316,7 @@ __global__ void __launch_bounds__(kPreprocThreads, 6) preprocess_fwd_kernel(cons
                 const float3 c = sh_to_rgb(a.D, a.shs + (size_t)idx * a.M * 3, p_orig,
                                            make_float3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]), cb);
                 reinterpret_cast<float4*>(rgb_out)[0] = make_float4(c.x, c.y, c.z, sigmoidf_(a.mask_logit[idx]));
-                reinterpret_cast<float4*>(rgb_out)[1] = make_float4(sg.dhat.x, sg.dhat.y, sg.dhat.z, 0.f);
+                reinterpret_cast<float4*>(rgb_out)[1] = make_float4(sg.ohat.x, sg.ohat.y, sg.ohat.z, 0.f);
                 a.g.clamped[idx] = (uint8_t)cb;
             } else if (a.colors_precomp == nullptr) {
                 uint32_t cb;
@@ -338,7 +353,7 @@ __global__ void __launch_bounds__(kPreprocThreads, 6) preprocess_fwd_kernel(cons
 // tiles_touched -> inclusive offsets (replaces cub::DeviceScan::InclusiveSum, rasterizer_impl.cu:277)
 // ------------------------------------------------------------------------------------------------
 // Single-pass chained scan: 4096 values per block (16 per thread, 128-bit loads/stores), block aggregate published
-// to a status array, predecessors resolved by a warp-wide decoupled look-back in blockIdx order.  The grand total
+// to a status array, predecessors resolved by a warp-wide decoupled look-back over ticketed block ids.  The grand total
 // lands in hdr->num_rendered so the host never needs it to launch the rest of the pass.  (A first version fused this
 // into preprocess_fwd; ncu showed the two block barriers it needs as that kernel's top stall — 14 warps per issue —
 // because every warp of the heavy kernel waited for the slowest one.  8 B/Gaussian of extra traffic is cheaper.)
@@ -354,8 +369,13 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(int P, const ui
     __shared__ uint32_t s_warp_sum[kScanThreads / 32];
     __shared__ uint32_t s_warp_dmax[kScanThreads / 32], s_warp_dmin_inv[kScanThreads / 32];
     __shared__ unsigned long long s_block_excl;
+    __shared__ uint32_t s_bid;
     const int tid = threadIdx.x;
-    const uint32_t bid = blockIdx.x;
+    // block id = start order (one atomic per block), see onesweep_pass_kernel: the look-back waits on blocks with smaller
+    // ids, which must therefore be running or done whatever order the hardware dispatches blocks in
+    if (tid == 0) s_bid = atomicAdd(&hdr->block_ticket, 1u);
+    __syncthreads();
+    const uint32_t bid = s_bid;
     const uint32_t lane = tid & 31, warp = tid >> 5;
     const int base = (int)(bid * kScanTile) + tid * kScanItems;
 
@@ -576,7 +596,7 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
         for (int i = 0; i < 6; ++i) a.dL_dcov3D[6 * (size_t)idx + i] = 0.f;
         if (a.dL_dsh) for (int i = 0; i < a.M * 3; ++i) a.dL_dsh[(size_t)idx * a.M * 3 + i] = 0.f;
         a.dL_dscale[3 * idx] = 0.f; a.dL_dscale[3 * idx + 1] = 0.f; a.dL_dscale[3 * idx + 2] = 0.f;
-        reinterpret_cast<float4*>(a.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        store_quat(a.dL_drot, idx, make_float4(0.f, 0.f, 0.f, 0.f));
         return;
     }
 
@@ -600,7 +620,7 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
         for (int i = 0; i < 6; ++i) cov3D[i] = a.cov3D_precomp[6 * (size_t)idx + i];
     } else {
         sc = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
-        rq = reinterpret_cast<const float4*>(a.rotations)[idx];
+        rq = load_quat(a.rotations, idx);
         cov3d_from_scale_rot(sc, a.scale_modifier, rq, cov3D);
     }
 
@@ -819,16 +839,19 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
         // sx = max(dist/2*k, 1e-7)*mod
         const bool sx_live = sg.dist * 0.5f * kDistToScale > kMinVal;
         const float dL_ddist = sx_live ? dL_da * 2.f * sg.sx * (0.5f * kDistToScale) : 0.f;
-        float3 dL_dd = make_float3(2.f * (av - bv) * Gd.x, 2.f * (av - bv) * Gd.y, 2.f * (av - bv) * Gd.z);
-        // orientation colour channels 4..6 carry d itself
+        // the covariance sees d only when the segment is not collapsed (dist > 1e-7: rotation branch), the orientation
+        // colour channels 4..6 carry diff/dist whenever dist >= 1e-7 (the reference's two getters differ at equality)
+        float3 dL_dd = sg.collapsed ? make_float3(0.f, 0.f, 0.f)
+                                    : make_float3(2.f * (av - bv) * Gd.x, 2.f * (av - bv) * Gd.y, 2.f * (av - bv) * Gd.z);
         const float* dcol = a.dL_dcolor + (size_t)idx * a.channels;
-        dL_dd.x += dcol[4]; dL_dd.y += dcol[5]; dL_dd.z += dcol[6];
         float3 dL_ddiff = make_float3(0.f, 0.f, 0.f);
-        if (!sg.collapsed) {
-            const float dd = d.x * dL_dd.x + d.y * dL_dd.y + d.z * dL_dd.z;
+        if (sg.dist >= kMinVal) {
+            dL_dd.x += dcol[4]; dL_dd.y += dcol[5]; dL_dd.z += dcol[6];
+            const float3 o = sg.ohat;
+            const float dd = o.x * dL_dd.x + o.y * dL_dd.y + o.z * dL_dd.z;
             const float inv = 1.f / sg.dist;
-            dL_ddiff = make_float3((dL_dd.x - d.x * dd) * inv + d.x * dL_ddist, (dL_dd.y - d.y * dd) * inv + d.y * dL_ddist,
-                                   (dL_dd.z - d.z * dd) * inv + d.z * dL_ddist);
+            dL_ddiff = make_float3((dL_dd.x - o.x * dd) * inv + o.x * dL_ddist, (dL_dd.y - o.y * dd) * inv + o.y * dL_ddist,
+                                   (dL_dd.z - o.z * dd) * inv + o.z * dL_ddist);
         }
         const long long i0 = a.pairs[2 * (size_t)idx], i1 = a.pairs[2 * (size_t)idx + 1];
         atomicAdd(a.dL_dendpoints + 3 * i0, 0.5f * dmean.x - dL_ddiff.x);
@@ -895,10 +918,10 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
                4 * y * (dMt.m[2][2] + dMt.m[0][0]);
         dq.w = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) -
                4 * z * (dMt.m[1][1] + dMt.m[0][0]);
-        reinterpret_cast<float4*>(a.dL_drot)[idx] = dq;
+        store_quat(a.dL_drot, idx, dq);
     } else {
         a.dL_dscale[3 * idx] = 0.f; a.dL_dscale[3 * idx + 1] = 0.f; a.dL_dscale[3 * idx + 2] = 0.f;
-        reinterpret_cast<float4*>(a.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        store_quat(a.dL_drot, idx, make_float4(0.f, 0.f, 0.f, 0.f));
     }
 }
 
@@ -946,7 +969,7 @@ __global__ void view_cov3d_kernel(int P, const float* __restrict__ scales, const
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     const float3 sc = make_float3(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]);
-    const float4 rq = reinterpret_cast<const float4*>(rotations)[idx];
+    const float4 rq = load_quat(rotations, idx);
     float c[6];
     cov3d_from_scale_rot(sc, mod, rq, c);
     for (int i = 0; i < 6; ++i) out[6 * (size_t)idx + i] = c[i];

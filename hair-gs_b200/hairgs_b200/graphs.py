@@ -11,9 +11,12 @@ What varies per view lives in device memory the caller fills between replays: th
 full_proj_transform, camera_center: 35 floats) and the six target planes.  The reference has no counterpart (its forward
 blocks on `num_rendered` mid-pass, rasterizer_impl.cu:281, which cannot be captured).
 
-Validation is deferred, never skipped: every replay copies (num_rendered, overflow, depth range) to pinned memory and
-the next use of the slot checks it against the plan (`HgsPlanError` if the view did not fit — its results were then
-computed on a truncated instance list and the caller must re-plan and redo that step).
+Validation is deferred, never skipped: every replay copies (num_rendered, overflow, depth range) to pinned memory; the
+next use of the slot checks it against the plan, and `validate()` checks every slot used so far.  A training loop calls
+`validate()` after the last view of a step and BEFORE the all-reduce / optimiser step (`HgsPlanError` if a view did not fit:
+its image and gradients came from a truncated instance list; the parameters are still untouched, so the caller re-plans —
+`measure_plan` — re-captures and redoes the step).  Widths and positions train, so a long run re-measures the plan
+periodically (e.g. with every topology edit, which needs a re-capture anyway).
 """
 import math
 
@@ -133,8 +136,9 @@ class GraphedStrandStep:
         m = self.model
         lam = self.lambdas
         l_dssim = float(lam.get("lambda_dssim", 0.2))
-        weights = (max(0.0, 1.0 - l_dssim), l_dssim, float(lam.get("lambda_mask", 0.1)),
-                   float(lam.get("lambda_orientation", 0.1)))
+        # defaults: the reference's OptimizationParams (arguments/__init__.py:84-86)
+        weights = (max(0.0, 1.0 - l_dssim), l_dssim, float(lam.get("lambda_mask", 0.01)),
+                   float(lam.get("lambda_orientation", 100.0)))
         settings = dict(image_height=self.H, image_width=self.W, tanfovx=math.tan(self.fovx * 0.5),
                         tanfovy=math.tan(self.fovy * 0.5), bg=self.bg7, scale_modifier=1.0, viewmatrix=wvt,
                         projmatrix=cd[16:32].view(4, 4), sh_degree=m.active_sh_degree, campos=cd[32:35], debug=False,
@@ -206,7 +210,19 @@ class GraphedStrandStep:
         self.replays += 1
         return self.loss[slot]
 
+    def validate(self):
+        """Call BEFORE anything irreversible consumes the gradients of the views replayed so far (the all-reduce and the
+        optimiser step mutate the parameters and their moments in place): waits for the last replay of every slot — one
+        event wait each, the read-back words are already in pinned memory — and raises HgsPlanError if any view did not
+        fit the captured plan, while the step can still be redone with a new plan.  Returns the instance counts."""
+        out = []
+        for p, ev in zip(self.plans, self.done):
+            if ev is not None:
+                ev.synchronize()
+                out.append(p.check())
+        return out
+
     def check(self):
-        """Synchronises and validates the last replay of every slot."""
+        """Synchronises the device and validates the last replay of every slot."""
         torch.cuda.synchronize(self.dev)
         return [p.check() for p, ev in zip(self.plans, self.done) if ev is not None]

@@ -129,21 +129,24 @@ def view_rot_of(world_view_transform):
     return [float(v) for v in world_view_transform[:3, :3].reshape(-1).tolist()]
 
 
-def hair_image_loss(image7, gt_rgb, gt_mask, gt_theta, confidence, view_rot, lambda_dssim=0.2, lambda_mask=0.1,
-                    lambda_orientation=0.1, orient_mask=None, bg_orient=(0.0, 0.0, 0.0)):
+def hair_image_loss(image7, gt_rgb, gt_mask, gt_theta, confidence, view_rot, lambda_dssim=0.2, lambda_mask=0.01,
+                    lambda_orientation=100.0, orient_mask=None, bg_orient=(0.0, 0.0, 0.0)):
     """loss, terms = the image-space part of Hair-GS's loss_function on the fused strand render.
 
     image7: [7,H,W] from rasterize_strands (rgb | mask logit | world orientation).  view_rot: view_rot_of(camera
     .world_view_transform) — nine host floats — or camera.world_view_transform itself as a CUDA [4,4] tensor (the
     kernel then reads the rotation from device memory: required inside a captured CUDA graph, hairgs_b200.graphs).
     terms (no grad): [total, l1, dssim, mask, orientation, n_orientation_pixels, -, -].
+    The lambda defaults are the reference's OptimizationParams (arguments/__init__.py:84-86).  Two documented deviations
+    (INTEGRATION.md): an empty orientation mask gives an orientation term of 0 (the reference's mean over nothing is NaN),
+    and the orientation channel uses the reference's own `norm >= 1e-7` collapsed-segment rule of get_orientation.
     """
     lambdas = (max(0.0, 1.0 - lambda_dssim), lambda_dssim, lambda_mask, lambda_orientation)
     return _HairImageLoss.apply(image7, gt_rgb, gt_mask, gt_theta, confidence, orient_mask, view_rot, lambdas, bg_orient)
 
 
 def hair_image_loss_torch(rgb, mask_plane, orientation, gt_rgb, gt_mask, gt_theta, confidence, world_view_transform,
-                          lambda_dssim=0.2, lambda_mask=0.1, lambda_orientation=0.1, orient_mask=None,
+                          lambda_dssim=0.2, lambda_mask=0.01, lambda_orientation=100.0, orient_mask=None,
                           bg_orient=(0.0, 0.0, 0.0)):
     """The same loss written with torch ops the way Hair-GS composes it (loss/losses.py:16-17, 24-84, 87-103, 244-288,
     311-316, 336-346).  It is what the three-render reference arm evaluates in bench.py and what the tests compare the

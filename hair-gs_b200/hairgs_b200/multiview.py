@@ -81,3 +81,52 @@ class GradBucket:
         if average_over:
             self.flat.div_(float(average_over))
         return self
+
+
+class AsyncReducer:
+    """All-reduce of a flat gradient bucket OFF the critical path ("on a side stream, overlapped with the
+    first view of the next batch").  launch(flat) snapshots the bucket into a staging buffer (one device copy on the
+    caller's stream) and sums the snapshot across ranks on a side stream; the caller's stream goes straight on to the
+    next batch, which may overwrite the bucket at once.  wait() makes the caller's stream wait for the sum, which is then
+    in `.staging` (what the optimiser consumes).  On CPU tensors (gloo tests) it degrades to a blocking all-reduce."""
+
+    def __init__(self, numel, device, group=None):
+        self.staging = torch.zeros(int(numel), dtype=torch.float32, device=device)
+        self.group = group
+        self.cuda = torch.device(device).type == "cuda"
+        self.stream = torch.cuda.Stream(device=device) if self.cuda else None
+        self.done = None
+        self.launched = 0
+
+    def _active(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def launch(self, flat):
+        if flat.numel() != self.staging.numel():
+            raise ValueError("AsyncReducer: bucket size changed")
+        self.launched += 1
+        if not self.cuda:
+            self.staging.copy_(flat)
+            if self._active():
+                dist.all_reduce(self.staging, op=dist.ReduceOp.SUM, group=self.group)
+            return self
+        dev = self.staging.device
+        cur = torch.cuda.current_stream(dev)
+        if self.done is not None:
+            cur.wait_event(self.done)          # the previous reduction has finished with the staging buffer
+        self.staging.copy_(flat, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            if self._active():
+                dist.all_reduce(self.staging, op=dist.ReduceOp.SUM, group=self.group)
+            self.done = torch.cuda.Event()
+            self.done.record(self.stream)
+        return self
+
+    def wait(self):
+        """The caller's stream waits for the last launched reduction; returns the staging buffer holding the sum."""
+        if self.cuda and self.done is not None:
+            torch.cuda.current_stream(self.staging.device).wait_event(self.done)
+        return self.staging

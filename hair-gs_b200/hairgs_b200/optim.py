@@ -99,10 +99,37 @@ class DensifyStats:
     """max_radii2D / xyz_gradient_accum / denom of scene/gaussian_model.py:208-211, updated by one kernel per view
     (update_densification_stats, :675-682)."""
 
-    def __init__(self, P, device):
+    def __init__(self, P, device, distributed=False):
+        """distributed=True (view-sharded training): update() accumulates this rank's views into LOCAL
+        buffers and reduce() folds them into the public tensors with (sum, sum, max) across ranks — called on
+        densification iterations only, so the per-view path stays collective-free."""
         self.max_radii2D = torch.zeros(P, dtype=torch.float32, device=device)
         self.xyz_gradient_accum = torch.zeros(P, 1, dtype=torch.float32, device=device)
         self.denom = torch.zeros(P, 1, dtype=torch.float32, device=device)
+        self.distributed = bool(distributed)
+        if self.distributed:
+            self.local_max_radii2D = torch.zeros_like(self.max_radii2D)
+            self.local_xyz_gradient_accum = torch.zeros_like(self.xyz_gradient_accum)
+            self.local_denom = torch.zeros_like(self.denom)
+
+    def reduce(self, group=None):
+        """Fold the views every rank has seen since the last call into max_radii2D / xyz_gradient_accum / denom:
+        all-reduce SUM of the two accumulators, MAX of the radii (the nonlinear reductions of
+        scene/gaussian_model.py:675-682 commute with this split: max of maxima, sum of per-view norms, sum of counts)."""
+        import torch.distributed as dist
+        if not self.distributed:
+            return self
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.local_xyz_gradient_accum, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(self.local_denom, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(self.local_max_radii2D, op=dist.ReduceOp.MAX, group=group)
+        self.xyz_gradient_accum.add_(self.local_xyz_gradient_accum)
+        self.denom.add_(self.local_denom)
+        torch.maximum(self.max_radii2D, self.local_max_radii2D, out=self.max_radii2D)
+        self.local_xyz_gradient_accum.zero_()
+        self.local_denom.zero_()
+        self.local_max_radii2D.zero_()
+        return self
 
     def update(self, viewspace_point_grad, radii):
         lib = L.load()
@@ -115,6 +142,7 @@ class DensifyStats:
             raise L.HgsError("DensifyStats.update: expected grad [P,>=2] and radii [P]")
         r = radii if (radii.dtype == torch.int32 and radii.is_contiguous()) else radii.to(torch.int32).contiguous()
         with torch.cuda.device(dev):
-            L.check(lib.hgs_densify_stats(P, r.data_ptr(), g.data_ptr(), g.shape[1], self.max_radii2D.data_ptr(),
-                                          self.xyz_gradient_accum.data_ptr(), self.denom.data_ptr(), L.stream_ptr(dev)),
-                    "densify_stats")
+            mr, acc, den = ((self.local_max_radii2D, self.local_xyz_gradient_accum, self.local_denom) if self.distributed
+                            else (self.max_radii2D, self.xyz_gradient_accum, self.denom))
+            L.check(lib.hgs_densify_stats(P, r.data_ptr(), g.data_ptr(), g.shape[1], mr.data_ptr(), acc.data_ptr(),
+                                          den.data_ptr(), L.stream_ptr(dev)), "densify_stats")

@@ -124,7 +124,7 @@ def _load_gold(path):
     return d, z
 
 
-@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLD, "*.npz")) if "knn" not in p and "loss_ref" not in p),
+@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLD, "*.npz")) if "knn" not in p and "loss_ref" not in p and "pyref" not in p),
                          ids=lambda p: os.path.basename(p)[:-4])
 def test_golden_fixtures(path, blocks):
     """No reference needed: the fixtures ARE the reference's outputs (generated by tests/golden/make_golden.py)."""
@@ -318,6 +318,46 @@ def test_sort_pairs_matches_stable_sort(n, end_bit):
     assert torch.equal(k_out, keys[order]) and torch.equal(v_out, vals[order])
 
 
+def test_lookback_is_safe_under_concurrent_oversubscribed_grids():
+    """The chained scans (onesweep passes, tile_scan) take their tile id from an atomic ticket, so a tile only ever waits on
+    tiles that have STARTED - whatever order the hardware dispatches blocks in.  Stress: two sorts of 6 M pairs (1465
+    blocks each, far more than fit on the device at once) and two full forward passes run concurrently on different
+    streams, several rounds; every result must equal the single-stream result and nothing may hang."""
+    import diff_gaussian_rasterization._C as ours_C
+    from hairgs_b200 import _lib as L
+    lib = L.load()
+    n, end_bit = 6_000_000, 45
+    g = torch.Generator(device="cuda").manual_seed(11)
+    streams = [torch.cuda.Stream(device=dev()) for _ in range(2)]
+    jobs = []
+    for s in streams:
+        keys = (torch.randint(0, 4096, (n,), generator=g, device=dev(), dtype=torch.int64) << 32) | \
+            torch.randint(0, 1 << 31, (n,), generator=g, device=dev(), dtype=torch.int64)
+        vals = torch.arange(n, device=dev(), dtype=torch.int32)
+        ref_k, order = torch.sort(keys & ((1 << end_bit) - 1), stable=True)
+        jobs.append(dict(keys=keys, vals=vals, ref_k=keys[order], ref_v=vals[order], ki=torch.empty_like(keys),
+                         vi=torch.empty_like(vals), ko=torch.empty_like(keys), vo=torch.empty_like(vals),
+                         ws=torch.empty(lib.hgs_sort_bytes(n), dtype=torch.uint8, device=dev())))
+    d = common.strand_inputs(3000, 100, 512, 512, dev(), seed=2)
+    N0, c0, r0, *_ = ours_C.rasterize_gaussians(*common.fwd_args(d))
+    torch.cuda.synchronize()
+    for rnd in range(4):
+        outs = []
+        for s, j in zip(streams, jobs):
+            s.wait_stream(torch.cuda.current_stream(dev()))
+            with torch.cuda.stream(s):
+                j["ki"].copy_(j["keys"])
+                j["vi"].copy_(j["vals"])
+                L.check(lib.hgs_sort_pairs(n, end_bit, j["ki"].data_ptr(), j["vi"].data_ptr(), j["ko"].data_ptr(),
+                                           j["vo"].data_ptr(), j["ws"].data_ptr(), s.cuda_stream))
+                outs.append(ours_C.rasterize_gaussians(*common.fwd_args(d)))
+        torch.cuda.synchronize()
+        for j in jobs:
+            assert torch.equal(j["ko"], j["ref_k"]) and torch.equal(j["vo"], j["ref_v"]), rnd
+        for N, c, r, *_ in outs:
+            assert N == N0 and torch.equal(c, c0) and torch.equal(r, r0), rnd
+
+
 def test_knn_vs_reference_and_oracle():
     from oracle import pyoracle
     import simple_knn._C as knn
@@ -336,7 +376,143 @@ def test_knn_vs_reference_and_oracle():
 
 
 # ---------------------------------------------------------------------------------------------------
-# full-size properties (BASELINE configs 3 and 5): no oracle can run these in seconds
+# BASELINE.json configs at FULL size against the reference build (oracle/_ref renders cfg3 in ~10 ms per pass)
+# ---------------------------------------------------------------------------------------------------
+def _full_cases():
+    d = dev()
+    return {
+        "cfg2_blobs_sh3": lambda: common.blob_inputs(300000, 512, 512, d, seed=0),
+        "cfg3_rgb": lambda: common.strand_inputs(10000, 100, 1024, 1024, d, seed=0),
+        "cfg3_mask": lambda: common.strand_inputs(10000, 100, 1024, 1024, d, seed=0, view=1, colors="mask"),
+        "cfg3_orientation": lambda: common.strand_inputs(10000, 100, 1024, 1024, d, seed=0, view=2, colors="orientation"),
+        "cfg5_rgb": lambda: common.strand_inputs(40000, 101, 2048, 2048, d, seed=0),
+    }
+
+
+@pytest.mark.parametrize("name", ["cfg2_blobs_sh3", "cfg3_rgb", "cfg3_mask", "cfg3_orientation", "cfg5_rgb"])
+def test_full_size_configs_vs_reference(name):
+    """cfg2 (300 k SH-3 Gaussians, 512^2), cfg3 (990 k strand Gaussians, 1024^2, all three colour sets) and cfg5 (4 M,
+    2048^2): radii, tiles_touched, offsets, sorted 47-bit keys, point_list, ranges, n_contrib and the depth / means2D /
+    conic / cov3D words bit-exact; pixels <= 1e-4; every gradient rel <= 1e-3."""
+    C = need_ref()
+    d = _full_cases()[name]()
+    No, co, ro, bo, vo = common.ours_forward(d)
+    Nr, cr, rr, br, vr = common.ref_forward(d)
+    assert No > d["means3D"].shape[0]      # the case really is at size
+    assert_forward_equal(vo, vr, co, cr, ro, rr, d, No, Nr)
+    del vo, vr
+    torch.manual_seed(7)
+    dL = torch.randn_like(cr)
+    import diff_gaussian_rasterization._C as ours_C
+    go = ours_C.rasterize_gaussians_backward(*common.bwd_args(d, ro, dL, bo[0], No, bo[1], bo[2]))
+    gr = C.rasterize_gaussians_backward(*common.bwd_args(d, rr, dL, br[0], Nr, br[1], br[2]))
+    for n, a, b in zip(GRAD_NAMES, go, gr):
+        assert a.shape == b.shape, n
+        if a.numel():
+            assert torch.isfinite(a).all(), n
+            assert common.rel_err(a, b) <= GRAD_TOL, (n, common.rel_err(a, b))
+
+
+def _ref_three_pass(sc, cam, bg7, w7, D):
+    """RGB, mask and orientation of one view the way Hair-GS renders them (loss/losses.py:246-249, 311-312,
+    train.py:146-155), on the REFERENCE: its CUDA rasterizer under its own render() and HairGaussianModel getters when the
+    byte-compiled reference Python travelled to the box (oracle/_ref/pyref), else under this repository's pinned glue."""
+    from oracle import ref_python as rp
+    C = need_ref()
+    P = torch.nn.Parameter
+    if rp.available():
+        ns = rp.load(with_cuda_ext=True)
+        m = ns.hair_gaussian_model.HairGaussianModel(D, device="cuda")
+        m._endpoints, m.endpoint_pairs = P(sc.endpoints.clone()), sc.endpoint_pairs
+        m._width, m._opacity, m._mask = P(sc.width.clone()), P(sc.opacity_logit.clone()), P(sc.mask_logit.clone())
+        m._features_dc, m._features_rest = P(sc.features_dc.clone()), P(sc.features_rest.clone())
+        m.active_sh_degree = D
+        render, how = ns.gaussian_renderer.render, "reference python + reference CUDA"
+        params = {"_endpoints": m._endpoints, "_width": m._width, "_opacity": m._opacity, "_mask": m._mask,
+                  "_features_dc": m._features_dc}
+    else:
+        import diff_gaussian_rasterization as dgr
+        from gaussian_renderer import render
+        from hairgs_b200 import models
+        m = models.StrandModel(sc, sh_degree=D).to(dev())
+        dgr._RasterizeGaussians.backend = C
+        how = "repository glue + reference CUDA"
+        params = {n: p for n, p in m.named_parameters() if p.numel()}
+    try:
+        r_rgb = render(cam, m, bg7[0:3])
+        r_mask = render(cam, m, bg7[3:4].repeat(3), override_color=m.get_mask.repeat(1, 3))
+        r_ori = render(cam, m, bg7[4:7], override_color=m.get_orientation)
+        loss = (r_rgb["render"] * w7[0:3]).sum() + (r_mask["render"][0:1] * w7[3:4]).sum() + (r_ori["render"] * w7[4:7]).sum()
+        loss.backward()
+    finally:
+        if not rp.available():
+            import diff_gaussian_rasterization as dgr
+            dgr._RasterizeGaussians.backend = dgr._C
+    img = torch.cat([r_rgb["render"], r_mask["render"][0:1], r_ori["render"]]).detach()
+    vs = r_rgb["viewspace_points"].grad + r_mask["viewspace_points"].grad + r_ori["viewspace_points"].grad
+    return img, r_rgb["radii"], {n: p.grad.clone() for n, p in params.items() if p.grad is not None}, vs, how
+
+
+def test_fused_and_graph_replay_vs_reference_three_pass_cfg3():
+    """The path bench.py's headline is measured on — fused strand pass, eager and as a CUDA-graph replay — at FULL cfg3 size
+    against the reference's three passes.  Reported and asserted: radius flips, pixels over 1e-4, max-abs pixel error,
+    gradient rel errors.  Bounds: the closed-form covariance of the strand entry and the reference's quaternion route
+    round differently in the last bit, which can move a radius by one and flip an alpha >= 1/255 test on isolated
+    (pixel, Gaussian) pairs: <= 2e-5 of the Gaussians / pixel values; everything else within the north_star tolerances."""
+    import json
+    from hairgs_b200 import fused, graphs, models, scenes
+    H = W = 1024
+    sc = scenes.strand_scene(10000, 100, seed=0).to(dev())
+    cams = scenes.orbit_cameras(16, W, H, device=dev())
+    cam = cams[3]
+    torch.manual_seed(5)
+    w7 = torch.randn(7, H, W, device=dev()) / (H * W)
+    bg7 = torch.zeros(7, device=dev())
+    ref_img, ref_radii, ref_g, ref_vs, how = _ref_three_pass(sc, cam, bg7, w7, 0)
+    names = {"endpoints": "_endpoints", "width": "_width", "opacity": "_opacity", "mask": "_mask", "features": "_features_dc"}
+    report = {"reference": how, "P": int(sc.endpoint_pairs.shape[0]), "pixel_values": int(ref_img.numel())}
+
+    def check(tag, img, radii, grads, vs):
+        diff = (img - ref_img).abs()
+        r = {"radius_flips": int((radii != ref_radii).sum()), "pixels_over_1e-4": int((diff > PIX_TOL).sum()),
+             "pixel_max_abs": float(diff.max()),
+             "grad_rel": {n: common.rel_err(grads[n], ref_g[n]) for n in ref_g if n in grads}}
+        if vs is not None:
+            r["grad_rel"]["viewspace_points"] = common.rel_err(vs, ref_vs)
+        report[tag] = r
+        return r
+
+    m1 = models.StrandModel(sc).to(dev())
+    out = fused.render_strands(cam, m1, bg7)
+    (out["image7"] * w7).sum().backward()
+    r1 = check("fused_eager", out["image7"].detach(), out["radii"], {n: p.grad for n, p in m1.named_parameters() if p.grad is not None},
+               out["viewspace_points"].grad)
+
+    m2 = models.StrandModel(sc).to(dev())
+    sink = fused.GradSink({k: torch.zeros_like(getattr(m2, n)) for k, n in names.items()})
+    cap, bits = graphs.measure_plan(m2, cams[:4], bg7)
+    step = graphs.GraphedStrandStep(m2, sink, bg7, H, W, cam.FoVx, cam.FoVy, cap, bits, dimage=w7.contiguous())
+    flat = lambda c: torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1), c.camera_center.reshape(-1)])  # noqa: E731
+    step.cam_buf[0].copy_(flat(cams[0]))
+    step.cam_buf[1].copy_(flat(cams[1]))
+    step.capture()
+    step.cam_buf[1].copy_(flat(cam))          # a view the graph was not captured on
+    step.replay(1)
+    step.check()
+    r2 = check("graph_replay", step.image[1], step.radii[1], {n: sink.tensors[k] for k, n in names.items()}, step.mean2d_grad[1])
+    os.makedirs(os.path.join(os.path.dirname(GOLD), "..", "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(GOLD), "..", "gpurun_out", "parity_cfg3_fused.json"), "w") as fh:
+        json.dump(report, fh, indent=1)
+    for tag, r in (("fused_eager", r1), ("graph_replay", r2)):
+        assert r["radius_flips"] <= 2e-5 * report["P"], (tag, r)
+        assert r["pixels_over_1e-4"] <= 2e-5 * report["pixel_values"], (tag, r)
+        assert r["pixel_max_abs"] < 0.05, (tag, r)
+        for n, v in r["grad_rel"].items():
+            assert v <= GRAD_TOL, (tag, n, v)
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE configs 3 and 5): size-independent invariants of the binning and the compositors
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("S,V,W,H", [(10000, 100, 1024, 1024), (40000, 101, 2048, 2048)], ids=["cfg3", "cfg5"])
 def test_full_size_properties(S, V, W, H):

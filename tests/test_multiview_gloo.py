@@ -106,3 +106,57 @@ def test_shard_views_cost_sorted():
     assert step0 == [5, 7, 8, 9] and step1 == [1, 2, 3, 4]
     with pytest.raises(ValueError):
         multiview.shard_views(3, 2, 0, costs=[1, 2])
+
+
+def _stats_worker(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hairgs_b200 import optim
+        P = 50
+        st = optim.DensifyStats(P, "cpu", distributed=True)
+        red = multiview.AsyncReducer(P * 3, "cpu")
+        flat = torch.zeros(P * 3)
+        for rnd in range(2):                              # two densification intervals
+            for view in range(rank, 6, world):            # this rank's views of the interval
+                g = torch.Generator().manual_seed(100 * rnd + view)
+                radii = torch.randint(0, 30, (P,), generator=g).float() * (torch.rand(P, generator=g) < 0.7)
+                grad = torch.randn(P, 3, generator=g)
+                vis = radii > 0
+                # what hgs_densify_stats does on the device (scene/gaussian_model.py:675-682), into the LOCAL buffers
+                st.local_max_radii2D[vis] = torch.max(st.local_max_radii2D[vis], radii[vis])
+                st.local_xyz_gradient_accum[vis] += torch.norm(grad[vis, :2], dim=-1, keepdim=True)
+                st.local_denom[vis] += 1
+                flat += grad.reshape(-1)
+            st.reduce()
+        summed = red.launch(flat).wait().clone()
+        if rank == 0:
+            torch.save((st.max_radii2D, st.xyz_gradient_accum, st.denom, summed), out_path)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_densify_stats_and_async_reducer_across_ranks(tmp_path, world):
+    """densification statistics are per-view nonlinear reductions -> accumulated locally, folded with
+    (sum, sum, max) across ranks on densification iterations; the gradient bucket goes through the side-stream reducer.
+    Both must equal the single-process result over all views."""
+    out = str(tmp_path / "stats.pt")
+    mp.spawn(_stats_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mr, acc, den, summed = torch.load(out)
+    P = 50
+    rmr, racc, rden, rflat = torch.zeros(P), torch.zeros(P, 1), torch.zeros(P, 1), torch.zeros(P * 3)
+    for rnd in range(2):
+        for view in range(6):
+            g = torch.Generator().manual_seed(100 * rnd + view)
+            radii = torch.randint(0, 30, (P,), generator=g).float() * (torch.rand(P, generator=g) < 0.7)
+            grad = torch.randn(P, 3, generator=g)
+            vis = radii > 0
+            rmr[vis] = torch.max(rmr[vis], radii[vis])
+            racc[vis] += torch.norm(grad[vis, :2], dim=-1, keepdim=True)
+            rden[vis] += 1
+            rflat += grad.reshape(-1)
+    assert torch.equal(mr, rmr) and torch.equal(den, rden)
+    assert torch.allclose(acc, racc, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(summed, rflat, rtol=1e-5, atol=1e-6)

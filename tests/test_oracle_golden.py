@@ -10,7 +10,7 @@ import pytest
 from oracle import pyoracle
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz")) if "knn" not in p and "loss_ref" not in p)
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz")) if "knn" not in p and "loss_ref" not in p and "pyref" not in p)
 
 
 def load(name):
