@@ -931,13 +931,14 @@ def parity_block(h, cfg, first, dL_np, can_fuse):
     fused = {"pixels_over_1e-4": int((diff > 1e-4).sum()), "pixel_max_abs": float(diff.max()),
              "radius_flips": int((radii7.cpu().numpy() != first["sh"]["radii"]).sum()), "pixels_total": int(diff.size)}
     # parameter gradients: the oracle's per-Gaussian gradients pulled back to the raw strand parameters by autograd
-    # through the torch getters (the chain the drop-in path runs)
+    # through the torch getters (the chain the drop-in path runs) - in float64, so that the yardstick is the chain rule
+    # itself and not the float32 rounding of the quaternion route (1/(1 + x.d) is ill-conditioned for segments near -x)
     from hairgs_b200 import models as _models
     scenes, _ = host_helpers()
     m2 = _models.StrandModel(scenes.StrandScene(m._endpoints.detach(), m.endpoint_pairs, m._width.detach(), m._opacity.detach(),
                                                 m._mask.detach(), m._features_dc.detach(), m._features_rest.detach(), 0),
-                             sh_degree=cfg["D"]).to(dev)
-    t = lambda a: torch.tensor(a, device=dev)  # noqa: E731
+                             sh_degree=cfg["D"]).to(dev).double()
+    t = lambda a: torch.tensor(a, device=dev, dtype=torch.float64)  # noqa: E731
     tot = 0.0
     for s in cfg["sets"]:
         gr = first[s]["grads"]
@@ -951,7 +952,8 @@ def parity_block(h, cfg, first, dL_np, can_fuse):
             tot = tot + (m2.get_orientation * t(gr["dL_dcolors"])).sum()
     tot.backward()
     ref = {n: p.grad for n, p in m2.named_parameters() if p.numel() > 0 and p.grad is not None}
-    fused["grad_rel"] = {n: round(rel(got[n].cpu().numpy(), ref[n].cpu().numpy()), 8) for n in ref if n in got}
+    fused["grad_rel"] = {n: round(rel(got[n].double().cpu().numpy(), ref[n].cpu().numpy()), 8) for n in ref if n in got}
+    fused["grad_reference"] = "CPU-oracle per-Gaussian gradients pulled back through the strand getters in float64"
     fused["grad_rel_max"] = max(fused["grad_rel"].values()) if fused["grad_rel"] else None
     # N2's stated tolerance: the closed-form covariance and the quaternion route may round a radius differently on a
     # handful of Gaussians (<= 1e-5 of them), which moves single pixels; everything else within the north_star bounds
@@ -1036,13 +1038,19 @@ def run_reference(args, cfg, config, need_flush):
     """Rank 0 alone (the reference is single-GPU, utils/general.py:116)."""
     import torch
     from oracle import ref_python
-    have = torch.cuda.is_available() and ref_python.available() and \
-        os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_dgr_C", "ref_dgr_C.so"))
-    if not have:
+    why = None
+    if not torch.cuda.is_available():
+        why = "no CUDA device"
+    elif not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_dgr_C", "ref_dgr_C.so")):
+        why = "oracle/_ref/ref_dgr_C/ref_dgr_C.so (the reference's CUDA rasterizer) is not built"
+    elif not ref_python.available():
+        why = "oracle/_ref/pyref (the reference's compiled Python) is not built"
+    if why is not None:
         # CPU port of the path on all host cores, bounded sample per step
         sys.path.insert(0, PKG)
         vps, cores, dt = cpu_port_views_per_s(cfg, max(1, min(args.steps, args.cpu_sample_views)))
         return dict(base_line(args, cfg, config, 1), impl="reference", value=vps, ms_per_step=1000.0 / vps,
+                    fallback=f"CPU port timed instead of the reference build: {why}",
                     cpu_baseline={"value": vps, "unit": "views/s", "cores": cores, "kind": "port",
                                   "sample": f"{args.cpu_sample_views} view(s) of {args.workload}, all colour sets, fwd+bwd"},
                     e2e={"value": vps, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0)

@@ -9,6 +9,9 @@
 //   (tile ranges are produced by finalize_sorted in composite_warp.cu)
 #include "hgs_common.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace hgs {
 
 // ------------------------------------------------------------------------------------------------
@@ -126,10 +129,27 @@ __global__ void __launch_bounds__(256) radix_histogram_kernel(const uint64_t* __
     __shared__ uint32_t s_hist[kMaxPasses * kRadix];
     for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
+    // Keys arrive in emission order: neighbouring lanes hold instances of the same or adjacent Gaussians, so the digits
+    // made of tile bits are (nearly) identical across a warp and a plain shared-memory atomic per lane would serialise 32
+    // ways on one address (it made this kernel 20 us on cfg3).  Runs of equal digits in adjacent lanes are counted once:
+    // the first lane of a run adds the run's length.  Random (depth) digits form 32 runs of one - no worse than before.
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint64_t k = xf(keys[i]);
-        for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p * kRadix + (uint32_t)((k >> (8 * p)) & 0xffu)], 1u);
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const uint32_t i = base + lane;
+        const bool valid = i < n;
+        const uint64_t k = valid ? xf(keys[i]) : 0ull;
+        for (int p = 0; p < passes; ++p) {
+            const uint32_t d = valid ? (uint32_t)((k >> (8 * p)) & 0xffu) : (0x100u + lane);
+            const uint32_t prev = __shfl_up_sync(0xffffffffu, d, 1);
+            const bool lead = lane == 0 || prev != d;
+            const uint32_t leaders = __ballot_sync(0xffffffffu, lead);
+            if (lead && valid) {
+                const uint32_t later = leaders & ~((2u << lane) - 1u);
+                const uint32_t end = later ? (uint32_t)__ffs(later) - 1u : 32u;
+                atomicAdd(&s_hist[p * kRadix + d], end - lane);
+            }
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) {
@@ -167,12 +187,17 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* tm
     return wex + incl - v;
 }
 
+// kBallot: how a key finds the lanes of its warp that hold the same digit.  false: one match.any per key - the round-1
+// kernel; on B200 the instruction runs on the SM's single ADU pipe at ~70 cycles per warp instruction, which made the pass
+// ADU-bound (75 % busy at 8 M pairs, 13 of 24 us at cfg3: profiles/r1_sort_8m.md, r2_sort.md).  true: nbits warp votes
+// (one per digit bit, intersected) - ~3 issue slots per bit on the ALU / vote path, ~25x less pipe time per key.
+template <bool kBallot>
 __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
     const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, uint32_t cap, const uint32_t* __restrict__ n_ptr, int shift,
     const uint32_t* __restrict__ ghist /*[256]*/,
     uint32_t* __restrict__ status /*[ntiles*256]*/, uint32_t* __restrict__ group /*[ngroups*256]*/, int group_shift,
-    uint32_t* __restrict__ ticket, const GeomHeader* range_hdr, int rb) {
+    uint32_t* __restrict__ ticket, const GeomHeader* range_hdr, int rb, int nbits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
 
@@ -210,7 +235,20 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const uint32_t d = (uint32_t)(xf(key[r]) >> shift) & 0xffu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t peers;
+        if (kBallot) {
+            peers = 0xffffffffu;
+#pragma unroll
+            for (int b = 0; b < kRadixBits; ++b) {
+                if (b < nbits) {  // the top digit of a key may have fewer than 8 significant bits
+                    const bool bit = (d >> b) & 1u;
+                    const uint32_t m = __ballot_sync(0xffffffffu, bit);
+                    peers &= bit ? m : ~m;
+                }
+            }
+        } else {
+            peers = __match_any_sync(0xffffffffu, d);
+        }
         const uint32_t lrank = __popc(peers & lt_mask);
         const int leader = __ffs(peers) - 1;
         uint32_t old = 0;
@@ -343,9 +381,14 @@ int launch_sort_pairs(int64_t n, const uint32_t* n_ptr, int end_bit, uint64_t* k
     const size_t clear = (size_t)((char*)L.status - (char*)L.hist) + (size_t)passes * L.ntiles * kRadix * 4;
     if (int e = check_cuda(cudaMemsetAsync(L.hist, 0, clear, s), "memset sort ws")) return e;
     static std::atomic<unsigned long long> attr_done{0};  // function attributes are per device
-    if (first_call_on_device(attr_done))
-        if (int e = check_cuda(cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (first_call_on_device(attr_done)) {
+        if (int e = check_cuda(cudaFuncSetAttribute(onesweep_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)sizeof(OnesweepSmem)), "onesweep smem attr")) return e;
+        if (int e = check_cuda(cudaFuncSetAttribute(onesweep_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)sizeof(OnesweepSmem)), "onesweep smem attr")) return e;
+    }
+    // HGS_SORT_RANK=match selects the round-1 match.any ranking (A/B measurements); default: warp votes
+    static const bool use_ballot = [] { const char* e = getenv("HGS_SORT_RANK"); return !(e != nullptr && strcmp(e, "match") == 0); }();
     const uint32_t nn = (uint32_t)n;
     int64_t hb = (n + 256 * 8 - 1) / (256 * 8);
     const int hblocks = (int)(hb < 148 * 8 ? hb : 148 * 8);
@@ -357,10 +400,12 @@ int launch_sort_pairs(int64_t n, const uint32_t* n_ptr, int end_bit, uint64_t* k
     int cur = start_buf & 1;
     for (int p = 0; p < passes; ++p) {
         StageScope prof(HGS_STAGE_SORT_ONESWEEP, s);
-        onesweep_pass_kernel<<<(unsigned)L.ntiles, kSortThreads, sizeof(OnesweepSmem), s>>>(
+        const int nbits = min(kRadixBits, end_bit - 8 * p);
+        auto kern = use_ballot ? onesweep_pass_kernel<true> : onesweep_pass_kernel<false>;
+        kern<<<(unsigned)L.ntiles, kSortThreads, sizeof(OnesweepSmem), s>>>(
             keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], nn, n_ptr, 8 * p, L.hist + p * kRadix,
             L.status + (size_t)p * L.ntiles * kRadix, L.group + (size_t)p * L.ngroups * kRadix, L.group_shift, L.tickets + p,
-            range_hdr, depth_bits);
+            range_hdr, depth_bits, nbits);
         if (int e = check_cuda(cudaGetLastError(), "onesweep launch")) return e;
         cur ^= 1;
     }

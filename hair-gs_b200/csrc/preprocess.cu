@@ -101,27 +101,40 @@ __device__ __forceinline__ void store_quat(float* __restrict__ q, int i, const f
 
 // Sigma = (S R)^T (S R) from scale and raw (un-normalised) quaternion (forward.cu:118-152).
 __device__ __forceinline__ void cov3d_from_scale_rot(const float3 scale, float mod, const float4 rot, float* cov3D) {
-    M3 S;
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) S.m[c][q] = (c == q) ? 1.0f : 0.0f;
-    S.m[0][0] = mod * scale.x;
-    S.m[1][1] = mod * scale.y;
-    S.m[2][2] = mod * scale.z;
+    // Every rounding is spelled out with intrinsics (never re-contracted by the compiler): which products the reference
+    // build keeps as a rounded FMUL and which it fuses into an FMA was determined against that build (oracle/rast_oracle.c
+    // cov3d_from_scale_rot, pinned bit for bit by tests/golden).  Left to the compiler, the pattern depends on the kernel
+    // this function is inlined into, and forward, backward and the state viewer must agree on every bit of Sigma.
+    const float sx = __fmul_rn(mod, scale.x), sy = __fmul_rn(mod, scale.y), sz = __fmul_rn(mod, scale.z);
     const float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
-    M3 R;
-    R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z);       R.m[0][2] = 2.f * (x * z + r * y);
-    R.m[1][0] = 2.f * (x * y + r * z);       R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
-    R.m[2][0] = 2.f * (x * z - r * y);       R.m[2][1] = 2.f * (y * z + r * x);       R.m[2][2] = 1.f - 2.f * (x * x + y * y);
-    M3 Mx = m3_mul(S, R);
-    M3 Sigma = m3_mul(m3_transpose(Mx), Mx);
-    cov3D[0] = Sigma.m[0][0];
-    cov3D[1] = Sigma.m[0][1];
-    cov3D[2] = Sigma.m[0][2];
-    cov3D[3] = Sigma.m[1][1];
-    cov3D[4] = Sigma.m[1][2];
-    cov3D[5] = Sigma.m[2][2];
+    const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z), xz = __fmul_rn(x, z), rz = __fmul_rn(r, z), rx = __fmul_rn(r, x);
+    float R[3][3];  // R[c][r], column-major as glm
+    R[0][0] = __fmaf_rn(-2.f, __fadd_rn(yy, zz), 1.f);
+    R[0][1] = __fmul_rn(2.f, __fmaf_rn(x, y, -rz));
+    R[0][2] = __fmul_rn(2.f, __fmaf_rn(r, y, xz));
+    R[1][0] = __fmul_rn(2.f, __fmaf_rn(x, y, rz));
+    R[1][1] = __fmaf_rn(-2.f, __fmaf_rn(x, x, zz), 1.f);
+    R[1][2] = __fmul_rn(2.f, __fmaf_rn(y, z, -rx));
+    R[2][0] = __fmul_rn(2.f, __fmaf_rn(-r, y, xz));
+    R[2][1] = __fmul_rn(2.f, __fmaf_rn(y, z, rx));
+    R[2][2] = __fmaf_rn(-2.f, __fmaf_rn(x, x, yy), 1.f);
+    float M[3][3];  // M = S R : M[c][r] = s_r R[c][r]
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        M[c][0] = __fmul_rn(sx, R[c][0]);
+        M[c][1] = __fmul_rn(sy, R[c][1]);
+        M[c][2] = __fmul_rn(sz, R[c][2]);
+    }
+    // Sigma = M^T M : Sigma[c][r] = M[r][0] M[c][0] + M[r][1] M[c][1] + M[r][2] M[c][2], contracted left to right
+    auto sig = [&](int c, int q) {
+        return __fmaf_rn(M[q][2], M[c][2], __fmaf_rn(M[q][0], M[c][0], __fmul_rn(M[q][1], M[c][1])));
+    };
+    cov3D[0] = sig(0, 0);
+    cov3D[1] = sig(0, 1);
+    cov3D[2] = sig(0, 2);
+    cov3D[3] = sig(1, 1);
+    cov3D[4] = sig(1, 2);
+    cov3D[5] = sig(2, 2);
 }
 
 // EWA projection of a 3D covariance (forward.cu:74-113).  Returns (xx, xy, yy) with the 0.3 low-pass.

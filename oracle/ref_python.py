@@ -3,8 +3,9 @@ as the `bench.py --impl reference` arm.  Never imported by anything under hair-g
 
 /root/reference does not exist on the GPU box and reference sources must not be copied into this repository, so —
 exactly like the CUDA sources that oracle/build_ref.py compiles into oracle/_ref/*.so — the reference's Python
-modules are COMPILED where they lie (py_compile -> sourceless byte code) into oracle/_ref/pyref/ (git-ignored,
-shipped to the box).  Modules compiled (reference paths):
+modules are COMPILED where they lie (compile() -> marshalled code objects, one `<module>.hgsref` file each) into
+oracle/_ref/pyref/ (git-ignored, shipped to the box) and imported through a private meta-path finder.  Modules compiled
+(reference paths):
 
     submodules/diff-gaussian-rasterization/diff_gaussian_rasterization/__init__.py   autograd surface (A2-A4)
     gaussian_renderer/__init__.py                                                    render() (A1)
@@ -25,9 +26,10 @@ load() leaves sys.modules as it found it (the reference's package names collide 
 packages and the reference can live in one test process.
 """
 import importlib
+import importlib.abc
 import importlib.util
+import marshal
 import os
-import py_compile
 import sys
 import types
 
@@ -36,6 +38,8 @@ ROOT = os.path.dirname(HERE)
 PYREF = os.path.join(HERE, "_ref", "pyref")
 REF = os.environ.get("HAIRGS_REFERENCE", "/root/reference")
 
+EXT = ".hgsref"
+MAGIC = b"HGSREF" + bytes(sys.version_info[:2]) + importlib.util.MAGIC_NUMBER
 MODULES = {
     "diff_gaussian_rasterization/__init__": "submodules/diff-gaussian-rasterization/diff_gaussian_rasterization/__init__.py",
     "gaussian_renderer/__init__": "gaussian_renderer/__init__.py",
@@ -62,19 +66,53 @@ def build(verbose=False):
         print(f"[oracle/_ref/pyref] reference not present at {REF}; using prebuilt byte code if any")
         return available()
     for dst, src in MODULES.items():
-        out = os.path.join(PYREF, dst + ".pyc")
+        out = os.path.join(PYREF, dst + EXT)
         os.makedirs(os.path.dirname(out), exist_ok=True)
         srcp = os.path.join(REF, src)
         if os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(srcp):
             continue
-        py_compile.compile(srcp, cfile=out, dfile=f"<reference>/{src}", doraise=True, optimize=0)
+        with open(srcp, "rb") as fh:
+            code = compile(fh.read(), f"<reference>/{src}", "exec", dont_inherit=True, optimize=0)
+        with open(out, "wb") as fh:
+            fh.write(MAGIC + marshal.dumps(code))
         if verbose:
             print(f"[oracle/_ref/pyref] {src} -> {os.path.relpath(out, ROOT)}")
     return True
 
 
 def available():
-    return all(os.path.exists(os.path.join(PYREF, d + ".pyc")) for d in MODULES)
+    return all(os.path.exists(os.path.join(PYREF, d + EXT)) for d in MODULES)
+
+
+class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """Imports the compiled reference modules by name while load() runs (first on sys.meta_path, removed afterwards)."""
+
+    def __init__(self):
+        self.table = {}
+        for dst in MODULES:
+            name = dst.replace("/", ".")
+            pkg = name.endswith(".__init__")
+            self.table[name[:-len(".__init__")] if pkg else name] = (os.path.join(PYREF, dst + EXT), pkg)
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname not in self.table:
+            return None
+        file, pkg = self.table[fullname]
+        spec = importlib.util.spec_from_loader(fullname, self, origin=file, is_package=pkg)
+        if pkg:
+            spec.submodule_search_locations = [os.path.dirname(file)]
+        return spec
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        file, _ = self.table[module.__name__]
+        with open(file, "rb") as fh:
+            blob = fh.read()
+        if blob[:len(MAGIC)] != MAGIC:
+            raise ImportError(f"{file}: compiled by another Python ({sys.version_info[:2]} needed); rebuild oracle/_ref/pyref")
+        exec(marshal.loads(blob[len(MAGIC):]), module.__dict__)
 
 
 def _stub(name, **attrs):
@@ -123,7 +161,8 @@ def load(with_cuda_ext=True):
     saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in _COLLIDING}
     for k in saved:
         del sys.modules[k]
-    saved_path = list(sys.path)
+    finder = _Finder()
+    sys.meta_path.insert(0, finder)
     try:
         os.environ.setdefault("BW_IMPLEMENTATION", "1")   # train.py:278 -> utils/general.py:119-124
         os.environ.setdefault("BALANCE_THRESHOLD", "8")
@@ -149,7 +188,6 @@ def load(with_cuda_ext=True):
             m = _stub(pkg)
             m.__path__ = [os.path.join(PYREF, pkg)]
             sys.modules[pkg] = m
-        sys.path.insert(0, PYREF)
         utils = sys.modules["utils"]
         for sub in _UTILS_SUBMODULES:      # what utils/__init__.py star-imports, minus the viewer / dataset modules
             mod = importlib.import_module("utils." + sub)
@@ -180,7 +218,7 @@ def load(with_cuda_ext=True):
         ns.arguments = importlib.import_module("arguments")
         ns.matrix_to_quaternion_stub = scenes.matrix_to_quaternion
     finally:
-        sys.path[:] = saved_path
+        sys.meta_path.remove(finder)
         for k in [k for k in sys.modules if k.split(".")[0] in _COLLIDING]:
             del sys.modules[k]
         sys.modules.update(saved)

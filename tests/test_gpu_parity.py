@@ -453,10 +453,54 @@ def _ref_three_pass(sc, cam, bg7, w7, D):
     return img, r_rgb["radii"], {n: p.grad.clone() for n, p in params.items() if p.grad is not None}, vs, how
 
 
+def _ref_three_pass_fp64_chain(sc, cam, bg7, w7, D):
+    """The same three reference passes, but only the reference's CUDA kernels run in float32: their per-Gaussian gradients
+    (dL/dmeans3D, dL/dscales, dL/drotations, dL/dopacity, dL/dsh, dL/dcolors) are pulled back to the raw strand parameters
+    through the getters in FLOAT64.  This is the yardstick for the parameter gradients: the float32 autograd of the
+    quaternion route (R = I + K + K^2/(1 + x.d), matrix_to_quaternion) loses digits for segments pointing near -x, which is
+    rounding noise of the reference's glue, not signal."""
+    from hairgs_b200 import models
+    C = need_ref()
+    m32 = models.StrandModel(sc, sh_degree=D).to(dev())
+    m64 = models.StrandModel(sc, sh_degree=D).to(dev()).double()
+    E = common.EMPTY()
+    tot = 0.0
+    with torch.no_grad():
+        base = dict(means3D=m32.get_xyz.contiguous(), opacity=m32.get_opacity.contiguous(), scales=m32.get_scaling.contiguous(),
+                    rotations=m32.get_rotation.contiguous(), sh=m32.get_features.contiguous())
+        cols = {"sh": None, "mask": m32.get_mask.repeat(1, 3).contiguous(), "orientation": m32.get_orientation.contiguous()}
+    sl = {"sh": slice(0, 3), "mask": slice(3, 4), "orientation": slice(4, 7)}
+    for s, col in cols.items():
+        bg = bg7[sl[s]] if s != "mask" else bg7[3:4].repeat(3)
+        dL = w7[sl[s]] if s != "mask" else torch.cat([w7[3:4], torch.zeros_like(w7[0:2])])
+        sh = base["sh"] if col is None else E
+        colors = E if col is None else col
+        N, color, radii, geom, binning, img = C.rasterize_gaussians(
+            bg.contiguous(), base["means3D"], colors, base["opacity"], base["scales"], base["rotations"], 1.0, E,
+            cam.world_view_transform, cam.full_proj_transform, cam.tanfovx, cam.tanfovy, cam.image_height, cam.image_width, sh, D,
+            cam.camera_center, False, False)
+        g2d, gcol, gop, gm3, gcov, gsh, gsc, grot = C.rasterize_gaussians_backward(
+            bg.contiguous(), base["means3D"], radii, colors, base["scales"], base["rotations"], 1.0, E, cam.world_view_transform,
+            cam.full_proj_transform, cam.tanfovx, cam.tanfovy, dL.contiguous(), sh, D, cam.camera_center, geom, N, binning, img, False)
+        d = lambda t: t.double()  # noqa: E731
+        tot = tot + (m64.get_xyz * d(gm3)).sum() + (m64.get_scaling * d(gsc)).sum() + (m64.get_rotation * d(grot)).sum() \
+            + (m64.get_opacity * d(gop)).sum()
+        if s == "sh":
+            tot = tot + (m64.get_features * d(gsh)).sum()
+        elif s == "mask":
+            tot = tot + (m64.get_mask.repeat(1, 3) * d(gcol)).sum()
+        else:
+            tot = tot + (m64.get_orientation * d(gcol)).sum()
+    tot.backward()
+    return {n: p.grad for n, p in m64.named_parameters() if p.numel() and p.grad is not None}
+
+
 def test_fused_and_graph_replay_vs_reference_three_pass_cfg3():
     """The path bench.py's headline is measured on — fused strand pass, eager and as a CUDA-graph replay — at FULL cfg3 size
     against the reference's three passes.  Reported and asserted: radius flips, pixels over 1e-4, max-abs pixel error,
-    gradient rel errors.  Bounds: the closed-form covariance of the strand entry and the reference's quaternion route
+    gradient rel errors (parameter gradients against the float64 pull-back of the reference CUDA's per-Gaussian gradients,
+    see _ref_three_pass_fp64_chain; the float32-chain numbers and the reference's own float32-vs-float64 discrepancy are
+    written to the report).  Bounds: the closed-form covariance of the strand entry and the reference's quaternion route
     round differently in the last bit, which can move a radius by one and flip an alpha >= 1/255 test on isolated
     (pixel, Gaussian) pairs: <= 2e-5 of the Gaussians / pixel values; everything else within the north_star tolerances."""
     import json
@@ -469,14 +513,17 @@ def test_fused_and_graph_replay_vs_reference_three_pass_cfg3():
     w7 = torch.randn(7, H, W, device=dev()) / (H * W)
     bg7 = torch.zeros(7, device=dev())
     ref_img, ref_radii, ref_g, ref_vs, how = _ref_three_pass(sc, cam, bg7, w7, 0)
+    ref_g64 = _ref_three_pass_fp64_chain(sc, cam, bg7, w7, 0)
     names = {"endpoints": "_endpoints", "width": "_width", "opacity": "_opacity", "mask": "_mask", "features": "_features_dc"}
-    report = {"reference": how, "P": int(sc.endpoint_pairs.shape[0]), "pixel_values": int(ref_img.numel())}
+    report = {"reference": how, "P": int(sc.endpoint_pairs.shape[0]), "pixel_values": int(ref_img.numel()),
+              "reference_fp32_chain_vs_fp64_chain": {n: common.rel_err(ref_g[n].double(), ref_g64[n]) for n in ref_g if n in ref_g64}}
 
     def check(tag, img, radii, grads, vs):
         diff = (img - ref_img).abs()
         r = {"radius_flips": int((radii != ref_radii).sum()), "pixels_over_1e-4": int((diff > PIX_TOL).sum()),
              "pixel_max_abs": float(diff.max()),
-             "grad_rel": {n: common.rel_err(grads[n], ref_g[n]) for n in ref_g if n in grads}}
+             "grad_rel": {n: common.rel_err(grads[n].double(), ref_g64[n]) for n in ref_g64 if n in grads},
+             "grad_rel_vs_fp32_chain": {n: common.rel_err(grads[n], ref_g[n]) for n in ref_g if n in grads}}
         if vs is not None:
             r["grad_rel"]["viewspace_points"] = common.rel_err(vs, ref_vs)
         report[tag] = r
