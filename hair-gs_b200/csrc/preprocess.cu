@@ -102,8 +102,8 @@ __device__ __forceinline__ void store_quat(float* __restrict__ q, int i, const f
 // Sigma = (S R)^T (S R) from scale and raw (un-normalised) quaternion (forward.cu:118-152).
 __device__ __forceinline__ void cov3d_from_scale_rot(const float3 scale, float mod, const float4 rot, float* cov3D) {
     // Every rounding is spelled out with intrinsics (never re-contracted by the compiler): which products the reference
-    // build keeps as a rounded FMUL and which it fuses into an FMA was determined against that build (oracle/rast_oracle.c
-    // cov3d_from_scale_rot, pinned bit for bit by tests/golden).  Left to the compiler, the pattern depends on the kernel
+    // build keeps as a rounded FMUL and which it fuses into an FMA was determined against that build and is pinned bit for
+    // bit by the recorded fixtures under tests/golden.  Left to the compiler, the pattern depends on the kernel
     // this function is inlined into, and forward, backward and the state viewer must agree on every bit of Sigma.
     const float sx = __fmul_rn(mod, scale.x), sy = __fmul_rn(mod, scale.y), sz = __fmul_rn(mod, scale.z);
     const float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
