@@ -72,6 +72,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager path only (no CUDA-graph replay)")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--graph-mode", default="batch", choices=["batch", "view"],
+                    help="batch: the views of a step as ONE two-branch CUDA graph (binning of view k+1 under the compositing of "
+                         "view k, graphs.GraphedStrandBatch); view: one graph per view (graphs.GraphedStrandStep)")
     ap.add_argument("--cpu-sample-views", type=int, default=6)
     ap.add_argument("--views-per-step", type=int, default=8,
                     help="views each rank renders per step (one gradient all-reduce / optimiser step per step); "
@@ -240,6 +243,7 @@ class Harness:
         import torch
         self.torch, self.cfg, self.dev, self.C, self.world, self.rank = torch, cfg, dev, backend, world, rank
         self.vps = max(1, int(args.views_per_step))
+        self.graph_mode = args.graph_mode
         self.model, self.cams = build_workload(cfg, dev, n_cameras(cfg, args))
         from hairgs_b200 import multiview
         self.multiview = multiview
@@ -335,17 +339,31 @@ class Harness:
     def setup_fused_graph(self):
         """The resident fused step as a CUDA-graph replay (hairgs_b200.graphs, dL/dimage given): same kernels."""
         torch = self.torch
-        self.fgraph, self.fgraph_note = None, None
+        self.fgraph, self.fgraph_note, self.fbatch = None, None, None
         if self.fsink is None:
             return
         try:
             from hairgs_b200 import graphs
             mine = [self.cams[v] for v in self.my_views]
             cap, bits = graphs.measure_plan(self.model, mine, self.bg7)
-            g = graphs.GraphedStrandStep(self.model, self.fsink, self.bg7, self.cfg["H"], self.cfg["W"], mine[0].FoVx,
-                                         mine[0].FoVy, cap, bits, dimage=self.dL7.contiguous())
             self.cam_flat = [torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1),
                                         c.camera_center.reshape(-1)]).contiguous() for c in mine]
+            if self.graph_mode == "batch" and self.vps > 1:
+                b = graphs.GraphedStrandBatch(self.model, self.fsink, self.bg7, self.cfg["H"], self.cfg["W"], mine[0].FoVx,
+                                              mine[0].FoVy, cap, bits, self.vps, dimage=self.dL7.contiguous())
+                self.cam_all = torch.stack(self.cam_flat)
+                self.cam_idx = [torch.tensor([(i * self.vps + k) % len(mine) for k in range(self.vps)], device=self.dev)
+                                for i in range(max(1, len(mine) // math.gcd(len(mine), self.vps)))]
+                b.cam_buf.copy_(self.cam_all[self.cam_idx[0]])
+                torch.cuda.synchronize(self.dev)
+                b.capture()
+                self.fbatch = b
+                self.fgraph = b
+                self.fgraph_note = (f"ONE two-branch CUDA graph per {self.vps}-view step (binning of view k+1 under the compositing "
+                                    f"of view k), plan: capacity {cap} instances, {bits} depth bits")
+                return
+            g = graphs.GraphedStrandStep(self.model, self.fsink, self.bg7, self.cfg["H"], self.cfg["W"], mine[0].FoVx,
+                                         mine[0].FoVy, cap, bits, dimage=self.dL7.contiguous())
             for slot in range(2):
                 g.cam_buf[slot].copy_(self.cam_flat[slot % len(mine)])
             torch.cuda.synchronize(self.dev)
@@ -357,6 +375,13 @@ class Harness:
             torch.cuda.synchronize(self.dev)
 
     def step_resident_fused_graph(self, it):
+        if self.fbatch is not None:
+            # the step's cameras are resident; V x 140 bytes device-to-device into the graph's input rows, ONE launch
+            self.fbatch.cam_buf.copy_(self.cam_all[self.cam_idx[it % len(self.cam_idx)]])
+            self.fbatch.replay(accumulate=False)
+            if self.freducer is not None:
+                self.freducer.launch(self.fbucket.flat)
+            return
         for k in range(self.vps):
             vi = it * self.vps + k
             slot = vi % 2
@@ -397,7 +422,7 @@ class Harness:
         torch = self.torch
         self.fused = fused
         self.opt_mode = optimizer
-        self.graphed, self.graph_note = None, None
+        self.graphed, self.graph_note, self.ebatch = None, None, None
         if fused:
             from hairgs_b200 import fused as fused_mod
             from hairgs_b200 import losses
@@ -457,11 +482,39 @@ class Harness:
         if not (graph and self.fused and self.hair_loss and self.esink is not None):
             return
         torch = self.torch
+        self.ebatch = None
         try:
             from hairgs_b200 import graphs
             mine = [self.cams[v] for v in self.my_views]
             cap, bits = graphs.measure_plan(self.model, mine, self.bg7)
             c0 = mine[0]
+            if self.graph_mode == "batch" and self.vps > 1:
+                # the step's views as ONE two-branch graph; two input sets so that the copy stream fills the next step's
+                # cameras / targets while this step's graph runs
+                V, H, W = self.vps, self.cfg["H"], self.cfg["W"]
+                if not hasattr(self, "tgt_sets"):
+                    self.tgt_sets = [torch.empty(V, 6, H, W, device=self.dev) for _ in range(2)]
+                    self.cam_sets = [torch.empty(V, 35, device=self.dev) for _ in range(2)]
+                    self.set_ready = [torch.cuda.Event() for _ in range(2)]
+                    self.set_free = [torch.cuda.Event() for _ in range(2)]
+                    self.losses_host = torch.zeros(V).pin_memory()
+                batches = []
+                for k in range(2):
+                    for v in range(V):
+                        idx = (k * V + v) % len(self.my_views)
+                        self.tgt_sets[k][v].copy_(self.targets_host[idx])
+                        self.cam_sets[k][v].copy_(self.cam_host[idx])
+                    torch.cuda.synchronize(self.dev)
+                    b = graphs.GraphedStrandBatch(self.model, self.esink, self.bg7, H, W, c0.FoVx, c0.FoVy, cap, bits, V,
+                                                  lambdas=LOSS_LAMBDAS, cam_buf=self.cam_sets[k], tgt_buf=self.tgt_sets[k])
+                    b.capture(accumulate_variant=False)
+                    batches.append(b)
+                self.ebatch = batches
+                self.graphed = batches[0]
+                self._batch_prefetched = -1
+                self.graph_note = (f"ONE two-branch CUDA graph per {V}-view step and input set (binning of view k+1 under the "
+                                   f"compositing of view k), plan: capacity {cap} instances, {bits} depth bits")
+                return
             g = graphs.GraphedStrandStep(self.model, self.esink, self.bg7, self.cfg["H"], self.cfg["W"], c0.FoVx, c0.FoVy,
                                          cap, bits, lambdas=LOSS_LAMBDAS, cam_buf=self.cam_dev, tgt_buf=self.tgt_dev)
             for slot in range(2):  # a real view in every slot before the warm-up / capture
@@ -473,9 +526,36 @@ class Harness:
             self.graphed = g
             self.graph_note = f"one CUDA graph per input slot, plan: capacity {cap} instances, {bits} depth bits"
         except Exception as e:  # stay measurable: fall back to the eager path and say so in the JSON line
-            self.graphed = None
+            self.graphed, self.ebatch = None, None
             self.graph_note = f"graph capture failed, eager path used: {type(e).__name__}: {e}"
             torch.cuda.synchronize(self.dev)
+
+    def _prefetch_batch(self, it):
+        """stage the V views of step `it` into input set it%2 on the copy stream."""
+        torch = self.torch
+        k, V = it % 2, self.vps
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.set_free[k])
+            for v in range(V):
+                idx = (it * V + v) % len(self.my_views)
+                self.tgt_sets[k][v].copy_(self.targets_host[idx], non_blocking=True)
+                self.cam_sets[k][v].copy_(self.cam_host[idx], non_blocking=True)
+            self.set_ready[k].record(self.copy_stream)
+        self._batch_prefetched = it
+
+    def _e2e_step_batch(self, it):
+        """H2D of the step's V cameras / target stacks (prefetched on the copy stream), ONE graph launch, D2H of the V losses."""
+        torch = self.torch
+        if self._batch_prefetched < it:
+            self._prefetch_batch(it)
+        k = it % 2
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self.set_ready[k])
+        if self._batch_prefetched < it + 1:
+            self._prefetch_batch(it + 1)     # the next step's copies overlap this step's kernels
+        losses = self.ebatch[k].replay(accumulate=False)
+        self.set_free[k].record(cur)
+        self.losses_host.copy_(losses, non_blocking=True)
 
     def _prefetch(self, it):
         """stage view `it` into slot it%2 on the copy stream (double-buffered data loader)."""
@@ -492,10 +572,15 @@ class Harness:
         """One step = views_per_step views (each: H2D of its camera/targets, render, loss, backward, D2H of the loss), then ONE
         gradient all-reduce and ONE optimiser step."""
         torch = self.torch
-        for k in range(self.vps):
-            self._e2e_view(it * self.vps + k, first=k == 0)
+        if getattr(self, "ebatch", None) is not None:
+            self._e2e_step_batch(it)
+        else:
+            for k in range(self.vps):
+                self._e2e_view(it * self.vps + k, first=k == 0)
         if self.opt_mode == "flat":
-            if self.graphed is not None:
+            if getattr(self, "ebatch", None) is not None:
+                self.ebatch[it % 2].validate()
+            elif self.graphed is not None:
                 self.graphed.validate()   # every view of the step fitted the captured plan, checked BEFORE the parameters move
             if self.world > 1:   # the optimiser needs the sum before it may move the parameters: no overlap possible
                 torch.distributed.all_reduce(self.opt.grads.flat)
@@ -908,9 +993,19 @@ def parity_block(h, cfg, first, dL_np, can_fuse):
     h.dL7.copy_(dL7)
     m = h.model
     try:
-        if getattr(h, "fgraph", None) is not None:
-            h.fgraph.cam_buf[0].copy_(torch.cat([cam.world_view_transform.reshape(-1), cam.full_proj_transform.reshape(-1),
-                                                 cam.camera_center.reshape(-1)]))
+        grad_div = 1.0
+        cam35 = torch.cat([cam.world_view_transform.reshape(-1), cam.full_proj_transform.reshape(-1), cam.camera_center.reshape(-1)])
+        if getattr(h, "fbatch", None) is not None:
+            # the batch graph renders V views per launch: all V input rows carry view 0, the batch gradient is V x the view's
+            h.fbatch.cam_buf.copy_(cam35[None].expand(h.fbatch.V, 35))
+            h.fbatch.replay(accumulate=False)
+            torch.cuda.synchronize(dev)
+            image7, radii7 = h.fbatch.image[h.fbatch.V - 1].clone(), h.fbatch.radii[h.fbatch.V - 1].clone()
+            grad_div = float(h.fbatch.V)
+            path = (f"CUDA-graph replay of the {h.fbatch.V}-view two-branch batch (hairgs_b200.graphs.GraphedStrandBatch), every "
+                    f"row = view 0, last view's image, batch gradient / {h.fbatch.V}")
+        elif getattr(h, "fgraph", None) is not None:
+            h.fgraph.cam_buf[0].copy_(cam35)
             h.fgraph.replay(0, accumulate=False)
             torch.cuda.synchronize(dev)
             image7, radii7 = h.fgraph.image[0].clone(), h.fgraph.radii[0].clone()
@@ -923,7 +1018,7 @@ def parity_block(h, cfg, first, dL_np, can_fuse):
             torch.cuda.synchronize(dev)
             image7, radii7 = o7["image7"].detach().clone(), o7["radii"].clone()
             path = "eager fused strand view (hairgs_b200.fused.render_strands)"
-        got = {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.numel() > 0 and p.grad is not None}
+        got = {n: p.grad.detach().clone() / grad_div for n, p in m.named_parameters() if p.numel() > 0 and p.grad is not None}
     finally:
         h.dL7.copy_(saved)
     ref_img = np.concatenate([first["sh"]["color"], first["mask"]["color"][0:1], first["orientation"]["color"]])
@@ -1170,7 +1265,8 @@ def run():
             if h.graphed is not None:
                 ms_e2e_eager = ms_e2e
                 ms_e2e, st_e2e = timed_loop(torch, h.step_e2e, args.steps, args.warmup, world, dev, flush, h.finish)
-                h.graphed.check()
+                for b in (h.ebatch or [h.graphed]):
+                    b.check()
             graph_note = h.graph_note
 
     # ---- per-stage device times (CUDA events recorded by the library on its launch stream) ----------
@@ -1220,7 +1316,8 @@ def run():
     h.setup_e2e(fused=can_fuse, optimizer="flat", graph=can_fuse and ms_e2e_eager is not None)
     ms_e2e_opt, _ = timed_loop(torch, h.step_e2e, args.steps, args.warmup, world, dev, flush, h.finish)
     if h.graphed is not None:
-        h.graphed.check()
+        for b in (h.ebatch or [h.graphed]):
+            b.check()
     clk = clocks.stop() if rank == 0 else None
 
     views = world * args.steps * h.vps

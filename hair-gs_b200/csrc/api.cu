@@ -194,29 +194,54 @@ int hgs_forward_read_num_rendered(const void* geom_ws, int32_t P, uint32_t* n_pi
                                       (cudaStream_t)stream), "read num_rendered");
 }
 
-// bin + sort + finalize + composite, shared by the generic and the strand entry
+// bin + sort + finalize (parts & 1) and composite (parts & 2), shared by the generic and the strand entry
 static int stage_b_impl(const hgs_raster_params* prm, const float* background, void* geom_ws, void* binning_ws,
-                        void* image_ws, int64_t N, float* out_color, cudaStream_t s) {
-    if (!geom_ws || !image_ws || (N > 0 && !binning_ws) || !out_color) { set_error("null workspace/output"); return HGS_ERR_INVALID; }
+                        void* image_ws, int64_t N, float* out_color, cudaStream_t s, int parts = 3) {
+    if (!geom_ws || !image_ws || (N > 0 && !binning_ws) || ((parts & 2) && !out_color)) { set_error("null workspace/output"); return HGS_ERR_INVALID; }
     if (N < 0 || N > 0x7fffffffll) { set_error("num_rendered out of range"); return HGS_ERR_OVERFLOW; }
     GeomLayout g = carve_geom(geom_ws, prm->P, prm->channels);
     ImageLayout im = carve_image(image_ws, prm->width, prm->height);
     BinningLayout b = carve_binning(binning_ws, N, prm->channels);
     const uint32_t gx = (prm->width + HGS_TILE - 1) / HGS_TILE, gy = (prm->height + HGS_TILE - 1) / HGS_TILE;
 
-    // the unsorted pairs go into the ping-pong buffer from which the sort's passes end in buffer 0, whatever their number
-    const int start = sort_passes(end_bit_for(prm)) & 1;
-    if (int e = launch_emit_keys(N > 0 ? prm->P : 0, g, g.rects, b.keys[start], b.vals[start], gx, (uint32_t)N, s)) return e;
-    if (int e = stage_check("emit_keys", prm->debug, s)) return e;
-    int res = 0;
-    const uint32_t* n_ptr = &g.hdr->num_rendered;  // live instance count stays on the device; N is only the capacity
-    if (int e = launch_sort_pairs(N, n_ptr, end_bit_for(prm), b.keys, b.vals, b.sort_ws, &res, s, g.hdr, depth_bits_for(prm),
-                                  start)) return e;
-    if (int e = stage_check("sort", prm->debug, s)) return e;
-    if (int e = launch_finalize_sorted(prm->channels, N, n_ptr, b.keys[res], b.vals[res], g, b, im.ranges, im.tile_order, (size_t)gx * gy, s)) return e;
-    if (int e = stage_check("finalize_sorted", prm->debug, s)) return e;
-    if (int e = launch_composite_fwd(prm->channels, im, b, prm->width, prm->height, background, out_color, s)) return e;
-    return stage_check("composite_fwd", prm->debug, s);
+    if (parts & 1) {
+        // the unsorted pairs go into the ping-pong buffer from which the sort's passes end in buffer 0, whatever their number
+        const int start = sort_passes(end_bit_for(prm)) & 1;
+        if (int e = launch_emit_keys(N > 0 ? prm->P : 0, g, g.rects, b.keys[start], b.vals[start], gx, (uint32_t)N, s)) return e;
+        if (int e = stage_check("emit_keys", prm->debug, s)) return e;
+        int res = 0;
+        const uint32_t* n_ptr = &g.hdr->num_rendered;  // live instance count stays on the device; N is only the capacity
+        if (int e = launch_sort_pairs(N, n_ptr, end_bit_for(prm), b.keys, b.vals, b.sort_ws, &res, s, g.hdr, depth_bits_for(prm),
+                                      start)) return e;
+        if (int e = stage_check("sort", prm->debug, s)) return e;
+        if (int e = launch_finalize_sorted(prm->channels, N, n_ptr, b.keys[res], b.vals[res], g, b, im.ranges, im.tile_order, (size_t)gx * gy, s)) return e;
+        if (int e = stage_check("finalize_sorted", prm->debug, s)) return e;
+    }
+    if (parts & 2) {
+        if (!background) { set_error("null background"); return HGS_ERR_INVALID; }
+        if (int e = launch_composite_fwd(prm->channels, im, b, prm->width, prm->height, background, out_color, s)) return e;
+        return stage_check("composite_fwd", prm->debug, s);
+    }
+    return HGS_OK;
+}
+
+static int validate_parts(const hgs_raster_params* prm) {
+    if (!prm) { set_error("null params"); return HGS_ERR_INVALID; }
+    if (prm->P < 0 || prm->width <= 0 || prm->height <= 0) { set_error("bad sizes P=%d W=%d H=%d", prm->P, prm->width, prm->height); return HGS_ERR_INVALID; }
+    if (prm->channels < 1 || prm->channels > HGS_MAX_CHANNELS) { set_error("channels must be 1..%d", HGS_MAX_CHANNELS); return HGS_ERR_INVALID; }
+    return HGS_OK;
+}
+
+int hgs_forward_stage_b_binning(const hgs_raster_params* prm, void* geom_ws, void* binning_ws, void* image_ws, int64_t N,
+                                void* stream) {
+    if (int e = validate_parts(prm)) return e;
+    return stage_b_impl(prm, nullptr, geom_ws, binning_ws, image_ws, N, nullptr, (cudaStream_t)stream, 1);
+}
+
+int hgs_forward_stage_b_composite(const hgs_raster_params* prm, const float* background, void* geom_ws, void* binning_ws,
+                                  void* image_ws, int64_t N, float* out_color, void* stream) {
+    if (int e = validate_parts(prm)) return e;
+    return stage_b_impl(prm, background, geom_ws, binning_ws, image_ws, N, out_color, (cudaStream_t)stream, 2);
 }
 
 int hgs_forward_stage_b(const hgs_raster_params* prm, const hgs_raster_inputs* in, void* geom_ws, void* binning_ws,

@@ -129,27 +129,10 @@ __global__ void __launch_bounds__(256) radix_histogram_kernel(const uint64_t* __
     __shared__ uint32_t s_hist[kMaxPasses * kRadix];
     for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    // Keys arrive in emission order: neighbouring lanes hold instances of the same or adjacent Gaussians, so the digits
-    // made of tile bits are (nearly) identical across a warp and a plain shared-memory atomic per lane would serialise 32
-    // ways on one address (it made this kernel 20 us on cfg3).  Runs of equal digits in adjacent lanes are counted once:
-    // the first lane of a run adds the run's length.  Random (depth) digits form 32 runs of one - no worse than before.
     const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t lane = threadIdx.x & 31;
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
-        const uint32_t i = base + lane;
-        const bool valid = i < n;
-        const uint64_t k = valid ? xf(keys[i]) : 0ull;
-        for (int p = 0; p < passes; ++p) {
-            const uint32_t d = valid ? (uint32_t)((k >> (8 * p)) & 0xffu) : (0x100u + lane);
-            const uint32_t prev = __shfl_up_sync(0xffffffffu, d, 1);
-            const bool lead = lane == 0 || prev != d;
-            const uint32_t leaders = __ballot_sync(0xffffffffu, lead);
-            if (lead && valid) {
-                const uint32_t later = leaders & ~((2u << lane) - 1u);
-                const uint32_t end = later ? (uint32_t)__ffs(later) - 1u : 32u;
-                atomicAdd(&s_hist[p * kRadix + d], end - lane);
-            }
-        }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t k = xf(keys[i]);
+        for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p * kRadix + (uint32_t)((k >> (8 * p)) & 0xffu)], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) {
@@ -187,10 +170,10 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* tm
     return wex + incl - v;
 }
 
-// kBallot: how a key finds the lanes of its warp that hold the same digit.  false: one match.any per key - the round-1
-// kernel; on B200 the instruction runs on the SM's single ADU pipe at ~70 cycles per warp instruction, which made the pass
-// ADU-bound (75 % busy at 8 M pairs, 13 of 24 us at cfg3: profiles/r1_sort_8m.md, r2_sort.md).  true: nbits warp votes
-// (one per digit bit, intersected) - ~3 issue slots per bit on the ALU / vote path, ~25x less pipe time per key.
+// kBallot: how a key finds the lanes of its warp that hold the same digit.  false: one match.any per key (~70 cycles of
+// the SM's single ADU pipe per warp instruction: the pass is ADU-bound, 75 % busy at 8 M pairs, profiles/r1_sort_8m.md).
+// true: nbits warp votes (one per digit bit, intersected), CUB's MatchAny.  Measured on B200 (profiles/r2_sort.md): the
+// votes go through the same pipe - 8 of them cost what one match.any costs, so the two variants time within 5 %.
 template <bool kBallot>
 __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
     const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
@@ -230,6 +213,9 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
     // __syncwarp between rounds, so the 16 rounds pipeline instead of serialising on LDS->STS round trips.
     // (Atomics of one warp to one address are performed in program order, which is what stability needs.)
     uint32_t rank[kSortItems];
+    // padding keys of the last, partial tile carry digit 0xff: all 8 bits are compared there so that they never pair up
+    // with a real top digit whose low nbits happen to be all ones
+    const int nb = (nvalid < (uint32_t)kSortTile) ? kRadixBits : nbits;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t* wh = sm.warp_hist[warp];
 #pragma unroll
@@ -240,7 +226,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
             peers = 0xffffffffu;
 #pragma unroll
             for (int b = 0; b < kRadixBits; ++b) {
-                if (b < nbits) {  // the top digit of a key may have fewer than 8 significant bits
+                if (b < nb) {  // the top digit of a key may have fewer than 8 significant bits
                     const bool bit = (d >> b) & 1u;
                     const uint32_t m = __ballot_sync(0xffffffffu, bit);
                     peers &= bit ? m : ~m;
@@ -387,11 +373,14 @@ int launch_sort_pairs(int64_t n, const uint32_t* n_ptr, int end_bit, uint64_t* k
         if (int e = check_cuda(cudaFuncSetAttribute(onesweep_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)sizeof(OnesweepSmem)), "onesweep smem attr")) return e;
     }
-    // HGS_SORT_RANK=match selects the round-1 match.any ranking (A/B measurements); default: warp votes
-    static const bool use_ballot = [] { const char* e = getenv("HGS_SORT_RANK"); return !(e != nullptr && strcmp(e, "match") == 0); }();
+    // HGS_SORT_RANK=ballot selects the warp-vote ranking (A/B measurements, profiles/r2_sort.md: both variants are bound
+    // by the same pipe on B200 and time within 5 % of each other; match.any issues fewer instructions)
+    static const bool use_ballot = [] { const char* e = getenv("HGS_SORT_RANK"); return e != nullptr && strcmp(e, "ballot") == 0; }();
     const uint32_t nn = (uint32_t)n;
+    // two blocks per SM: every block ends with up to passes x 256 global atomics on the SAME 1280 words, and same-address
+    // atomics serialise in L2 - with 8 blocks per SM that flush, not the key traffic, was most of the kernel
     int64_t hb = (n + 256 * 8 - 1) / (256 * 8);
-    const int hblocks = (int)(hb < 148 * 8 ? hb : 148 * 8);
+    const int hblocks = (int)(hb < 148 * 2 ? hb : 148 * 2);
     {
         StageScope prof(HGS_STAGE_SORT_HISTOGRAM, s);
         radix_histogram_kernel<<<hblocks, 256, 0, s>>>(keys[start_buf & 1], nn, n_ptr, passes, L.hist, range_hdr, depth_bits);

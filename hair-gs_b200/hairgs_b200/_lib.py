@@ -89,6 +89,11 @@ def load():
     lib.hgs_forward_stage_b.restype = c_int
     lib.hgs_forward_stage_b.argtypes = [P(RasterParams), P(RasterInputs), c_void_p, c_void_p, c_void_p, c_int64,
                                         c_void_p, c_void_p, c_void_p]
+    lib.hgs_forward_stage_b_binning.restype = c_int
+    lib.hgs_forward_stage_b_binning.argtypes = [P(RasterParams), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.hgs_forward_stage_b_composite.restype = c_int
+    lib.hgs_forward_stage_b_composite.argtypes = [P(RasterParams), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                                  c_void_p]
     lib.hgs_rasterize_backward.restype = c_int
     lib.hgs_rasterize_backward.argtypes = [P(RasterParams), P(RasterInputs), c_int64, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, P(RasterGrads), c_void_p]
@@ -136,7 +141,7 @@ def load():
     lib.hgs_profile_collect.argtypes = [c_void_p, c_void_p]
     lib.hgs_stage_name.restype = c_char_p
     lib.hgs_stage_name.argtypes = [c_int]
-    if lib.hgs_abi_version() != 3:
+    if lib.hgs_abi_version() != 4:
         raise ImportError("libhairgs_rast.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

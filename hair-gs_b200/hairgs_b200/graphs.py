@@ -226,3 +226,199 @@ class GraphedStrandStep:
         """Synchronises the device and validates the last replay of every slot."""
         torch.cuda.synchronize(self.dev)
         return [p.check() for p, ev in zip(self.plans, self.done) if ev is not None]
+
+
+class GraphedStrandBatch:
+    """The V views of one optimiser step as ONE CUDA graph with two branches, so that the binning of view k+1 runs UNDER the
+    compositing of view k (SURVEY.md 8e batch schedule):
+
+        binning stream (high priority):  [stage A + scan + keys + sort + ranges/packing](0) -> (1) -> ... -> (V-1)
+        main stream:                      wait bin(0): [composite fwd + image loss + composite bwd + preprocess bwd](0) -> ...
+
+    The binning chain of a cfg3 view is ~0.23 ms of one-wave, latency-bound kernels at <= 30 % issue utilisation; the
+    compositors are issue-bound.  Neither can use the SM alone, together they can: the binning kernels take the issue slots
+    and the CTA slots the compositors leave idle.  Every view has its own workspaces (geometry, binning, image: ~0.5 GB per
+    cfg3 view), so the binning branch never waits for the main branch; the main branch is ordered (the backward of view k
+    adds to the gradients view k-1 wrote), which is the only dependency between views.  The first view OVERWRITES the
+    gradient sink (or adds, `replay(accumulate=True)`), the others add: one replay = the gradient of the whole batch.
+
+    Inputs that change per step live in static device buffers the caller fills before replay(): cam_buf [V,35]
+    (world_view_transform | full_proj_transform | camera_center per view) and tgt_buf [V,6,H,W] (image[3] | mask |
+    orientation field | confidence); or a fixed dL/dimage7 (`dimage`) instead of the image loss.  Outputs: losses [V],
+    terms [V,8], per-view image / radii / mean2d_grad.  validate() / check() as for GraphedStrandStep."""
+
+    def __init__(self, model, sink, bg7, H, W, fovx, fovy, capacity, depth_bits, views, lambdas=None, dimage=None,
+                 cam_buf=None, tgt_buf=None):
+        dev = model._endpoints.device
+        if dev.type != "cuda":
+            raise L.HgsError("GraphedStrandBatch needs a CUDA model: this rasterizer has no CPU path")
+        if sink is None or not all(k in sink.tensors for k in ("endpoints", "width", "opacity", "mask", "features")):
+            raise L.HgsError("GraphedStrandBatch needs a fused.GradSink with endpoints / width / opacity / mask / features")
+        if int(capacity) <= 0 or int(views) < 1:
+            raise L.HgsError("GraphedStrandBatch: capacity and views must be positive (see measure_plan)")
+        self.lib = L.load()
+        self.model, self.sink, self.dev = model, sink, dev
+        self.bg7 = L.f32c(bg7, "bg7", dev)
+        self.H, self.W, self.V = int(H), int(W), int(views)
+        self.tanfovx, self.tanfovy = math.tan(float(fovx) * 0.5), math.tan(float(fovy) * 0.5)
+        self.lambdas = dict(lambdas or {})
+        if dimage is not None and (dimage.shape != (7, self.H, self.W) or dimage.dtype != torch.float32
+                                   or dimage.device != dev or not dimage.is_contiguous()):
+            raise L.HgsError("GraphedStrandBatch: dimage must be a contiguous float32 [7,H,W] tensor on the model's device")
+        self.dimage = dimage
+        V, P = self.V, int(model.endpoint_pairs.shape[0])
+        self.P = P
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.cam_buf = cam_buf if cam_buf is not None else torch.zeros(V, 35, **f32)
+        self.tgt_buf = tgt_buf if tgt_buf is not None else (torch.zeros(V, 6, self.H, self.W, **f32) if dimage is None else None)
+        if self.cam_buf.shape != (V, 35) or self.cam_buf.dtype != torch.float32 or not self.cam_buf.is_contiguous():
+            raise L.HgsError("GraphedStrandBatch: cam_buf must be a contiguous float32 [V,35] tensor")
+        if self.tgt_buf is not None and (self.tgt_buf.shape != (V, 6, self.H, self.W) or not self.tgt_buf.is_contiguous()):
+            raise L.HgsError("GraphedStrandBatch: tgt_buf must be a contiguous float32 [V,6,H,W] tensor")
+        self.plans = [LaunchPlan(capacity, depth_bits) for _ in range(V)]
+        lib = self.lib
+        u8 = dict(dtype=torch.uint8, device=dev)
+        # per-view workspaces and outputs, allocated once (outside any capture)
+        self.geom = [torch.empty(lib.hgs_geom_bytes(P, 7), **u8) for _ in range(V)]
+        self.img_ws = [torch.empty(lib.hgs_image_bytes(self.W, self.H), **u8) for _ in range(V)]
+        self.binning = [torch.empty(lib.hgs_binning_bytes(int(capacity), 7), **u8) for _ in range(V)]
+        self.image = [torch.empty(7, self.H, self.W, **f32) for _ in range(V)]
+        self.radii = [torch.empty(P, dtype=torch.int32, device=dev) for _ in range(V)]
+        self.acc = [torch.empty(P * 15, **f32) for _ in range(V)]      # mean2D 3 | conic 4 | opacity 1 | colour 7
+        self.mean2d_grad = [a[:3 * P].view(P, 3) for a in self.acc]
+        self.losses = torch.zeros(V, **f32)
+        self.terms = torch.zeros(V, 8, **f32)
+        self.bin_stream = torch.cuda.Stream(device=dev, priority=-1)
+        self.graphs = {}
+        self.done = None
+        self.replays = 0
+
+    def _prm_inp(self, v, features):
+        m = self.model
+        cd = self.cam_buf[v]
+        prm = L.RasterParams(P=self.P, D=int(m.active_sh_degree), M=int(features.shape[1]), width=self.W, height=self.H,
+                             channels=7, tan_fovx=self.tanfovx, tan_fovy=self.tanfovy, scale_modifier=1.0, prefiltered=0,
+                             debug=0, sort_depth_bits=int(self.plans[v].depth_bits))
+        inp = L.StrandInputs(num_endpoints=int(m._endpoints.shape[0]), background=self.bg7.data_ptr(),
+                             endpoints=m._endpoints.data_ptr(), endpoint_pairs=m.endpoint_pairs.data_ptr(),
+                             width=m._width.data_ptr(), opacity_logit=m._opacity.data_ptr(), mask_logit=m._mask.data_ptr(),
+                             features=features.data_ptr(), viewmatrix=cd[0:16].data_ptr(), projmatrix=cd[16:32].data_ptr(),
+                             cam_pos=cd[32:35].data_ptr())
+        return prm, inp
+
+    def _batch(self, accumulate_first):
+        """The body that is captured (also run eagerly as warm-up): two branches, see the class docstring."""
+        import ctypes
+        lib, dev, V = self.lib, self.dev, self.V
+        m = self.model
+        for t in (m._endpoints, m._width, m._opacity, m._mask):
+            if not t.is_contiguous() or t.dtype != torch.float32:
+                raise L.HgsError("GraphedStrandBatch: parameters must be contiguous float32 tensors")
+        main = torch.cuda.current_stream(dev)
+        side = self.bin_stream
+        cap = int(self.plans[0].capacity)
+        lam = self.lambdas
+        l_dssim = float(lam.get("lambda_dssim", 0.2))
+        weights = (max(0.0, 1.0 - l_dssim), l_dssim, float(lam.get("lambda_mask", 0.01)),
+                   float(lam.get("lambda_orientation", 100.0)))
+        s = self.sink
+        E = int(m._endpoints.shape[0])
+        Mf = int(m._features_dc.shape[1] + m._features_rest.shape[1])
+        for k, t in s.tensors.items():
+            want = {"endpoints": 3 * E, "width": self.P, "opacity": self.P, "mask": self.P, "features": 3 * Mf * self.P}.get(k)
+            if want is not None and (t.numel() != want or t.dtype != torch.float32 or t.device != dev or not t.is_contiguous()):
+                raise L.HgsError("grad_sink: tensors must be contiguous float32 on the render device, shaped like the parameters")
+        with torch.no_grad(), torch.cuda.device(dev):
+            features = m.get_features.contiguous()      # cat(dc, rest): once per batch, shared by the views
+            self._features = features
+            side.wait_stream(main)                      # fork
+            bin_done = []
+            for v in range(V):
+                prm, inp = self._prm_inp(v, features)
+                with torch.cuda.stream(side):
+                    st = side.cuda_stream
+                    L.check(lib.hgs_strands_forward_stage_a(ctypes.byref(prm), ctypes.byref(inp), self.geom[v].data_ptr(),
+                                                            self.radii[v].data_ptr(), st), "strands stage A")
+                    L.check(lib.hgs_forward_read_num_rendered(self.geom[v].data_ptr(), self.P, self.plans[v].host.data_ptr(), st),
+                            "read num_rendered")
+                    L.check(lib.hgs_forward_stage_b_binning(ctypes.byref(prm), self.geom[v].data_ptr(), self.binning[v].data_ptr(),
+                                                            self.img_ws[v].data_ptr(), cap, st), "binning")
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    bin_done.append(ev)
+            for v in range(V):
+                prm, inp = self._prm_inp(v, features)
+                main.wait_event(bin_done[v])
+                st = main.cuda_stream
+                L.check(lib.hgs_forward_stage_b_composite(ctypes.byref(prm), self.bg7.data_ptr(), self.geom[v].data_ptr(),
+                                                          self.binning[v].data_ptr(), self.img_ws[v].data_ptr(), cap,
+                                                          self.image[v].data_ptr(), st), "composite")
+                if self.dimage is not None:
+                    dimage = self.dimage
+                else:
+                    tgt = self.tgt_buf[v]
+                    terms, dimage = losses.hair_image_loss_raw(self.image[v], tgt[0:3], tgt[3], tgt[4], tgt[5], tgt[3] > 0.5,
+                                                               self.cam_buf[v][0:16].view(4, 4), weights,
+                                                               lam.get("bg_orient", (0.0, 0.0, 0.0)))
+                    self.terms[v].copy_(terms)
+                acc = self.acc[v]
+                grads = L.StrandGrads(dL_dmean2D=acc.data_ptr(), dL_dconic=acc[3 * self.P:].data_ptr(),
+                                      dL_dopacity=acc[7 * self.P:].data_ptr(), dL_dcolor=acc[8 * self.P:].data_ptr(),
+                                      dL_dendpoints=s.tensors["endpoints"].data_ptr(), dL_dwidth=s.tensors["width"].data_ptr(),
+                                      dL_dopacity_logit=s.tensors["opacity"].data_ptr(),
+                                      dL_dmask_logit=s.tensors["mask"].data_ptr(), dL_dfeatures=s.tensors["features"].data_ptr(),
+                                      accumulate=1 if (accumulate_first or v > 0) else 0)
+                L.check(lib.hgs_strands_backward(ctypes.byref(prm), ctypes.byref(inp), cap, self.geom[v].data_ptr(),
+                                                 self.binning[v].data_ptr(), self.img_ws[v].data_ptr(), dimage.data_ptr(),
+                                                 ctypes.byref(grads), st), "strands backward")
+            if self.dimage is None:
+                self.losses.copy_(self.terms[:, 0])
+            main.wait_stream(side)                      # join
+
+    def capture(self, warmup=2, accumulate_variant=True):
+        """`warmup` eager batches on a side stream, then one graph per mode (first view overwrites / adds).  cam_buf (and
+        tgt_buf) must already hold real views."""
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._batch(False)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        for p in self.plans:
+            p.check()
+        pool = None
+        for acc in ((False, True) if accumulate_variant else (False,)):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
+                self._batch(acc)
+            pool = g.pool()
+            self.graphs[acc] = g
+        return self
+
+    def replay(self, accumulate=False):
+        """Replays the whole batch on the current stream; returns the static [V] tensor of the views' losses."""
+        if self.done is not None:
+            self.done.synchronize()
+            for p in self.plans:
+                p.check()
+        if accumulate not in self.graphs:
+            raise L.HgsError("GraphedStrandBatch was captured without the accumulate variant")
+        self.graphs[accumulate].replay()
+        self.done = torch.cuda.Event()
+        self.done.record(torch.cuda.current_stream(self.dev))
+        self.sink.accumulate = True
+        self.replays += 1
+        return self.losses
+
+    def validate(self):
+        """Before the all-reduce / optimiser step: waits for the last replay and raises HgsPlanError if a view did not fit."""
+        if self.done is None:
+            return []
+        self.done.synchronize()
+        return [p.check() for p in self.plans]
+
+    def check(self):
+        torch.cuda.synchronize(self.dev)
+        return [p.check() for p in self.plans] if self.done is not None else []

@@ -54,7 +54,7 @@
 extern "C" {
 #endif
 
-#define HGS_ABI_VERSION 3
+#define HGS_ABI_VERSION 4
 #define HGS_TILE 16            /* BLOCK_X == BLOCK_Y == 16, cuda_rasterizer/config.h:16-17 */
 #define HGS_MAX_CHANNELS 8     /* colour channels per pass: 3 (reference) .. 8 (fused RGB+mask+orientation) */
 
@@ -196,6 +196,18 @@ int hgs_forward_read_num_rendered(const void* geom_ws, int32_t P, uint32_t* n_pi
 int hgs_forward_stage_b(const hgs_raster_params* prm, const hgs_raster_inputs* in,
                         void* geom_ws, void* binning_ws, void* image_ws, int64_t capacity,
                         const int32_t* radii, float* out_color, void* stream);
+
+/* Stage B in its two halves (ABI v4), for callers that overlap the latency-bound binning of one view with the issue-bound
+ * compositing of another on a second stream (hairgs_b200/graphs.py: GraphedStrandBatch; the reference runs K4-K7 back to
+ * back on one stream, rasterizer_impl.cu:284-333):
+ *   binning    key emission + (tile|depth) sort + tile ranges + sorted-order record packing   (K4-K6)
+ *   composite  per-tile alpha compositing into out_color / final_T / n_contrib                (K7)
+ * Same workspaces and `capacity` as hgs_forward_stage_b, which is exactly binning followed by composite.  Valid for both
+ * entries (Gaussians given, or strand end points): only prm and the background are read. */
+int hgs_forward_stage_b_binning(const hgs_raster_params* prm, void* geom_ws, void* binning_ws, void* image_ws,
+                                int64_t capacity, void* stream);
+int hgs_forward_stage_b_composite(const hgs_raster_params* prm, const float* background, void* geom_ws, void* binning_ws,
+                                  void* image_ws, int64_t capacity, float* out_color, void* stream);
 
 /* Backward pass.  R = the capacity binning_ws was carved with (num_rendered in exact mode, see
  * hgs_binning_capacity); workspaces are the forward's. */

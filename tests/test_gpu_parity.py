@@ -1091,3 +1091,59 @@ def test_graphed_step_detects_a_plan_that_does_not_fit():
     with pytest.raises(graphs.HgsPlanError):
         step.capture()
     assert cap > 4096
+
+
+def test_graphed_batch_equals_sum_of_eager_views():
+    """hairgs_b200.graphs.GraphedStrandBatch: V views of one optimiser step captured as ONE two-branch graph (binning of view
+    k+1 on a second stream under the compositing of view k).  Replayed on cameras / targets it was not captured on, the
+    per-view losses, images and radii must equal the eager path's and the sink must hold the SUM of the views' gradients
+    (first view overwrites, the others add; `accumulate=True` adds the whole batch to what is there)."""
+    from hairgs_b200 import fused, graphs, losses
+    model, cams, tgts, sink, names = _graph_fixture()
+    H, W, V = 192, 256, 3
+    bg7 = torch.zeros(7, device=dev())
+    lam = dict(lambda_dssim=0.2, lambda_mask=0.01, lambda_orientation=100.0)
+    eager = []
+    for cam, t in zip(cams, tgts):
+        sink.begin_step()
+        out = fused.render_strands(cam, model, bg7, grad_sink=sink)
+        loss, terms = losses.hair_image_loss(out["image7"], t[0:3], t[3], t[4], t[5],
+                                             losses.view_rot_of(cam.world_view_transform.cpu()), orient_mask=t[3] > 0.5, **lam)
+        loss.backward()
+        eager.append((float(loss), out["image7"].detach().clone(), out["radii"].clone(), {k: v.clone() for k, v in sink.tensors.items()}))
+    cap, bits = graphs.measure_plan(model, cams, bg7)
+    batch = graphs.GraphedStrandBatch(model, sink, bg7, H, W, cams[0].FoVx, cams[0].FoVy, cap, bits, V, lambdas=lam)
+    flat = lambda c: torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1), c.camera_center.reshape(-1)])  # noqa: E731
+
+    def load(order):
+        for row, i in enumerate(order):
+            batch.cam_buf[row].copy_(flat(cams[i]))
+            batch.tgt_buf[row].copy_(tgts[i])
+
+    load((0, 1, 2))
+    batch.capture()
+    for order in ((3, 0, 2), (1, 1, 3), (2, 3, 0)):
+        load(order)
+        for k in names:
+            sink.tensors[k].fill_(float("nan"))           # the first view of a batch overwrites
+        loss = batch.replay()
+        torch.cuda.synchronize()
+        for row, i in enumerate(order):
+            ref_loss, ref_img, ref_radii, _ = eager[i]
+            assert abs(float(loss[row]) - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss)), (order, row)
+            assert torch.equal(batch.image[row], ref_img) and torch.equal(batch.radii[row], ref_radii), (order, row)
+        for k in names:
+            want = sum(eager[i][3][k] for i in order)
+            assert common.rel_err(sink.tensors[k], want) <= 1e-5, (order, k, common.rel_err(sink.tensors[k], want))
+    before = {k: v.clone() for k, v in sink.tensors.items()}
+    batch.replay(accumulate=True)
+    torch.cuda.synchronize()
+    for k in names:
+        assert common.rel_err(sink.tensors[k], 2 * before[k]) <= 1e-5, k
+    assert all(n > 0 for n in batch.validate())
+    # a plan that does not fit is reported before anything consumes the gradients
+    small = graphs.GraphedStrandBatch(model, sink, bg7, H, W, cams[0].FoVx, cams[0].FoVy, 4096, bits, 2, lambdas=lam)
+    small.cam_buf[0].copy_(flat(cams[0]))
+    small.cam_buf[1].copy_(flat(cams[1]))
+    with pytest.raises(graphs.HgsPlanError):
+        small.capture()

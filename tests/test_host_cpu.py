@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(L.LIB_PATH)
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/hairgs_rast.h but not exported"
-    assert L.load().hgs_abi_version() == 3
+    assert L.load().hgs_abi_version() == 4
 
 
 def test_struct_layouts_match_header():
