@@ -319,6 +319,25 @@ int hgs_strands_backward(const hgs_raster_params* prm, const hgs_strand_inputs* 
     return stage_check("strand preprocess_bwd", prm->debug, s);
 }
 
+int hgs_graph_instantiate(void* graph, int32_t use_node_priority, void** exec) {
+    if (!graph || !exec) { set_error("null graph"); return HGS_ERR_INVALID; }
+    cudaGraphExec_t e = nullptr;
+    const unsigned long long flags = use_node_priority ? cudaGraphInstantiateFlagUseNodePriority : 0ull;
+    if (int err = check_cuda(cudaGraphInstantiateWithFlags(&e, (cudaGraph_t)graph, flags), "cudaGraphInstantiateWithFlags")) return err;
+    *exec = (void*)e;
+    return HGS_OK;
+}
+
+int hgs_graph_launch(void* exec, void* stream) {
+    if (!exec) { set_error("null graph exec"); return HGS_ERR_INVALID; }
+    return check_cuda(cudaGraphLaunch((cudaGraphExec_t)exec, (cudaStream_t)stream), "cudaGraphLaunch");
+}
+
+int hgs_graph_exec_destroy(void* exec) {
+    if (!exec) return HGS_OK;
+    return check_cuda(cudaGraphExecDestroy((cudaGraphExec_t)exec), "cudaGraphExecDestroy");
+}
+
 int hgs_rasterize_forward(hgs_alloc_fn geom_alloc, void* geom_user, hgs_alloc_fn binning_alloc, void* binning_user,
                           hgs_alloc_fn image_alloc, void* image_user, const hgs_raster_params* prm,
                           const hgs_raster_inputs* in, float* out_color, int32_t* radii, void* stream) {

@@ -271,7 +271,24 @@ struct FwdHalfSmem {
     float4 q_col[2][QN * (CS / 4)];
 };
 
-template <int C, int CS, bool kStats>
+// Per-warp landing zone of the bulk-copy staged walk (kBulk): two stages of one 32-instance chunk each.  The tile's list is
+// contiguous in the three sorted-order record arrays (finalize_sorted), so a chunk is three 1-D bulk copies
+// (cp.async.bulk, the TMA engine: 512 B + 512 B + 32*CS*4 B) completed through the stage's mbarrier; the reference stages
+// its batches with plain loads and two block barriers per batch (forward.cu:294-326).
+template <int CS>
+struct __align__(128) FwdStage {
+    float4 lo[32];
+    float4 hi[32];
+    float4 col[32 * (CS / 4)];
+};
+static constexpr int kFwdStages = 4;  // chunks in flight per warp: the engine's latency for a 2 KB copy is ~2 chunk times
+template <int CS>
+struct __align__(128) FwdBulkSmem {
+    FwdStage<CS> stage[kFwdStages];
+    uint64_t bar[kFwdStages];
+};
+
+template <int C, int CS, bool kStats, bool kBulk>
 __global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __restrict__ ranges,
                                                                  const uint32_t* __restrict__ tile_order, int W, int H,
                                                                  const float4* __restrict__ pk_lo,
@@ -284,11 +301,21 @@ __global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __
     using WS = FwdHalfSmem<CS>;
     constexpr uint32_t QN = WS::QN;
     __shared__ WS s_ws[8];
+    extern __shared__ __align__(128) unsigned char fwd_dyn_smem[];   // kBulk: FwdBulkSmem<CS>[8]
 
     constexpr bool kExactOrder = C <= 4;  // see composite_fwd_kernel
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t half = lane >> 4, hl = lane & 15;
     WS& ws = s_ws[warp];
+    FwdBulkSmem<CS>* bs = kBulk ? &reinterpret_cast<FwdBulkSmem<CS>*>(fwd_dyn_smem)[warp] : nullptr;
+    if (kBulk) {
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < kFwdStages; ++k) mbar_init(&bs->bar[k], 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+    }
     const uint32_t horizontal_blocks = (W + HGS_TILE - 1) / HGS_TILE;
     const uint32_t tile = tile_order[blockIdx.x];
     const uint32_t X0 = (tile % horizontal_blocks) * HGS_TILE, Y0 = (tile / horizontal_blocks) * HGS_TILE;
@@ -384,7 +411,26 @@ __global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __
     if (!__all_sync(0xffffffffu, done) && nchunks > 0) {
         float4 nlo = make_float4(0, 0, 0, 0), nhi = make_float4(0, 0, 0, 0), nc0 = make_float4(0, 0, 0, 0),
                nc1 = make_float4(0, 0, 0, 0);
-        if ((int)lane < total) {
+        // kBulk: lane 0 asks the TMA engine for chunk c (three contiguous pieces) into stage c & 1
+        auto issue = [&](int c) {
+            if (lane == 0) {
+                const uint32_t cnt = (uint32_t)min(32, total - c * 32);
+                const size_t i = (size_t)range.x + (size_t)c * 32;
+                FwdStage<CS>& st = bs->stage[c % kFwdStages];
+                uint64_t* bar = &bs->bar[c % kFwdStages];
+                mbar_expect_tx(bar, cnt * (32u + 4u * CS));
+                bulk_g2s(st.lo, pk_lo + i, cnt * 16u, bar);
+                bulk_g2s(st.hi, pk_hi + i, cnt * 16u, bar);
+                bulk_g2s(st.col, pk_col + i * (CS / 4), cnt * 4u * CS, bar);
+            }
+        };
+        int issued = 0;  // kBulk: last chunk whose copy was issued (every issued copy must LAND before the warp may exit)
+        if (kBulk) {
+            for (int k = 0; k < kFwdStages - 1 && k < nchunks; ++k) {
+                issue(k);
+                issued = k;
+            }
+        } else if ((int)lane < total) {
             const size_t i = (size_t)range.x + lane;
             nlo = pk_lo[i];
             nhi = pk_hi[i];
@@ -393,16 +439,33 @@ __global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __
         }
         bool all_done = false;
         for (int c = 0; c < nchunks; ++c) {
-            const float4 lo = nlo, hi = nhi, c0 = nc0, c1 = nc1;
+            float4 lo, hi, c0, c1 = make_float4(0, 0, 0, 0);
             const bool have = c * 32 + (int)lane < total;
-            if (c + 1 < nchunks) {  // prefetch the next chunk while this one is blended
-                const int p = (c + 1) * 32 + (int)lane;
-                if (p < total) {
-                    const size_t i = (size_t)range.x + p;
-                    nlo = pk_lo[i];
-                    nhi = pk_hi[i];
-                    nc0 = pk_col[i * (CS / 4)];
-                    if (CS > 4) nc1 = pk_col[i * (CS / 4) + 1];
+            if (kBulk) {
+                // the stage of chunk c + kFwdStages - 1 held chunk c - 1, which every lane has copied out (the __syncwarp
+                // below orders those reads before the engine's writes)
+                if (c + kFwdStages - 1 < nchunks) {
+                    issue(c + kFwdStages - 1);
+                    issued = c + kFwdStages - 1;
+                }
+                mbar_wait(&bs->bar[c % kFwdStages], (uint32_t)(c / kFwdStages) & 1u);
+                const FwdStage<CS>& st = bs->stage[c % kFwdStages];
+                lo = st.lo[lane];
+                hi = st.hi[lane];
+                c0 = st.col[lane * (CS / 4)];
+                if (CS > 4) c1 = st.col[lane * (CS / 4) + 1];
+                __syncwarp();
+            } else {
+                lo = nlo; hi = nhi; c0 = nc0; c1 = nc1;
+                if (c + 1 < nchunks) {  // prefetch the next chunk while this one is blended
+                    const int p = (c + 1) * 32 + (int)lane;
+                    if (p < total) {
+                        const size_t i = (size_t)range.x + p;
+                        nlo = pk_lo[i];
+                        nhi = pk_hi[i];
+                        nc0 = pk_col[i * (CS / 4)];
+                        if (CS > 4) nc1 = pk_col[i * (CS / 4) + 1];
+                    }
                 }
             }
             // culled only when a comparison is TRUE, so NaNs keep the instance (the reference would evaluate it)
@@ -446,6 +509,9 @@ __global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __
             }
             if (__all_sync(0xffffffffu, done)) {
                 all_done = true;
+                // an in-flight bulk copy targets this CTA's shared memory: it must land before the block can retire
+                if (kBulk)
+                    for (int k = c + 1; k <= issued; ++k) mbar_wait(&bs->bar[k % kFwdStages], (uint32_t)(k / kFwdStages) & 1u);
                 break;
             }
         }
@@ -1051,13 +1117,37 @@ static int launch_fwd_c(const ImageLayout& im, const BinningLayout& b, int W, in
     const unsigned grid = (unsigned)(((W + HGS_TILE - 1) / HGS_TILE) * ((H + HGS_TILE - 1) / HGS_TILE));
     constexpr int CS = (C <= 4) ? 4 : 8;
     const PackedView p = packed_view(b);
+    // HGS_FWD_SMEM_PAD=<bytes>: unused dynamic shared memory added to the forward launch to LOWER its occupancy
+    // (experiments on co-scheduling with the binning kernels of the next view, profiles/r2_overlap.md)
+    static const int pad = [] { const char* e = getenv("HGS_FWD_SMEM_PAD"); return e ? atoi(e) : 0; }();
+    // HGS_FWD_STAGING=bulk: chunks staged into shared memory by the TMA engine (cp.async.bulk + mbarrier) instead of the
+    // register prefetch (A/B in profiles/r2_fwd_staging.md)
+    static const bool bulk = [] { const char* e = getenv("HGS_FWD_STAGING"); return e != nullptr && strcmp(e, "bulk") == 0; }();
+    if ((pad > 0 || bulk) && composite_blocks_4x4() && !g_fwd_stats_on) {
+        const int dyn = bulk ? (int)(8 * sizeof(FwdBulkSmem<CS>)) + pad : pad;
+        static std::atomic<unsigned long long> pad_done{0};
+        if (first_call_on_device(pad_done)) {
+            if (int e = check_cuda(cudaFuncSetAttribute(composite_fwd_half_kernel<C, CS, false, false>,
+                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, dyn), "fwd pad attr")) return e;
+            if (int e = check_cuda(cudaFuncSetAttribute(composite_fwd_half_kernel<C, CS, false, true>,
+                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, dyn), "fwd bulk attr")) return e;
+        }
+        StageScope prof(HGS_STAGE_COMPOSITE_FWD, s);
+        if (bulk)
+            composite_fwd_half_kernel<C, CS, false, true><<<grid, 256, dyn, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col,
+                                                                                  bg, im.final_T, im.n_contrib, out_color);
+        else
+            composite_fwd_half_kernel<C, CS, false, false><<<grid, 256, dyn, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col,
+                                                                                   bg, im.final_T, im.n_contrib, out_color);
+        return check_cuda(cudaGetLastError(), "composite_fwd launch");
+    }
     StageScope prof(HGS_STAGE_COMPOSITE_FWD, s);
     if (composite_blocks_4x4() && g_fwd_stats_on)
-        composite_fwd_half_kernel<C, CS, true><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col, bg,
-                                                                     im.final_T, im.n_contrib, out_color);
+        composite_fwd_half_kernel<C, CS, true, false><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col, bg,
+                                                                            im.final_T, im.n_contrib, out_color);
     else if (composite_blocks_4x4())
-        composite_fwd_half_kernel<C, CS, false><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col, bg,
-                                                                      im.final_T, im.n_contrib, out_color);
+        composite_fwd_half_kernel<C, CS, false, false><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col, bg,
+                                                                             im.final_T, im.n_contrib, out_color);
     else
         composite_fwd_kernel<C, CS><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col, bg, im.final_T,
                                                           im.n_contrib, out_color);

@@ -94,6 +94,12 @@ def load():
     lib.hgs_forward_stage_b_composite.restype = c_int
     lib.hgs_forward_stage_b_composite.argtypes = [P(RasterParams), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                                   c_void_p]
+    lib.hgs_graph_instantiate.restype = c_int
+    lib.hgs_graph_instantiate.argtypes = [c_void_p, c_int32, P(c_void_p)]
+    lib.hgs_graph_launch.restype = c_int
+    lib.hgs_graph_launch.argtypes = [c_void_p, c_void_p]
+    lib.hgs_graph_exec_destroy.restype = c_int
+    lib.hgs_graph_exec_destroy.argtypes = [c_void_p]
     lib.hgs_rasterize_backward.restype = c_int
     lib.hgs_rasterize_backward.argtypes = [P(RasterParams), P(RasterInputs), c_int64, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, P(RasterGrads), c_void_p]

@@ -289,7 +289,7 @@ class GraphedStrandBatch:
         self.losses = torch.zeros(V, **f32)
         self.terms = torch.zeros(V, 8, **f32)
         self.bin_stream = torch.cuda.Stream(device=dev, priority=-1)
-        self.graphs = {}
+        self.graphs, self.execs, self.use_priority = {}, {}, True
         self.done = None
         self.replays = 0
 
@@ -331,10 +331,14 @@ class GraphedStrandBatch:
         with torch.no_grad(), torch.cuda.device(dev):
             features = m.get_features.contiguous()      # cat(dc, rest): once per batch, shared by the views
             self._features = features
+            import os
+            parts = os.environ.get("HGS_BATCH_PARTS", "both")   # debug / measurement: "bin" or "comp" runs one branch only
             side.wait_stream(main)                      # fork
             bin_done = []
             for v in range(V):
                 prm, inp = self._prm_inp(v, features)
+                if parts == "comp":
+                    continue
                 with torch.cuda.stream(side):
                     st = side.cuda_stream
                     L.check(lib.hgs_strands_forward_stage_a(ctypes.byref(prm), ctypes.byref(inp), self.geom[v].data_ptr(),
@@ -347,8 +351,11 @@ class GraphedStrandBatch:
                     ev.record(side)
                     bin_done.append(ev)
             for v in range(V):
+                if parts == "bin":
+                    break
                 prm, inp = self._prm_inp(v, features)
-                main.wait_event(bin_done[v])
+                if parts != "comp":
+                    main.wait_event(bin_done[v])
                 st = main.cuda_stream
                 L.check(lib.hgs_forward_stage_b_composite(ctypes.byref(prm), self.bg7.data_ptr(), self.geom[v].data_ptr(),
                                                           self.binning[v].data_ptr(), self.img_ws[v].data_ptr(), cap,
@@ -388,13 +395,24 @@ class GraphedStrandBatch:
         torch.cuda.synchronize(self.dev)
         for p in self.plans:
             p.check()
+        import ctypes
+        import os
+        # Node priorities: torch instantiates its graphs without cudaGraphInstantiateFlagUseNodePriority, so every node would
+        # run at the launch stream's priority and the binning branch would queue behind the compositors' blocks.  The
+        # captured cudaGraph_t is therefore kept (keep_graph=True) and instantiated by the library with the flag
+        # (hgs_graph_instantiate); HGS_GRAPH_PRIORITY=0 falls back to torch's own instantiation (A/B measurements).
+        self.use_priority = os.environ.get("HGS_GRAPH_PRIORITY", "1") != "0"
         pool = None
         for acc in ((False, True) if accumulate_variant else (False,)):
-            g = torch.cuda.CUDAGraph()
+            g = torch.cuda.CUDAGraph(keep_graph=True) if self.use_priority else torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
                 self._batch(acc)
             pool = g.pool()
             self.graphs[acc] = g
+            if self.use_priority:
+                ex = ctypes.c_void_p()
+                L.check(self.lib.hgs_graph_instantiate(ctypes.c_void_p(g.raw_cuda_graph()), 1, ctypes.byref(ex)), "graph instantiate")
+                self.execs[acc] = ex
         return self
 
     def replay(self, accumulate=False):
@@ -405,12 +423,23 @@ class GraphedStrandBatch:
                 p.check()
         if accumulate not in self.graphs:
             raise L.HgsError("GraphedStrandBatch was captured without the accumulate variant")
-        self.graphs[accumulate].replay()
+        if self.use_priority:
+            with torch.cuda.device(self.dev):
+                L.check(self.lib.hgs_graph_launch(self.execs[accumulate], L.stream_ptr(self.dev)), "graph launch")
+        else:
+            self.graphs[accumulate].replay()
         self.done = torch.cuda.Event()
         self.done.record(torch.cuda.current_stream(self.dev))
         self.sink.accumulate = True
         self.replays += 1
         return self.losses
+
+    def __del__(self):
+        try:
+            for ex in self.execs.values():
+                self.lib.hgs_graph_exec_destroy(ex)
+        except Exception:
+            pass
 
     def validate(self):
         """Before the all-reduce / optimiser step: waits for the last replay and raises HgsPlanError if a view did not fit."""

@@ -209,6 +209,15 @@ int hgs_forward_stage_b_binning(const hgs_raster_params* prm, void* geom_ws, voi
 int hgs_forward_stage_b_composite(const hgs_raster_params* prm, const float* background, void* geom_ws, void* binning_ws,
                                   void* image_ws, int64_t capacity, float* out_color, void* stream);
 
+/* CUDA-graph helpers (ABI v4).  A captured graph runs all of its kernel nodes at the priority of the stream it is launched
+ * into unless it is instantiated with cudaGraphInstantiateFlagUseNodePriority; the two-branch batch graph needs the node
+ * priorities (its binning branch is captured on a high-priority stream so that its short, latency-bound kernels are
+ * dispatched ahead of the thousands of queued compositor blocks of the other branch).  `graph` is a cudaGraph_t obtained
+ * from the capture (e.g. torch.cuda.CUDAGraph(keep_graph=True).raw_cuda_graph()); *exec receives a cudaGraphExec_t. */
+int hgs_graph_instantiate(void* graph, int32_t use_node_priority, void** exec);
+int hgs_graph_launch(void* exec, void* stream);
+int hgs_graph_exec_destroy(void* exec);
+
 /* Backward pass.  R = the capacity binning_ws was carved with (num_rendered in exact mode, see
  * hgs_binning_capacity); workspaces are the forward's. */
 int hgs_rasterize_backward(const hgs_raster_params* prm, const hgs_raster_inputs* in,

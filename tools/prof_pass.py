@@ -19,7 +19,9 @@ if use_ref:
     backend = refload.ref_dgr()
 else:
     import diff_gaussian_rasterization._C as backend
-h = bench.Harness(bench.WORKLOADS[name], dev, backend, 1, 0)
+import types  # noqa: E402
+args = types.SimpleNamespace(views_per_step=1, gpus=1, graph_mode="view")
+h = bench.Harness(bench.WORKLOADS[name], args, dev, backend, 1, 0)
 fused = len(sys.argv) > 3 and sys.argv[3] == "fused"
 if fused:
     h.setup_fused()
