@@ -1075,6 +1075,13 @@ def algorithmic_bytes(stage, P, N, HW, T, M, D, sh_mode, C=3):
         return 24 * N  # one pass: read + write of (u64 key, u32 value)
     if stage == "tile_ranges":
         return 8 * N + 8 * T   # §8(d) `ranges`; the sorted-order record packing this kernel also does is not credited
+    if stage == "tile_offsets":
+        return 16 * T      # tile counters read, ranges + order written
+    if stage == "tile_scatter":
+        return 20 * P + 8 * N      # rect/depth/offset/count per Gaussian read, one 8-byte word per instance written
+    if stage == "tile_sort_pack":
+        cs = 16 if C <= 4 else 32
+        return (8 + 12 + 2 * (32 + cs)) * N // 3   # per launch: three size-class launches share the instances
     if stage == "composite_fwd":
         return (28 + 4 * C) * N + (8 + 4 * C) * HW
     if stage == "composite_bwd":
@@ -1290,7 +1297,7 @@ def run():
     lib.hgs_profile_collect(ms, cnt)
     lib.hgs_profile_enable(0)
     total = sum(ms)
-    for sidx in range(11):
+    for sidx in range(15):
         if cnt[sidx] == 0:
             continue
         name = lib.hgs_stage_name(sidx).decode()
@@ -1310,7 +1317,8 @@ def run():
                         "stages are listed under 'stages'; traffic is null unless profiles/traffic.json was captured on "
                         "exactly this library build"}
     binning_ms = sum(stages[k]["ms_per_launch"] * stages[k]["launches_per_step"] for k in
-                     ("tile_scan", "emit_keys", "sort_histogram", "sort_onesweep", "tile_ranges") if k in stages) / (h.vps * (1 if can_fuse else len(cfg["sets"])))
+                     ("tile_scan", "emit_keys", "sort_histogram", "sort_onesweep", "tile_ranges", "tile_offsets", "tile_scatter",
+                      "tile_sort_pack") if k in stages) / (h.vps * (1 if can_fuse else len(cfg["sets"])))
 
     # ---- the same e2e step with the optimiser included; runs last because it moves the parameters -------
     h.setup_e2e(fused=can_fuse, optimizer="flat", graph=can_fuse and ms_e2e_eager is not None)

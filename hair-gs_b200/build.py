@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libhairgs_rast.so")
-SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "composite_warp.cu", "knn.cu", "losses.cu", "optimizer.cu", "merge.cu"]
+SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "tilesort.cu", "composite_warp.cu", "knn.cu", "losses.cu", "optimizer.cu", "merge.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -75,6 +75,8 @@ int launch_finalize_sorted(int, int64_t, const uint32_t*, const uint64_t*, const
 int launch_composite_fwd(int, const ImageLayout&, const BinningLayout&, int, int, const float*, float*, cudaStream_t);
 int launch_composite_bwd(int, const ImageLayout&, const BinningLayout&, const uint32_t*, int, int, const float*,
                          const float*, const hgs_raster_grads*, cudaStream_t);
+int launch_tile_binning(int, int, int64_t, const GeomLayout&, const BinningLayout&, const ImageLayout&, uint32_t, uint32_t,
+                        cudaStream_t);
 int set_fwd_stats(void* dev_ptr);
 int set_composite_blocks(int mode);
 int launch_weighted_l1(int, long long, const float*, const float*, const float*, float*, float*, cudaStream_t);
@@ -150,14 +152,17 @@ int hgs_profile_collect(double* ms, int64_t* launches) {
 const char* hgs_stage_name(int stage) {
     static const char* names[HGS_STAGE_COUNT] = {"preprocess_fwd", "emit_keys", "sort_histogram", "sort_onesweep",
                                                   "tile_ranges", "composite_fwd", "composite_bwd", "preprocess_bwd",
-                                                  "knn", "other", "tile_scan"};
+                                                  "knn", "other", "tile_scan", "tile_count", "tile_offsets", "tile_scatter",
+                                                  "tile_sort_pack"};
     return (stage >= 0 && stage < HGS_STAGE_COUNT) ? names[stage] : "?";
 }
 
 int hgs_abi_version(void) { return HGS_ABI_VERSION; }
 const char* hgs_last_error(void) { return g_err; }
 
-size_t hgs_geom_bytes(int32_t P, int32_t channels) { return carve_geom(nullptr, P, channels).bytes; }
+size_t hgs_geom_bytes(int32_t P, int32_t channels, int32_t width, int32_t height) {
+    return carve_geom(nullptr, P, channels, tile_count_of(width, height)).bytes;
+}
 size_t hgs_image_bytes(int32_t width, int32_t height) { return carve_image(nullptr, width, height).bytes; }
 size_t hgs_binning_bytes(int64_t n, int32_t channels) { return carve_binning(nullptr, n, channels).bytes; }
 size_t hgs_sort_bytes(int64_t n) { return carve_sort(nullptr, n).bytes; }
@@ -181,7 +186,7 @@ int hgs_forward_stage_a(const hgs_raster_params* prm, const hgs_raster_inputs* i
     if (int e = validate(prm, in)) return e;
     cudaStream_t s = (cudaStream_t)stream;
     if (!geom_ws) { set_error("null geometry workspace"); return HGS_ERR_INVALID; }
-    GeomLayout g = carve_geom(geom_ws, prm->P, prm->channels);
+    GeomLayout g = carve_geom(geom_ws, prm->P, prm->channels, tile_count_of(prm->width, prm->height));
     if (prm->P == 0) return check_cuda(cudaMemsetAsync(g.hdr, 0, g.clear_bytes, s), "memset geom header");
     if (int e = launch_preprocess_fwd(prm, in, g, radii, s)) return e;
     return stage_check("preprocess", prm->debug, s);
@@ -199,12 +204,16 @@ static int stage_b_impl(const hgs_raster_params* prm, const float* background, v
                         void* image_ws, int64_t N, float* out_color, cudaStream_t s, int parts = 3) {
     if (!geom_ws || !image_ws || (N > 0 && !binning_ws) || ((parts & 2) && !out_color)) { set_error("null workspace/output"); return HGS_ERR_INVALID; }
     if (N < 0 || N > 0x7fffffffll) { set_error("num_rendered out of range"); return HGS_ERR_OVERFLOW; }
-    GeomLayout g = carve_geom(geom_ws, prm->P, prm->channels);
+    GeomLayout g = carve_geom(geom_ws, prm->P, prm->channels, tile_count_of(prm->width, prm->height));
     ImageLayout im = carve_image(image_ws, prm->width, prm->height);
     BinningLayout b = carve_binning(binning_ws, N, prm->channels);
     const uint32_t gx = (prm->width + HGS_TILE - 1) / HGS_TILE, gy = (prm->height + HGS_TILE - 1) / HGS_TILE;
 
-    if (parts & 1) {
+    if ((parts & 1) && prm->sort_mode != HGS_SORT_GLOBAL) {
+        // HGS_SORT_TILE: partition by tile + in-tile sort (tilesort.cu); the sorted pairs end in ping-pong buffer 0
+        if (int e = launch_tile_binning(N > 0 ? prm->P : 0, prm->channels, N, g, b, im, gx, gy, s)) return e;
+        if (int e = stage_check("tile_binning", prm->debug, s)) return e;
+    } else if (parts & 1) {
         // the unsorted pairs go into the ping-pong buffer from which the sort's passes end in buffer 0, whatever their number
         const int start = sort_passes(end_bit_for(prm)) & 1;
         if (int e = launch_emit_keys(N > 0 ? prm->P : 0, g, g.rects, b.keys[start], b.vals[start], gx, (uint32_t)N, s)) return e;
@@ -270,7 +279,7 @@ int hgs_strands_forward_stage_a(const hgs_raster_params* prm, const hgs_strand_i
     if (int e = validate_strands(prm, in)) return e;
     cudaStream_t s = (cudaStream_t)stream;
     if (!geom_ws) { set_error("null geometry workspace"); return HGS_ERR_INVALID; }
-    GeomLayout g = carve_geom(geom_ws, prm->P, prm->channels);
+    GeomLayout g = carve_geom(geom_ws, prm->P, prm->channels, tile_count_of(prm->width, prm->height));
     if (prm->P == 0) return check_cuda(cudaMemsetAsync(g.hdr, 0, g.clear_bytes, s), "memset geom header");
     if (int e = launch_strand_preprocess_fwd(prm, in, g, radii, s)) return e;
     return stage_check("strand preprocess", prm->debug, s);
@@ -294,7 +303,7 @@ int hgs_strands_backward(const hgs_raster_params* prm, const hgs_strand_inputs* 
     if (!gr->accumulate)
         if (int e = check_cuda(cudaMemsetAsync(gr->dL_dendpoints, 0, (size_t)in->num_endpoints * 3 * 4, s), "memset dL_dendpoints")) return e;
     if (P == 0) return HGS_OK;
-    GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels);
+    GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels, tile_count_of(prm->width, prm->height));
     ImageLayout im = carve_image((void*)image_ws, prm->width, prm->height);
     BinningLayout b = carve_binning((void*)binning_ws, R, prm->channels);
     const int res = 0;  // the sorted pairs always end in ping-pong buffer 0 (stage_b_impl)
@@ -344,7 +353,7 @@ int hgs_rasterize_forward(hgs_alloc_fn geom_alloc, void* geom_user, hgs_alloc_fn
     if (int e = validate(prm, in)) return e;
     if (!geom_alloc || !binning_alloc || !image_alloc) { set_error("null allocator"); return HGS_ERR_INVALID; }
     cudaStream_t s = (cudaStream_t)stream;
-    void* geom = geom_alloc(geom_user, hgs_geom_bytes(prm->P, prm->channels));
+    void* geom = geom_alloc(geom_user, hgs_geom_bytes(prm->P, prm->channels, prm->width, prm->height));
     void* img = image_alloc(image_user, hgs_image_bytes(prm->width, prm->height));
     if (!geom || !img) { set_error("allocator returned NULL"); return HGS_ERR_ALLOC; }
     if (int e = hgs_forward_stage_a(prm, in, geom, radii, s)) return e;
@@ -352,11 +361,14 @@ int hgs_rasterize_forward(hgs_alloc_fn geom_alloc, void* geom_user, hgs_alloc_fn
     uint32_t host[3] = {0, 0, 0};
     if (int e = check_cuda(cudaMemcpyAsync(host, geom, sizeof(host), cudaMemcpyDeviceToHost, s), "read num_rendered")) return e;
     if (int e = check_cuda(cudaStreamSynchronize(s), "sync num_rendered")) return e;
-    if (host[2] || host[0] > 0x7fffffffu) { set_error("instance count overflows int32"); return HGS_ERR_OVERFLOW; }
+    if ((host[2] & 1u) || host[0] > 0x7fffffffu) { set_error("instance count overflows int32"); return HGS_ERR_OVERFLOW; }
     const int64_t N = host[0];
     void* bin = binning_alloc(binning_user, hgs_binning_bytes(N, prm->channels));
     if (!bin) { set_error("allocator returned NULL"); return HGS_ERR_ALLOC; }
-    if (int e = hgs_forward_stage_b(prm, in, geom, bin, img, N, radii, out_color, s)) return e;
+    // stage A counted the tile lists: one longer than HGS_TILE_SORT_MAX (bit 2) needs the global radix sort
+    hgs_raster_params p2 = *prm;
+    if (host[2] & 4u) p2.sort_mode = HGS_SORT_GLOBAL;
+    if (int e = hgs_forward_stage_b(&p2, in, geom, bin, img, N, radii, out_color, s)) return e;
     return (int)N;
 }
 
@@ -371,7 +383,7 @@ int hgs_rasterize_backward(const hgs_raster_params* prm, const hgs_raster_inputs
     if (!geom_ws || !image_ws || !dL_dpix || (R > 0 && !binning_ws)) { set_error("null workspace"); return HGS_ERR_INVALID; }
     const int P = prm->P;
     if (P == 0) return HGS_OK;
-    GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels);
+    GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels, tile_count_of(prm->width, prm->height));
     ImageLayout im = carve_image((void*)image_ws, prm->width, prm->height);
     BinningLayout b = carve_binning((void*)binning_ws, R, prm->channels);
     const int res = 0;  // the sorted pairs always end in ping-pong buffer 0 (stage_b_impl)
@@ -511,7 +523,7 @@ int64_t hgs_state_view(int what, const hgs_raster_params* prm, const hgs_raster_
         case HGS_VIEW_CLAMPED: case HGS_VIEW_COV3D: {
             if (!geom_ws || !in) { set_error("null geometry workspace"); return HGS_ERR_INVALID; }
             if (P == 0) return 0;
-            GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels);
+            GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels, tile_count_of(prm->width, prm->height));
             if (int e = launch_view_geom(what, prm, in, g, dst, s)) return e;
             static const int per[] = {4, 8, 16, 0, 0, 0, 3};
             if (what == HGS_VIEW_RGB) return (int64_t)P * prm->channels * 4;
@@ -520,7 +532,7 @@ int64_t hgs_state_view(int what, const hgs_raster_params* prm, const hgs_raster_
         }
         case HGS_VIEW_TILES_TOUCHED: case HGS_VIEW_POINT_OFFSETS: {
             if (!geom_ws) { set_error("null geometry workspace"); return HGS_ERR_INVALID; }
-            GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels);
+            GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels, tile_count_of(prm->width, prm->height));
             return d2d(what == HGS_VIEW_TILES_TOUCHED ? (void*)g.tiles_touched : (void*)g.offsets, (size_t)P * 4);
         }
         case HGS_VIEW_KEYS_SORTED: case HGS_VIEW_POINT_LIST: {

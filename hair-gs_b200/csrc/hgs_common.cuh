@@ -67,6 +67,7 @@ static constexpr int kPreprocThreads = 256;
 struct GeomLayout {
     GeomHeader* hdr;
     unsigned long long* scan_state;  // [ceil(P/256)] chained-scan status words (directly after hdr: one memset clears both)
+    uint32_t* tile_count;     // [tiles] instances per tile, counted by preprocess_fwd (also inside the cleared region)
     float4* rec;              // [2P] : rec[2i] = GaussRecLo, rec[2i+1] = GaussRecHi
     float* rgb;               // [P*cstride] colours used by the compositors (SH result or repacked colors_precomp)
     float* depths;            // [P]
@@ -80,8 +81,11 @@ struct GeomLayout {
 };
 
 __host__ __device__ inline int color_stride(int channels) { return channels <= 4 ? 4 : 8; }
+__host__ __device__ inline size_t tile_count_of(int width, int height) {
+    return (size_t)((width + HGS_TILE - 1) / HGS_TILE) * (size_t)((height + HGS_TILE - 1) / HGS_TILE);
+}
 
-__host__ __device__ inline GeomLayout carve_geom(void* base, int P, int channels) {
+__host__ __device__ inline GeomLayout carve_geom(void* base, int P, int channels, size_t tiles) {
     GeomLayout g;
     char* p = (char*)base;
     size_t off = 0;
@@ -90,6 +94,7 @@ __host__ __device__ inline GeomLayout carve_geom(void* base, int P, int channels
     g.cstride = color_stride(channels);
     g.hdr = (GeomHeader*)(p + off);            off = align_up(off + sizeof(GeomHeader));
     g.scan_state = (unsigned long long*)(p + off); off = align_up(off + nblk * 8);
+    g.tile_count = (uint32_t*)(p + off);       off = align_up(off + tiles * 4);
     g.clear_bytes = off;
     g.rec = (float4*)(p + off);                off = align_up(off + Pz * 32);
     g.rgb = (float*)(p + off);                 off = align_up(off + Pz * 4 * g.cstride);
@@ -107,6 +112,7 @@ struct ImageLayout {
     uint32_t* n_contrib;   // [H*W]
     uint2* ranges;         // [tiles]  (the reference over-allocates H*W entries, rasterizer_impl.cu:172-178)
     uint32_t* tile_order;  // [tiles]  tile ids, longest list first (CTA i composites tile_order[i])
+    uint32_t* tile_cursor; // [tiles]  scatter cursors (HGS_SORT_TILE)
     size_t bytes;
 };
 
@@ -120,6 +126,7 @@ __host__ __device__ inline ImageLayout carve_image(void* base, int W, int H) {
     im.n_contrib = (uint32_t*)(p + off); off = align_up(off + hw * 4);
     im.ranges = (uint2*)(p + off);       off = align_up(off + tiles * 8);
     im.tile_order = (uint32_t*)(p + off); off = align_up(off + tiles * 4);
+    im.tile_cursor = (uint32_t*)(p + off); off = align_up(off + tiles * 4);
     im.bytes = off;
     return im;
 }

@@ -355,6 +355,13 @@ __global__ void __launch_bounds__(kPreprocThreads, 6) preprocess_fwd_kernel(cons
             a.g.rec[2 * (size_t)idx + 1] = make_float4(conic.z, opacity, ext.x, ext.y);
             touched = (rmax.y - rmin.y) * (rmax.x - rmin.x);
             a.g.rects[idx] = make_uint2(rmin.x | (rmin.y << 16), rmax.x | (rmax.y << 16));
+            // per-tile instance counts for the tile-partitioned binning (tilesort.cu): the tile ranges fall out of these
+            // counters, and the longest list is known before stage B is verified (bit 2 of the overflow word)
+            bool too_long = false;
+            for (uint32_t ty = rmin.y; ty < rmax.y; ++ty)
+                for (uint32_t tx = rmin.x; tx < rmax.x; ++tx)
+                    too_long |= atomicAdd(&a.g.tile_count[ty * a.grid_x + tx], 1u) >= (uint32_t)HGS_TILE_SORT_MAX;
+            if (too_long) atomicOr(&a.g.hdr->overflow, 4u);
         } while (false);
         if (a.radii) a.radii[idx] = radius_i;
         a.g.tiles_touched[idx] = touched;

@@ -17,6 +17,13 @@ NUM_CHANNELS = 3
 SYNC_FREE = True        # False: size the binning workspace exactly, after a blocking read-back (reference behaviour)
 _capacity_hint = {}     # (device, P, H, W) -> instance capacity to try first
 _depth_bits_hint = {}   # (device, P, H, W) -> sort_depth_bits to try first (depth-range compaction of the sort keys)
+_sort_mode_hint = {}    # (device, P, H, W) -> L.SORT_GLOBAL once a view had a tile list too long for the in-tile sort
+# HGS_SORT_MODE=global|tile: binning formulation tried first (A/B measurements); default tile (csrc/tilesort.cu)
+DEFAULT_SORT_MODE = L.SORT_GLOBAL if __import__("os").environ.get("HGS_SORT_MODE", "tile") == "global" else L.SORT_TILE
+
+
+def sort_mode_for(key):
+    return _sort_mode_hint.get(key, DEFAULT_SORT_MODE)
 _pinned_pool = []
 _pinned_next = 0
 
@@ -100,7 +107,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         u8 = dict(dtype=torch.uint8, device=dev)
         out_color = torch.empty((C, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
-        geom = torch.empty((lib.hgs_geom_bytes(P, C),), **u8)
+        geom = torch.empty((lib.hgs_geom_bytes(P, C, W, H),), **u8)
         img = torch.empty((lib.hgs_image_bytes(W, H),), **u8)
         if P == 0:
             # rasterize_points.cu:81 short-circuit: zero outputs, empty scratch
@@ -120,6 +127,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         key = (dev.index, P, H, W)
         cap = _capacity_hint.get(key) if SYNC_FREE else None
         prm.sort_depth_bits = _depth_bits_hint.get(key, 0) if SYNC_FREE else 0
+        prm.sort_mode = sort_mode_for(key)
         binning = None
         if cap is not None:
             binning = torch.empty((lib.hgs_binning_bytes(cap, C),), **u8)
@@ -131,13 +139,19 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         if (overflow & 1) != 0 or N < 0:
             raise L.HgsError("instance count overflows int32")
         need = _depth_range_bits(host)
-        fits = prm.sort_depth_bits in (0, 32) or need <= prm.sort_depth_bits
+        if overflow & 4:
+            _sort_mode_hint[key] = L.SORT_GLOBAL    # a tile list is longer than HGS_TILE_SORT_MAX (counted in stage A)
+        if prm.sort_mode == L.SORT_TILE:
+            fits = (overflow & 4) == 0
+        else:
+            fits = prm.sort_depth_bits in (0, 32) or need <= prm.sort_depth_bits
         if cap is None or N > cap or not fits:
             if cap is None or N > cap:
                 binning = torch.empty((lib.hgs_binning_bytes(N, C),), **u8)
                 cap_b = N
             else:
                 cap_b = cap
+            prm.sort_mode = sort_mode_for(key)
             prm.sort_depth_bits = _next_depth_bits(H, W, need) if SYNC_FREE else 0
             L.check(lib.hgs_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
                                             binning.data_ptr() if cap_b > 0 else None, img.data_ptr(), cap_b,

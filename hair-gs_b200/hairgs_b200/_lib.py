@@ -24,7 +24,9 @@ class RasterParams(ctypes.Structure):
     _fields_ = [("P", c_int32), ("D", c_int32), ("M", c_int32), ("width", c_int32), ("height", c_int32),
                 ("channels", c_int32), ("tan_fovx", c_float), ("tan_fovy", c_float),
                 ("scale_modifier", c_float), ("prefiltered", c_int32), ("debug", c_int32),
-                ("sort_depth_bits", c_int32)]
+                ("sort_depth_bits", c_int32), ("sort_mode", c_int32)]
+
+SORT_TILE, SORT_GLOBAL = 0, 1
 
 
 class RasterInputs(ctypes.Structure):
@@ -68,7 +70,7 @@ def load():
     lib.hgs_abi_version.restype = c_int
     lib.hgs_last_error.restype = c_char_p
     lib.hgs_geom_bytes.restype = c_size_t
-    lib.hgs_geom_bytes.argtypes = [c_int32, c_int32]
+    lib.hgs_geom_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32]
     lib.hgs_image_bytes.restype = c_size_t
     lib.hgs_image_bytes.argtypes = [c_int32, c_int32]
     lib.hgs_binning_bytes.restype = c_size_t

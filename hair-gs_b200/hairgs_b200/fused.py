@@ -54,7 +54,7 @@ def strands_forward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit,
         stream = L.stream_ptr(dev)
         image = torch.empty((7, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
-        geom = torch.empty((lib.hgs_geom_bytes(P, 7),), **u8)
+        geom = torch.empty((lib.hgs_geom_bytes(P, 7, W, H),), **u8)
         img = torch.empty((lib.hgs_image_bytes(W, H),), **u8)
         L.check(lib.hgs_strands_forward_stage_a(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
                                                 radii.data_ptr(), stream), "strands stage A")
@@ -67,6 +67,7 @@ def strands_forward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit,
             L.check(lib.hgs_forward_read_num_rendered(geom.data_ptr(), P, plan.host.data_ptr(), stream),
                     "read num_rendered")
             prm.sort_depth_bits = int(plan.depth_bits)
+            prm.sort_mode = int(plan.sort_mode)
             cap = int(plan.capacity)
             binning = torch.empty((lib.hgs_binning_bytes(cap, 7),), **u8)
             L.check(lib.hgs_strands_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
@@ -80,6 +81,7 @@ def strands_forward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit,
         key = (dev.index, P, H, W, 7)
         cap = _dgr._capacity_hint.get(key) if _dgr.SYNC_FREE else None
         prm.sort_depth_bits = _dgr._depth_bits_hint.get(key, 0) if _dgr.SYNC_FREE else 0
+        prm.sort_mode = _dgr.sort_mode_for(key)
         binning = None
         if cap is not None:
             binning = torch.empty((lib.hgs_binning_bytes(cap, 7),), **u8)
@@ -91,11 +93,17 @@ def strands_forward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit,
         if (overflow & 1) != 0 or N < 0:
             raise L.HgsError("instance count overflows int32")
         need = _dgr._depth_range_bits(host)
-        fits = prm.sort_depth_bits in (0, 32) or need <= prm.sort_depth_bits
+        if overflow & 4:
+            _dgr._sort_mode_hint[key] = L.SORT_GLOBAL   # a tile list is longer than HGS_TILE_SORT_MAX (counted in stage A)
+        if prm.sort_mode == L.SORT_TILE:
+            fits = (overflow & 4) == 0
+        else:
+            fits = prm.sort_depth_bits in (0, 32) or need <= prm.sort_depth_bits
         if cap is None or N > cap or not fits:
             if cap is None or N > cap:
                 cap = N
                 binning = torch.empty((lib.hgs_binning_bytes(N, 7),), **u8)
+            prm.sort_mode = _dgr.sort_mode_for(key)
             prm.sort_depth_bits = _dgr._next_depth_bits(H, W, need) if _dgr.SYNC_FREE else 0
             L.check(lib.hgs_strands_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
                                                     binning.data_ptr() if cap > 0 else None, img.data_ptr(), cap,

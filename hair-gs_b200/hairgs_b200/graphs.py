@@ -35,8 +35,11 @@ class LaunchPlan:
     """Fixed launch plan of the strand forward: capacity of the binning workspace (instances) and the sort's depth bits.
     `host` is the pinned read-back target of hgs_forward_read_num_rendered."""
 
-    def __init__(self, capacity, depth_bits):
+    def __init__(self, capacity, depth_bits, sort_mode=None):
         self.capacity, self.depth_bits = int(capacity), int(depth_bits)
+        # binning formulation of the captured view: in-tile sort unless a view of this scene had a tile list longer than
+        # HGS_TILE_SORT_MAX (diff_gaussian_rasterization._C._sort_mode_hint, filled by the eager passes of measure_plan)
+        self.sort_mode = int(_dgr.DEFAULT_SORT_MODE if sort_mode is None else sort_mode)
         self.host = torch.zeros(8, dtype=torch.int32).pin_memory()
 
     def check(self):
@@ -46,6 +49,11 @@ class LaunchPlan:
             raise HgsPlanError("instance count overflows int32")
         if N > self.capacity:
             raise HgsPlanError(f"view has {N} tile instances, the captured plan holds {self.capacity}")
+        if self.sort_mode == L.SORT_TILE:
+            if overflow & 4:
+                raise HgsPlanError("a tile list is longer than HGS_TILE_SORT_MAX: the captured plan sorts inside the tiles; "
+                                   "re-plan (measure_plan switches the scene to the global sort)")
+            return N
         need = _dgr._depth_range_bits(self.host)
         if self.depth_bits not in (0, 32) and need > self.depth_bits:
             raise HgsPlanError(f"view needs {need} depth bits in the sort keys, the captured plan compares {self.depth_bits}")
@@ -121,7 +129,8 @@ class GraphedStrandStep:
                     or c.dtype != torch.float32 or t.dtype != torch.float32 or not t.is_contiguous():
                 raise L.HgsError("GraphedStrandStep: slot buffers must be float32 [35] and contiguous [6,H,W] on the model's "
                                  "device")
-        self.plans = [LaunchPlan(capacity, depth_bits) for _ in range(slots)]
+        key = (dev.index, int(model.endpoint_pairs.shape[0]), self.H, self.W, 7)
+        self.plans = [LaunchPlan(capacity, depth_bits, _dgr.sort_mode_for(key)) for _ in range(slots)]
         self.done = [None] * slots          # event after the slot's last replay
         self.graphs, self.loss, self.terms = [], [], []
         self.mean2d_grad, self.radii, self.image = [None] * slots, [None] * slots, [None] * slots  # static outputs
@@ -275,11 +284,12 @@ class GraphedStrandBatch:
             raise L.HgsError("GraphedStrandBatch: cam_buf must be a contiguous float32 [V,35] tensor")
         if self.tgt_buf is not None and (self.tgt_buf.shape != (V, 6, self.H, self.W) or not self.tgt_buf.is_contiguous()):
             raise L.HgsError("GraphedStrandBatch: tgt_buf must be a contiguous float32 [V,6,H,W] tensor")
-        self.plans = [LaunchPlan(capacity, depth_bits) for _ in range(V)]
+        key = (dev.index, int(model.endpoint_pairs.shape[0]), self.H, self.W, 7)
+        self.plans = [LaunchPlan(capacity, depth_bits, _dgr.sort_mode_for(key)) for _ in range(V)]
         lib = self.lib
         u8 = dict(dtype=torch.uint8, device=dev)
         # per-view workspaces and outputs, allocated once (outside any capture)
-        self.geom = [torch.empty(lib.hgs_geom_bytes(P, 7), **u8) for _ in range(V)]
+        self.geom = [torch.empty(lib.hgs_geom_bytes(P, 7, self.W, self.H), **u8) for _ in range(V)]
         self.img_ws = [torch.empty(lib.hgs_image_bytes(self.W, self.H), **u8) for _ in range(V)]
         self.binning = [torch.empty(lib.hgs_binning_bytes(int(capacity), 7), **u8) for _ in range(V)]
         self.image = [torch.empty(7, self.H, self.W, **f32) for _ in range(V)]
@@ -298,7 +308,7 @@ class GraphedStrandBatch:
         cd = self.cam_buf[v]
         prm = L.RasterParams(P=self.P, D=int(m.active_sh_degree), M=int(features.shape[1]), width=self.W, height=self.H,
                              channels=7, tan_fovx=self.tanfovx, tan_fovy=self.tanfovy, scale_modifier=1.0, prefiltered=0,
-                             debug=0, sort_depth_bits=int(self.plans[v].depth_bits))
+                             debug=0, sort_depth_bits=int(self.plans[v].depth_bits), sort_mode=int(self.plans[v].sort_mode))
         inp = L.StrandInputs(num_endpoints=int(m._endpoints.shape[0]), background=self.bg7.data_ptr(),
                              endpoints=m._endpoints.data_ptr(), endpoint_pairs=m.endpoint_pairs.data_ptr(),
                              width=m._width.data_ptr(), opacity_logit=m._opacity.data_ptr(), mask_logit=m._mask.data_ptr(),

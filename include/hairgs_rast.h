@@ -86,7 +86,17 @@ typedef struct hgs_raster_params {
                              * (hgs_forward_read_num_rendered words 3-4): a caller that enqueued stage B on a hint must
                              * check (depth_max - depth_min) >> sort_depth_bits == 0 and otherwise repeat stage B with 0
                              * (the device also raises bit 1 of the overflow word).  Only read by the stage-B entries. */
+    int32_t sort_mode;      /* HGS_SORT_TILE (0, default): instances are partitioned by tile first (per-tile counts, one
+                             * scatter) and every tile's list is sorted by (depth, id) inside shared memory by the kernel
+                             * that also packs the sorted records - two passes over the instances.  A tile list longer than
+                             * HGS_TILE_SORT_MAX raises bit 2 of the overflow word: repeat stage B with HGS_SORT_GLOBAL.
+                             * HGS_SORT_GLOBAL (1): stable radix sort of the 64-bit (tile | depth) keys, the reference's
+                             * formulation (rasterizer_impl.cu:300-308); sort_depth_bits applies to this mode only.
+                             * Both produce identical keys, point list, ranges and records. */
 } hgs_raster_params;
+#define HGS_SORT_TILE 0
+#define HGS_SORT_GLOBAL 1
+#define HGS_TILE_SORT_MAX 16384
 
 /* Device pointers of the per-Gaussian inputs (rasterizer.h:33-58 pointer arguments). */
 typedef struct hgs_raster_inputs {
@@ -164,7 +174,7 @@ int hgs_abi_version(void);
 const char* hgs_last_error(void);
 
 /* Workspace sizes in bytes (required<T>() of the reference).  binning: N = num_rendered. */
-size_t hgs_geom_bytes(int32_t P, int32_t channels);
+size_t hgs_geom_bytes(int32_t P, int32_t channels, int32_t width, int32_t height);  /* ABI v4: + per-tile counters */
 size_t hgs_image_bytes(int32_t width, int32_t height);
 size_t hgs_binning_bytes(int64_t num_rendered, int32_t channels);
 /* capacity a binning workspace of `bytes` bytes was sized for: num_rendered itself if it matches, else the
@@ -361,7 +371,11 @@ enum hgs_stage {
     HGS_STAGE_KNN = 8,
     HGS_STAGE_OTHER = 9,
     HGS_STAGE_TILE_SCAN = 10,
-    HGS_STAGE_COUNT = 11
+    HGS_STAGE_TILE_COUNT = 11,      /* (unused: the per-tile counts are taken by preprocess_fwd) */
+    HGS_STAGE_TILE_OFFSETS = 12,    /* tile ranges + processing order */
+    HGS_STAGE_TILE_SCATTER = 13,    /* instances to their tile's range */
+    HGS_STAGE_TILE_SORT_PACK = 14,  /* per-tile (depth, id) sort + sorted-order record packing (3 size classes) */
+    HGS_STAGE_COUNT = 15
 };
 /* Debug: when dev_ptr != NULL the forward compositor writes one uint4 per (tile, warp):
  * (chunks walked, cull candidates, blends summed over lanes, pixels terminated | list chunks << 8). */

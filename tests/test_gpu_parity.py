@@ -41,6 +41,20 @@ def blocks(request):
     assert lib.hgs_debug_set_composite_blocks(0) == 0
 
 
+@pytest.fixture(params=["tile", "global"])
+def sort_mode(request):
+    """Runs the test once per binning formulation: partition by tile + in-tile sort (default, csrc/tilesort.cu) and the
+    global radix sort of the (tile | depth) keys (the reference's formulation, csrc/binning.cu)."""
+    import diff_gaussian_rasterization._C as ours_C
+    from hairgs_b200 import _lib as L
+    saved = ours_C.DEFAULT_SORT_MODE
+    ours_C.DEFAULT_SORT_MODE = L.SORT_TILE if request.param == "tile" else L.SORT_GLOBAL
+    ours_C._sort_mode_hint.clear()
+    yield request.param
+    ours_C.DEFAULT_SORT_MODE = saved
+    ours_C._sort_mode_hint.clear()
+
+
 def need_ref():
     C = refload.ref_dgr()
     if C is None:
@@ -81,7 +95,7 @@ def assert_forward_equal(vo, vr, co, cr, ro, rr, d, No, Nr):
 
 
 @pytest.mark.parametrize("name", CASE_NAMES)
-def test_forward_and_backward_vs_reference(name, blocks):
+def test_forward_and_backward_vs_reference(name, blocks, sort_mode):
     C = need_ref()
     d = _cases()[name]()
     No, co, ro, bo, vo = common.ours_forward(d)
@@ -126,7 +140,7 @@ def _load_gold(path):
 
 @pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLD, "*.npz")) if "knn" not in p and "loss_ref" not in p and "pyref" not in p),
                          ids=lambda p: os.path.basename(p)[:-4])
-def test_golden_fixtures(path, blocks):
+def test_golden_fixtures(path, blocks, sort_mode):
     """No reference needed: the fixtures ARE the reference's outputs (generated by tests/golden/make_golden.py)."""
     import diff_gaussian_rasterization._C as ours_C
     d, z = _load_gold(path)
@@ -197,7 +211,7 @@ def test_empty_and_fully_culled():
 
 
 @pytest.mark.parametrize("P,W,H", [(1, 16, 16), (1, 1, 1), (7, 33, 17), (300, 2048, 16)])
-def test_tiny_and_odd_shapes(P, W, H, blocks):
+def test_tiny_and_odd_shapes(P, W, H, blocks, sort_mode):
     C = need_ref()
     d = common.blob_inputs(P, W, H, dev(), seed=30 + P, scale_mul=20.0)
     No, co, ro, bo, vo = common.ours_forward(d)
@@ -892,6 +906,7 @@ def test_sort_depth_range_compaction_paths():
     lib = L.load()
     d = common.blob_inputs(30000, 256, 256, dev(), seed=41)
     key = (0, 30000, 256, 256)
+    ours_C._sort_mode_hint[key] = L.SORT_GLOBAL      # the depth-range compaction belongs to the global radix sort
 
     def onesweep_launches(fn):
         lib.hgs_profile_collect(None, None)
@@ -900,7 +915,7 @@ def test_sort_depth_range_compaction_paths():
         ms, cnt = (ctypes.c_double * 16)(), (ctypes.c_int64 * 16)()
         lib.hgs_profile_collect(ms, cnt)
         lib.hgs_profile_enable(0)
-        names = [lib.hgs_stage_name(i).decode() for i in range(11)]
+        names = [lib.hgs_stage_name(i).decode() for i in range(15)]
         return out, cnt[names.index("sort_onesweep")]
 
     runs = []
@@ -924,6 +939,7 @@ def test_sort_depth_range_compaction_paths():
     assert runs[1][1] < full_passes                   # the hinted call sorted fewer digits
     assert runs[2][1] > runs[1][1]                    # the too-small hint cost a second stage B
     assert runs[2][2] == auto_hint                    # and did not poison the hint
+    ours_C._sort_mode_hint.pop(key, None)
     for ri, ((N, color, radii, _, v), _, _) in enumerate(runs[1:]):
         assert N == N0 and torch.equal(color, color0) and torch.equal(radii, radii0)
         for name in ("point_list_keys", "point_list", "ranges", "n_contrib"):
@@ -1147,3 +1163,54 @@ def test_graphed_batch_equals_sum_of_eager_views():
     small.cam_buf[1].copy_(flat(cams[1]))
     with pytest.raises(graphs.HgsPlanError):
         small.capture()
+
+
+def test_tile_sort_falls_back_to_the_global_sort_for_very_long_tile_lists():
+    """HGS_SORT_TILE sorts a tile's list inside shared memory: lists longer than HGS_TILE_SORT_MAX (16384) do not fit.  Stage
+    A counts the lists, raises bit 2 of the overflow word, and the pass is finished with the global radix sort - outputs
+    equal the reference's, and the scene is remembered as a global-sort scene."""
+    import diff_gaussian_rasterization._C as ours_C
+    from hairgs_b200 import _lib as L
+    C = need_ref()
+    ours_C._sort_mode_hint.clear()
+    P = 20000
+    d = common.blob_inputs(P, 64, 64, dev(), seed=77, scale_mul=0.2)
+    # every Gaussian in front of the camera, projected into the image centre: one tile list of ~P entries
+    cam_dir = -d["campos"] / d["campos"].norm()
+    g = torch.Generator().manual_seed(3)
+    d["means3D"] = (d["campos"] + cam_dir * 0.4)[None, :] + 1e-3 * torch.randn(P, 3, generator=g).to(dev())
+    d["means3D"] = d["means3D"].contiguous()
+    No, co, ro, bo, vo = common.ours_forward(d)
+    Nr, cr, rr, br, vr = common.ref_forward(d)
+    assert int((vr["ranges"][:, 1] - vr["ranges"][:, 0]).max()) > 16384       # the case really exceeds the in-tile limit
+    assert ours_C._sort_mode_hint.get((0, P, 64, 64)) == L.SORT_GLOBAL
+    assert_forward_equal(vo, vr, co, cr, ro, rr, d, No, Nr)
+    ours_C._sort_mode_hint.clear()
+
+
+def test_tile_sort_equals_global_sort_at_size():
+    """The two binning formulations on cfg3-sized strands (lists up to ~9 k entries) and on blobs: keys, point list, ranges,
+    n_contrib and pixels bit-identical."""
+    import diff_gaussian_rasterization._C as ours_C
+    from hairgs_b200 import _lib as L
+    saved = ours_C.DEFAULT_SORT_MODE
+    try:
+        for make in (lambda: common.strand_inputs(10000, 100, 1024, 1024, dev(), seed=0, view=5, n_views=16),
+                     lambda: common.blob_inputs(200000, 640, 400, dev(), seed=5, scale_mul=2.0)):
+            d = make()
+            outs = {}
+            for mode in (L.SORT_TILE, L.SORT_GLOBAL):
+                ours_C.DEFAULT_SORT_MODE = mode
+                ours_C._sort_mode_hint.clear()
+                ours_C._capacity_hint.clear()
+                for _ in range(2):       # first call sizes the workspace exactly, second runs sync-free on the hint
+                    N, c, r, b, v = common.ours_forward(d)
+                assert ours_C._sort_mode_hint == {}
+                outs[mode] = (N, c.clone(), r.clone(), {k: v[k].clone() for k in ("point_list_keys", "point_list", "ranges", "n_contrib", "accum_alpha")})
+            (N0, c0, r0, v0), (N1, c1, r1, v1) = outs[L.SORT_TILE], outs[L.SORT_GLOBAL]
+            assert N0 == N1 and torch.equal(r0, r1) and common.bits_equal(c0, c1) == 0
+            for k in v0:
+                assert common.bits_equal(v0[k], v1[k]) == 0, k
+    finally:
+        ours_C.DEFAULT_SORT_MODE = saved
+        ours_C._sort_mode_hint.clear()

@@ -29,16 +29,16 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(L.RasterParams) == 12 * 4
+    assert ctypes.sizeof(L.RasterParams) == 13 * 4
     assert ctypes.sizeof(L.RasterInputs) == 11 * 8
     assert ctypes.sizeof(L.RasterGrads) == 9 * 8
 
 
 def test_workspace_size_queries():
     lib = L.load()
-    assert lib.hgs_geom_bytes(0, 3) > 0
-    a, b = lib.hgs_geom_bytes(1000, 3), lib.hgs_geom_bytes(2000, 3)
-    assert b > a and lib.hgs_geom_bytes(1000, 7) > a
+    assert lib.hgs_geom_bytes(0, 3, 64, 64) > 0
+    a, b = lib.hgs_geom_bytes(1000, 3, 64, 64), lib.hgs_geom_bytes(2000, 3, 64, 64)
+    assert b > a and lib.hgs_geom_bytes(1000, 7, 64, 64) > a and lib.hgs_geom_bytes(1000, 3, 1024, 1024) > a
     assert lib.hgs_image_bytes(1024, 1024) >= 1024 * 1024 * 8 + 4096 * 8
     assert lib.hgs_binning_bytes(1 << 20, 3) >= (1 << 20) * 72
     assert lib.hgs_binning_bytes(0, 3) >= 0 and lib.hgs_sort_bytes(10) > 0 and lib.hgs_knn_bytes(100) > 0
@@ -199,9 +199,9 @@ def test_graph_replay_host_logic_without_gpu():
     with pytest.raises(L.HgsError, match="no CPU path"):
         graphs.GraphedStrandStep(m, None, torch.zeros(7), 32, 32, 1.0, 1.0, 4096, 32)
 
-    def plan(capacity, bits, n, overflow, dmax, dmin):
+    def plan(capacity, bits, n, overflow, dmax, dmin, sort_mode=L.SORT_GLOBAL):
         p = graphs.LaunchPlan.__new__(graphs.LaunchPlan)
-        p.capacity, p.depth_bits = capacity, bits
+        p.capacity, p.depth_bits, p.sort_mode = capacity, bits, sort_mode
         p.host = torch.tensor([n, 0, overflow, dmax, ~dmin, 0, 0, 0], dtype=torch.int64).to(torch.int32)
         return p
 
@@ -214,5 +214,10 @@ def test_graph_replay_host_logic_without_gpu():
         plan(1000, 24, 900, 0, hi, lo).check()
     with pytest.raises(graphs.HgsPlanError, match="int32"):
         plan(1000, 25, 900, 1, hi, lo).check()
+    # in-tile sort plans: the depth range is irrelevant, a tile list longer than HGS_TILE_SORT_MAX (bit 2) is not
+    assert plan(1000, 24, 900, 0, hi, lo, L.SORT_TILE).check() == 900
+    with pytest.raises(graphs.HgsPlanError, match="HGS_TILE_SORT_MAX"):
+        plan(1000, 32, 900, 4, hi, lo, L.SORT_TILE).check()
+    assert plan(1000, 32, 900, 4, hi, lo, L.SORT_GLOBAL).check() == 900
     assert issubclass(graphs.HgsPlanError, L.HgsError)
     assert fused.GradSink({}).accumulate is False
