@@ -76,7 +76,7 @@ int launch_composite_fwd(int, const ImageLayout&, const BinningLayout&, int, int
 int launch_composite_bwd(int, const ImageLayout&, const BinningLayout&, const uint32_t*, int, int, const float*,
                          const float*, const hgs_raster_grads*, cudaStream_t);
 int launch_tile_binning(int, int, int64_t, const GeomLayout&, const BinningLayout&, const ImageLayout&, uint32_t, uint32_t,
-                        cudaStream_t);
+                        uint32_t, int, cudaStream_t);
 int set_fwd_stats(void* dev_ptr);
 int set_composite_blocks(int mode);
 int launch_weighted_l1(int, long long, const float*, const float*, const float*, float*, float*, cudaStream_t);
@@ -211,7 +211,8 @@ static int stage_b_impl(const hgs_raster_params* prm, const float* background, v
 
     if ((parts & 1) && prm->sort_mode != HGS_SORT_GLOBAL) {
         // HGS_SORT_TILE: partition by tile + in-tile sort (tilesort.cu); the sorted pairs end in ping-pong buffer 0
-        if (int e = launch_tile_binning(N > 0 ? prm->P : 0, prm->channels, N, g, b, im, gx, gy, s)) return e;
+        if (int e = launch_tile_binning(N > 0 ? prm->P : 0, prm->channels, N, g, b, im, gx, gy, (uint32_t)prm->slice_base,
+                                        prm->slice_shift <= 0 ? 32 : prm->slice_shift, s)) return e;
         if (int e = stage_check("tile_binning", prm->debug, s)) return e;
     } else if (parts & 1) {
         // the unsorted pairs go into the ping-pong buffer from which the sort's passes end in buffer 0, whatever their number

@@ -67,7 +67,8 @@ static constexpr int kPreprocThreads = 256;
 struct GeomLayout {
     GeomHeader* hdr;
     unsigned long long* scan_state;  // [ceil(P/256)] chained-scan status words (directly after hdr: one memset clears both)
-    uint32_t* tile_count;     // [tiles] instances per tile, counted by preprocess_fwd (also inside the cleared region)
+    uint32_t* tile_count;     // [tiles * HGS_TILE_SLICES] instances per (tile, depth slice), counted by preprocess_fwd (also
+                              // inside the cleared region)
     float4* rec;              // [2P] : rec[2i] = GaussRecLo, rec[2i+1] = GaussRecHi
     float* rgb;               // [P*cstride] colours used by the compositors (SH result or repacked colors_precomp)
     float* depths;            // [P]
@@ -81,6 +82,13 @@ struct GeomLayout {
 };
 
 __host__ __device__ inline int color_stride(int channels) { return channels <= 4 ? 4 : 8; }
+// depth slice of an instance (HGS_SORT_TILE): monotone in the depth's bit pattern, so the slices of a tile list are ordered
+__host__ __device__ inline uint32_t depth_slice(uint32_t depth_bits, uint32_t base, int shift) {
+    if (shift >= 32) return 0u;
+    const uint32_t d = depth_bits > base ? depth_bits - base : 0u;
+    const uint32_t s = d >> shift;
+    return s < (uint32_t)HGS_TILE_SLICES ? s : (uint32_t)HGS_TILE_SLICES - 1u;
+}
 __host__ __device__ inline size_t tile_count_of(int width, int height) {
     return (size_t)((width + HGS_TILE - 1) / HGS_TILE) * (size_t)((height + HGS_TILE - 1) / HGS_TILE);
 }
@@ -94,7 +102,7 @@ __host__ __device__ inline GeomLayout carve_geom(void* base, int P, int channels
     g.cstride = color_stride(channels);
     g.hdr = (GeomHeader*)(p + off);            off = align_up(off + sizeof(GeomHeader));
     g.scan_state = (unsigned long long*)(p + off); off = align_up(off + nblk * 8);
-    g.tile_count = (uint32_t*)(p + off);       off = align_up(off + tiles * 4);
+    g.tile_count = (uint32_t*)(p + off);       off = align_up(off + tiles * HGS_TILE_SLICES * 4);
     g.clear_bytes = off;
     g.rec = (float4*)(p + off);                off = align_up(off + Pz * 32);
     g.rgb = (float*)(p + off);                 off = align_up(off + Pz * 4 * g.cstride);
@@ -112,7 +120,11 @@ struct ImageLayout {
     uint32_t* n_contrib;   // [H*W]
     uint2* ranges;         // [tiles]  (the reference over-allocates H*W entries, rasterizer_impl.cu:172-178)
     uint32_t* tile_order;  // [tiles]  tile ids, longest list first (CTA i composites tile_order[i])
-    uint32_t* tile_cursor; // [tiles]  scatter cursors (HGS_SORT_TILE)
+    // HGS_SORT_TILE (tilesort.cu): per (tile, slice) list start, scatter cursor, and the work lists of the three size classes
+    uint32_t* list_start;  // [tiles * S]
+    uint32_t* list_cursor; // [tiles * S]  (zeroed per pass together with work_count, which follows it)
+    uint32_t* work_count;  // [8]  entries of the three work lists [0..2], claim counters of the sort kernels [4..6]
+    uint32_t* work;        // [3][tiles * S]  non-empty lists by size class
     size_t bytes;
 };
 
@@ -126,7 +138,10 @@ __host__ __device__ inline ImageLayout carve_image(void* base, int W, int H) {
     im.n_contrib = (uint32_t*)(p + off); off = align_up(off + hw * 4);
     im.ranges = (uint2*)(p + off);       off = align_up(off + tiles * 8);
     im.tile_order = (uint32_t*)(p + off); off = align_up(off + tiles * 4);
-    im.tile_cursor = (uint32_t*)(p + off); off = align_up(off + tiles * 4);
+    im.list_start = (uint32_t*)(p + off);  off = align_up(off + tiles * HGS_TILE_SLICES * 4);
+    im.list_cursor = (uint32_t*)(p + off); off += tiles * HGS_TILE_SLICES * 4;
+    im.work_count = (uint32_t*)(p + off);  off = align_up(off + 8 * 4);
+    im.work = (uint32_t*)(p + off);        off = align_up(off + 3 * tiles * HGS_TILE_SLICES * 4);
     im.bytes = off;
     return im;
 }

@@ -38,6 +38,8 @@ struct PreArgs {
     int32_t* radii;
     GeomLayout g;
     uint32_t nblocks;
+    uint32_t slice_base;         // depth-slice hints of the tile-partitioned binning (hgs_raster_params.slice_base / _shift)
+    int slice_shift;
     // strand-aligned entry (kStrand): Gaussians derived from segment end points (scene/hair_gaussian_model.py:134-206)
     const float* endpoints;      // [E,3]
     const long long* pairs;      // [P,2]
@@ -259,6 +261,8 @@ __global__ void __launch_bounds__(kPreprocThreads, 6) preprocess_fwd_kernel(cons
 
     uint32_t touched = 0;
     int radius_i = 0;
+    uint2 vis_rmin = make_uint2(0, 0), vis_rmax = make_uint2(0, 0);
+    uint32_t vis_slice = 0;
     if (idx < a.P) {
         // start every input stream now: the cull / degenerate early-outs below would otherwise serialise them
         if (kStrand) {
@@ -355,18 +359,37 @@ __global__ void __launch_bounds__(kPreprocThreads, 6) preprocess_fwd_kernel(cons
             a.g.rec[2 * (size_t)idx + 1] = make_float4(conic.z, opacity, ext.x, ext.y);
             touched = (rmax.y - rmin.y) * (rmax.x - rmin.x);
             a.g.rects[idx] = make_uint2(rmin.x | (rmin.y << 16), rmax.x | (rmax.y << 16));
-            // per-tile instance counts for the tile-partitioned binning (tilesort.cu): the tile ranges fall out of these
-            // counters, and the longest list is known before stage B is verified (bit 2 of the overflow word)
-            bool too_long = false;
-            for (uint32_t ty = rmin.y; ty < rmax.y; ++ty)
-                for (uint32_t tx = rmin.x; tx < rmax.x; ++tx)
-                    too_long |= atomicAdd(&a.g.tile_count[ty * a.grid_x + tx], 1u) >= (uint32_t)HGS_TILE_SORT_MAX;
-            if (too_long) atomicOr(&a.g.hdr->overflow, 4u);
+            vis_rmin = rmin;
+            vis_rmax = rmax;
+            vis_slice = depth_slice(__float_as_uint(p_view.z), a.slice_base, a.slice_shift);
         } while (false);
         if (a.radii) a.radii[idx] = radius_i;
         a.g.tiles_touched[idx] = touched;
     }
-
+    // ---- instances per (tile, depth slice) for the tile-partitioned binning (tilesort.cu): the tile ranges fall out of these
+    // counters.  Warp-aggregated: neighbouring lanes hold neighbouring segments of a strand, which mostly share their tile -
+    // one atomic per distinct list and trip instead of one per lane (a hot tile takes ~9 k instances at cfg3, and atomics on
+    // one address serialise in L2).  The whole warp takes part in every trip (the loop bound is the warp's largest rect).
+    {
+        const uint32_t lane = threadIdx.x & 31;
+        const uint32_t w = vis_rmax.x - vis_rmin.x;
+        const uint32_t trips = __reduce_max_sync(0xffffffffu, touched);
+        bool too_long = false;
+        for (uint32_t k = 0; k < trips; ++k) {
+            const bool has = k < touched;
+            uint32_t list = 0xffffffffu;
+            if (has) {
+                const uint32_t ky = k / w, kx = k - ky * w;
+                list = ((vis_rmin.y + ky) * a.grid_x + vis_rmin.x + kx) * (uint32_t)HGS_TILE_SLICES + vis_slice;
+            }
+            const uint32_t peers = __match_any_sync(0xffffffffu, list);
+            if (has && lane == (uint32_t)(__ffs(peers) - 1)) {
+                const uint32_t cnt = __popc(peers);
+                too_long |= atomicAdd(&a.g.tile_count[list], cnt) + cnt > (uint32_t)HGS_TILE_SORT_MAX;
+            }
+        }
+        if (too_long) atomicOr(&a.g.hdr->overflow, 4u);   // bit 2: a list does not fit the in-tile sort
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1022,6 +1045,7 @@ int launch_preprocess_fwd(const hgs_raster_params* prm, const hgs_raster_inputs*
     a.viewmatrix = in->viewmatrix; a.projmatrix = in->projmatrix; a.cam_pos = in->cam_pos;
     a.radii = radii; a.g = g;
     a.nblocks = (prm->P + kPreprocThreads - 1) / kPreprocThreads;
+    a.slice_base = (uint32_t)prm->slice_base; a.slice_shift = prm->slice_shift <= 0 ? 32 : prm->slice_shift;
     a.endpoints = nullptr; a.pairs = nullptr; a.width = nullptr; a.opacity_logit = nullptr; a.mask_logit = nullptr;
     if (int e = check_cuda(cudaMemsetAsync(g.hdr, 0, g.clear_bytes, s), "memset geom header")) return e;
     {
@@ -1048,6 +1072,7 @@ int launch_strand_preprocess_fwd(const hgs_raster_params* prm, const hgs_strand_
     a.viewmatrix = in->viewmatrix; a.projmatrix = in->projmatrix; a.cam_pos = in->cam_pos;
     a.radii = radii; a.g = g;
     a.nblocks = (prm->P + kPreprocThreads - 1) / kPreprocThreads;
+    a.slice_base = (uint32_t)prm->slice_base; a.slice_shift = prm->slice_shift <= 0 ? 32 : prm->slice_shift;
     a.endpoints = in->endpoints; a.pairs = (const long long*)in->endpoint_pairs; a.width = in->width;
     a.opacity_logit = in->opacity_logit; a.mask_logit = in->mask_logit;
     if (int e = check_cuda(cudaMemsetAsync(g.hdr, 0, g.clear_bytes, s), "memset geom header")) return e;

@@ -24,6 +24,26 @@ DEFAULT_SORT_MODE = L.SORT_GLOBAL if __import__("os").environ.get("HGS_SORT_MODE
 
 def sort_mode_for(key):
     return _sort_mode_hint.get(key, DEFAULT_SORT_MODE)
+
+
+_slice_hint = {}        # (device, P, H, W) -> (smallest, largest) depth bit pattern seen: depth slices of the tile lists
+
+
+def slice_params(key):
+    """(slice_base, slice_shift) of hgs_raster_params for this scene: HGS_TILE_SLICES slices over the depth range of the views
+    seen so far; (0, 0) = no hint yet (everything in slice 0).  Pure performance hints - any values give the same output."""
+    lo_hi = _slice_hint.get(key)
+    if lo_hi is None:
+        return 0, 0
+    lo, hi = lo_hi
+    return int(lo), max((int(hi - lo)).bit_length() - (L.TILE_SLICES.bit_length() - 1), 1)
+
+
+def note_depth_range(key, host):
+    dmax, dmin = int(host[3]) & 0xffffffff, (~int(host[4])) & 0xffffffff
+    if dmax >= dmin and dmax < 0x7f800000:
+        old = _slice_hint.get(key)
+        _slice_hint[key] = (dmin, dmax) if old is None else (min(old[0], dmin), max(old[1], dmax))
 _pinned_pool = []
 _pinned_next = 0
 
@@ -102,6 +122,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                                 cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
                                 image_width, sh, degree, campos, prefiltered, debug)
     P, H, W, C = prm.P, prm.height, prm.width, prm.channels
+    prm.slice_base, prm.slice_shift = slice_params((dev.index, P, H, W))
     with torch.cuda.device(dev):
         stream = L.stream_ptr(dev)
         u8 = dict(dtype=torch.uint8, device=dev)
@@ -139,6 +160,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         if (overflow & 1) != 0 or N < 0:
             raise L.HgsError("instance count overflows int32")
         need = _depth_range_bits(host)
+        note_depth_range(key, host)
         if overflow & 4:
             _sort_mode_hint[key] = L.SORT_GLOBAL    # a tile list is longer than HGS_TILE_SORT_MAX (counted in stage A)
         if prm.sort_mode == L.SORT_TILE:

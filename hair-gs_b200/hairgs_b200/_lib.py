@@ -24,9 +24,10 @@ class RasterParams(ctypes.Structure):
     _fields_ = [("P", c_int32), ("D", c_int32), ("M", c_int32), ("width", c_int32), ("height", c_int32),
                 ("channels", c_int32), ("tan_fovx", c_float), ("tan_fovy", c_float),
                 ("scale_modifier", c_float), ("prefiltered", c_int32), ("debug", c_int32),
-                ("sort_depth_bits", c_int32), ("sort_mode", c_int32)]
+                ("sort_depth_bits", c_int32), ("sort_mode", c_int32), ("slice_base", c_int32), ("slice_shift", c_int32)]
 
 SORT_TILE, SORT_GLOBAL = 0, 1
+TILE_SLICES = 16
 
 
 class RasterInputs(ctypes.Structure):

@@ -50,6 +50,11 @@ def strands_forward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit,
     dev, prm, inp, keep = _prep(endpoints, endpoint_pairs, width, opacity_logit, mask_logit, features, settings)
     P, H, W = prm.P, prm.height, prm.width
     u8 = dict(dtype=torch.uint8, device=dev)
+    plan = settings.get("plan")
+    if plan is not None:
+        prm.slice_base, prm.slice_shift = plan.slice_base, plan.slice_shift
+    else:
+        prm.slice_base, prm.slice_shift = _dgr.slice_params((dev.index, P, H, W, 7))
     with torch.cuda.device(dev):
         stream = L.stream_ptr(dev)
         image = torch.empty((7, H, W), dtype=torch.float32, device=dev)
@@ -58,7 +63,6 @@ def strands_forward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit,
         img = torch.empty((lib.hgs_image_bytes(W, H),), **u8)
         L.check(lib.hgs_strands_forward_stage_a(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
                                                 radii.data_ptr(), stream), "strands stage A")
-        plan = settings.get("plan")
         if plan is not None:
             # fixed launch plan (hairgs_b200.graphs): no host synchronisation and no host-side decision depends on
             # this view's instance count, so the whole pass can be captured in a CUDA graph.  The count, the
@@ -93,6 +97,7 @@ def strands_forward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit,
         if (overflow & 1) != 0 or N < 0:
             raise L.HgsError("instance count overflows int32")
         need = _dgr._depth_range_bits(host)
+        _dgr.note_depth_range(key, host)
         if overflow & 4:
             _dgr._sort_mode_hint[key] = L.SORT_GLOBAL   # a tile list is longer than HGS_TILE_SORT_MAX (counted in stage A)
         if prm.sort_mode == L.SORT_TILE:

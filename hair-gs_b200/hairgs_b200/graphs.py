@@ -35,8 +35,9 @@ class LaunchPlan:
     """Fixed launch plan of the strand forward: capacity of the binning workspace (instances) and the sort's depth bits.
     `host` is the pinned read-back target of hgs_forward_read_num_rendered."""
 
-    def __init__(self, capacity, depth_bits, sort_mode=None):
+    def __init__(self, capacity, depth_bits, sort_mode=None, slices=(0, 0)):
         self.capacity, self.depth_bits = int(capacity), int(depth_bits)
+        self.slice_base, self.slice_shift = int(slices[0]), int(slices[1])   # depth-slice hints of the in-tile sort
         # binning formulation of the captured view: in-tile sort unless a view of this scene had a tile list longer than
         # HGS_TILE_SORT_MAX (diff_gaussian_rasterization._C._sort_mode_hint, filled by the eager passes of measure_plan)
         self.sort_mode = int(_dgr.DEFAULT_SORT_MODE if sort_mode is None else sort_mode)
@@ -130,7 +131,7 @@ class GraphedStrandStep:
                 raise L.HgsError("GraphedStrandStep: slot buffers must be float32 [35] and contiguous [6,H,W] on the model's "
                                  "device")
         key = (dev.index, int(model.endpoint_pairs.shape[0]), self.H, self.W, 7)
-        self.plans = [LaunchPlan(capacity, depth_bits, _dgr.sort_mode_for(key)) for _ in range(slots)]
+        self.plans = [LaunchPlan(capacity, depth_bits, _dgr.sort_mode_for(key), _dgr.slice_params(key)) for _ in range(slots)]
         self.done = [None] * slots          # event after the slot's last replay
         self.graphs, self.loss, self.terms = [], [], []
         self.mean2d_grad, self.radii, self.image = [None] * slots, [None] * slots, [None] * slots  # static outputs
@@ -285,7 +286,7 @@ class GraphedStrandBatch:
         if self.tgt_buf is not None and (self.tgt_buf.shape != (V, 6, self.H, self.W) or not self.tgt_buf.is_contiguous()):
             raise L.HgsError("GraphedStrandBatch: tgt_buf must be a contiguous float32 [V,6,H,W] tensor")
         key = (dev.index, int(model.endpoint_pairs.shape[0]), self.H, self.W, 7)
-        self.plans = [LaunchPlan(capacity, depth_bits, _dgr.sort_mode_for(key)) for _ in range(V)]
+        self.plans = [LaunchPlan(capacity, depth_bits, _dgr.sort_mode_for(key), _dgr.slice_params(key)) for _ in range(V)]
         lib = self.lib
         u8 = dict(dtype=torch.uint8, device=dev)
         # per-view workspaces and outputs, allocated once (outside any capture)
@@ -308,7 +309,8 @@ class GraphedStrandBatch:
         cd = self.cam_buf[v]
         prm = L.RasterParams(P=self.P, D=int(m.active_sh_degree), M=int(features.shape[1]), width=self.W, height=self.H,
                              channels=7, tan_fovx=self.tanfovx, tan_fovy=self.tanfovy, scale_modifier=1.0, prefiltered=0,
-                             debug=0, sort_depth_bits=int(self.plans[v].depth_bits), sort_mode=int(self.plans[v].sort_mode))
+                             debug=0, sort_depth_bits=int(self.plans[v].depth_bits), sort_mode=int(self.plans[v].sort_mode),
+                             slice_base=int(self.plans[v].slice_base), slice_shift=int(self.plans[v].slice_shift))
         inp = L.StrandInputs(num_endpoints=int(m._endpoints.shape[0]), background=self.bg7.data_ptr(),
                              endpoints=m._endpoints.data_ptr(), endpoint_pairs=m.endpoint_pairs.data_ptr(),
                              width=m._width.data_ptr(), opacity_logit=m._opacity.data_ptr(), mask_logit=m._mask.data_ptr(),

@@ -50,6 +50,7 @@ def sort_mode(request):
     saved = ours_C.DEFAULT_SORT_MODE
     ours_C.DEFAULT_SORT_MODE = L.SORT_TILE if request.param == "tile" else L.SORT_GLOBAL
     ours_C._sort_mode_hint.clear()
+    ours_C._slice_hint.clear()
     yield request.param
     ours_C.DEFAULT_SORT_MODE = saved
     ours_C._sort_mode_hint.clear()
@@ -1173,6 +1174,7 @@ def test_tile_sort_falls_back_to_the_global_sort_for_very_long_tile_lists():
     from hairgs_b200 import _lib as L
     C = need_ref()
     ours_C._sort_mode_hint.clear()
+    ours_C._slice_hint.clear()
     P = 20000
     d = common.blob_inputs(P, 64, 64, dev(), seed=77, scale_mul=0.2)
     # every Gaussian in front of the camera, projected into the image centre: one tile list of ~P entries
@@ -1203,7 +1205,8 @@ def test_tile_sort_equals_global_sort_at_size():
                 ours_C.DEFAULT_SORT_MODE = mode
                 ours_C._sort_mode_hint.clear()
                 ours_C._capacity_hint.clear()
-                for _ in range(2):       # first call sizes the workspace exactly, second runs sync-free on the hint
+                ours_C._slice_hint.clear()
+                for _ in range(2):       # first call: exact workspace, no depth-slice hints; second: sync-free on the hints
                     N, c, r, b, v = common.ours_forward(d)
                 assert ours_C._sort_mode_hint == {}
                 outs[mode] = (N, c.clone(), r.clone(), {k: v[k].clone() for k in ("point_list_keys", "point_list", "ranges", "n_contrib", "accum_alpha")})

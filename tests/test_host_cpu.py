@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(L.RasterParams) == 13 * 4
+    assert ctypes.sizeof(L.RasterParams) == 15 * 4
     assert ctypes.sizeof(L.RasterInputs) == 11 * 8
     assert ctypes.sizeof(L.RasterGrads) == 9 * 8
 
