@@ -81,8 +81,9 @@ __global__ void __launch_bounds__(kOffThreads) tile_offsets_kernel(uint32_t tile
         if (t < tiles) {
             // the reference clears the ranges and writes the non-empty tiles only (rasterizer_impl.cu:116-138,310); a
             // binning workspace that is too small (sync-free guess) truncates the lists instead of overrunning it
-            ranges[t] = c ? make_uint2(min(start, capacity), min(start + c, capacity)) : make_uint2(0u, 0u);
-            atomicAdd(&s_count[c ? __clz(c) : 32], 1u);
+            const uint2 r = c ? make_uint2(min(start, capacity), min(start + c, capacity)) : make_uint2(0u, 0u);
+            ranges[t] = r;
+            atomicAdd(&s_count[r.y > r.x ? __clz(r.y - r.x) : 32], 1u);   // same (clamped) length as the ordering pass below
             uint32_t run = start;
 #pragma unroll
             for (int q = 0; q < S; ++q) {
@@ -211,9 +212,12 @@ __global__ void __launch_bounds__(kThreads) tile_sort_pack_kernel(
         const uint32_t item = s_item;
         if (item >= n_work) return;
         const uint32_t list = work[item];
-        const uint32_t n = list_count[list];
         const uint32_t start = list_start[list];
-        if (n > (uint32_t)HGS_TILE_SORT_MAX || start >= capacity || start + n > capacity) continue;  // stage B will be repeated
+        if (start >= capacity) continue;
+        // A binning workspace that is too small (sync-free guess) or a list that is too long: the caller repeats stage B, but
+        // what is inside the workspace must still be valid records - the first slots of the list are all filled (the cursor
+        // hands out every slot once), so the part that fits is sorted and packed.
+        const uint32_t n = min(min(list_count[list], capacity - start), (uint32_t)HGS_TILE_SORT_MAX);
         uint32_t npad = 2;
         while (npad < n) npad <<= 1;
         for (uint32_t i = tid; i < npad; i += kThreads) s[i] = i < n ? bucket[start + i] : ~0ull;

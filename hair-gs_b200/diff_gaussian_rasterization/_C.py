@@ -18,8 +18,10 @@ SYNC_FREE = True        # False: size the binning workspace exactly, after a blo
 _capacity_hint = {}     # (device, P, H, W) -> instance capacity to try first
 _depth_bits_hint = {}   # (device, P, H, W) -> sort_depth_bits to try first (depth-range compaction of the sort keys)
 _sort_mode_hint = {}    # (device, P, H, W) -> L.SORT_GLOBAL once a view had a tile list too long for the in-tile sort
-# HGS_SORT_MODE=global|tile: binning formulation tried first (A/B measurements); default tile (csrc/tilesort.cu)
-DEFAULT_SORT_MODE = L.SORT_GLOBAL if __import__("os").environ.get("HGS_SORT_MODE", "tile") == "global" else L.SORT_TILE
+# HGS_SORT_MODE=global|tile: binning formulation.  Default: the global radix sort.  The tile-partitioned formulation
+# (csrc/tilesort.cu) is bit-identical and fully tested but measured SLOWER on B200 (profiles/r2_tilesort.md): sorting the
+# lists with a shared-memory bitonic network costs more than the five one-wave radix passes it replaces.
+DEFAULT_SORT_MODE = L.SORT_TILE if __import__("os").environ.get("HGS_SORT_MODE", "global") == "tile" else L.SORT_GLOBAL
 
 
 def sort_mode_for(key):
@@ -161,8 +163,10 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
             raise L.HgsError("instance count overflows int32")
         need = _depth_range_bits(host)
         note_depth_range(key, host)
-        if overflow & 4:
-            _sort_mode_hint[key] = L.SORT_GLOBAL    # a tile list is longer than HGS_TILE_SORT_MAX (counted in stage A)
+        if (overflow & 4) and prm.slice_shift > 0:
+            # a (tile, slice) list is longer than HGS_TILE_SORT_MAX (counted in stage A) although the depth slices were in
+            # effect: this scene is a global-sort scene from now on (without slice hints - first view - only this pass is)
+            _sort_mode_hint[key] = L.SORT_GLOBAL
         if prm.sort_mode == L.SORT_TILE:
             fits = (overflow & 4) == 0
         else:
@@ -173,7 +177,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                 cap_b = N
             else:
                 cap_b = cap
-            prm.sort_mode = sort_mode_for(key)
+            prm.sort_mode = L.SORT_GLOBAL if (overflow & 4) else sort_mode_for(key)
             prm.sort_depth_bits = _next_depth_bits(H, W, need) if SYNC_FREE else 0
             L.check(lib.hgs_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
                                             binning.data_ptr() if cap_b > 0 else None, img.data_ptr(), cap_b,

@@ -98,8 +98,8 @@ def strands_forward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit,
             raise L.HgsError("instance count overflows int32")
         need = _dgr._depth_range_bits(host)
         _dgr.note_depth_range(key, host)
-        if overflow & 4:
-            _dgr._sort_mode_hint[key] = L.SORT_GLOBAL   # a tile list is longer than HGS_TILE_SORT_MAX (counted in stage A)
+        if (overflow & 4) and prm.slice_shift > 0:
+            _dgr._sort_mode_hint[key] = L.SORT_GLOBAL   # see diff_gaussian_rasterization._C.rasterize_gaussians
         if prm.sort_mode == L.SORT_TILE:
             fits = (overflow & 4) == 0
         else:
@@ -108,7 +108,7 @@ def strands_forward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit,
             if cap is None or N > cap:
                 cap = N
                 binning = torch.empty((lib.hgs_binning_bytes(N, 7),), **u8)
-            prm.sort_mode = _dgr.sort_mode_for(key)
+            prm.sort_mode = L.SORT_GLOBAL if (overflow & 4) else _dgr.sort_mode_for(key)
             prm.sort_depth_bits = _dgr._next_depth_bits(H, W, need) if _dgr.SYNC_FREE else 0
             L.check(lib.hgs_strands_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
                                                     binning.data_ptr() if cap > 0 else None, img.data_ptr(), cap,

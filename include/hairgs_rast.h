@@ -86,12 +86,13 @@ typedef struct hgs_raster_params {
                              * (hgs_forward_read_num_rendered words 3-4): a caller that enqueued stage B on a hint must
                              * check (depth_max - depth_min) >> sort_depth_bits == 0 and otherwise repeat stage B with 0
                              * (the device also raises bit 1 of the overflow word).  Only read by the stage-B entries. */
-    int32_t sort_mode;      /* HGS_SORT_TILE (0, default): instances are partitioned by (tile, depth slice) first (counts taken
+    int32_t sort_mode;      /* HGS_SORT_TILE (0): instances are partitioned by (tile, depth slice) first (counts taken
                              * by the preprocess, one scatter) and every list is sorted by (depth, id) inside shared memory by
                              * the kernel that also packs the sorted records - two passes over the instances.  A list longer
                              * than HGS_TILE_SORT_MAX raises bit 2 of the overflow word in stage A: run stage B with HGS_SORT_GLOBAL.
                              * HGS_SORT_GLOBAL (1): stable radix sort of the 64-bit (tile | depth) keys, the reference's
-                             * formulation (rasterizer_impl.cu:300-308); sort_depth_bits applies to this mode only.
+                             * formulation (rasterizer_impl.cu:300-308); sort_depth_bits applies to this mode only.  This is
+                             * what the Python packages select by default (measured faster on B200, profiles/r2_tilesort.md).
                              * Both produce identical keys, point list, ranges and records. */
     int32_t slice_base;     /* HGS_SORT_TILE only, performance hints (any values are CORRECT): every tile list is split into */
     int32_t slice_shift;    /* HGS_TILE_SLICES depth slices, slice = clamp((depth_bits - slice_base) >> slice_shift, 0, S-1),

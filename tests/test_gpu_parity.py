@@ -1185,6 +1185,14 @@ def test_tile_sort_falls_back_to_the_global_sort_for_very_long_tile_lists():
     No, co, ro, bo, vo = common.ours_forward(d)
     Nr, cr, rr, br, vr = common.ref_forward(d)
     assert int((vr["ranges"][:, 1] - vr["ranges"][:, 0]).max()) > 16384       # the case really exceeds the in-tile limit
+    assert_forward_equal(vo, vr, co, cr, ro, rr, d, No, Nr)
+    # second view of the scene: the depth slices are in effect now, and all P Gaussians sit within 3 mm of depth -> one
+    # slice still takes more than HGS_TILE_SORT_MAX: the scene is remembered as a global-sort scene, outputs unchanged
+    d["means3D"] = ((d["campos"] + cam_dir * 0.4)[None, :] + 1e-6 * torch.randn(P, 3, generator=g).to(dev())).contiguous()
+    No, co, ro, bo, vo = common.ours_forward(d)
+    Nr, cr, rr, br, vr = common.ref_forward(d)
+    assert_forward_equal(vo, vr, co, cr, ro, rr, d, No, Nr)
+    No, co, ro, bo, vo = common.ours_forward(d)
     assert ours_C._sort_mode_hint.get((0, P, 64, 64)) == L.SORT_GLOBAL
     assert_forward_equal(vo, vr, co, cr, ro, rr, d, No, Nr)
     ours_C._sort_mode_hint.clear()
@@ -1208,7 +1216,7 @@ def test_tile_sort_equals_global_sort_at_size():
                 ours_C._slice_hint.clear()
                 for _ in range(2):       # first call: exact workspace, no depth-slice hints; second: sync-free on the hints
                     N, c, r, b, v = common.ours_forward(d)
-                assert ours_C._sort_mode_hint == {}
+                assert ours_C._sort_mode_hint == {}     # with depth slices every list fits the in-tile sort
                 outs[mode] = (N, c.clone(), r.clone(), {k: v[k].clone() for k in ("point_list_keys", "point_list", "ranges", "n_contrib", "accum_alpha")})
             (N0, c0, r0, v0), (N1, c1, r1, v1) = outs[L.SORT_TILE], outs[L.SORT_GLOBAL]
             assert N0 == N1 and torch.equal(r0, r1) and common.bits_equal(c0, c1) == 0
