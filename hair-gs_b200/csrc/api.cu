@@ -74,7 +74,7 @@ int launch_finalize_sorted(int, int64_t, const uint32_t*, const uint64_t*, const
                            uint32_t*, size_t, cudaStream_t);
 int launch_composite_fwd(int, const ImageLayout&, const BinningLayout&, int, int, const float*, float*, cudaStream_t);
 int launch_composite_bwd(int, const ImageLayout&, const BinningLayout&, const uint32_t*, int, int, const float*,
-                         const float*, const hgs_raster_grads*, cudaStream_t);
+                         const float*, const hgs_raster_grads*, float*, cudaStream_t);
 int launch_tile_binning(int, int, int64_t, const GeomLayout&, const BinningLayout&, const ImageLayout&, uint32_t, uint32_t,
                         uint32_t, int, cudaStream_t);
 int set_fwd_stats(void* dev_ptr);
@@ -297,8 +297,9 @@ int hgs_strands_backward(const hgs_raster_params* prm, const hgs_strand_inputs* 
                          void* stream) {
     if (int e = validate_strands(prm, in)) return e;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!gr || !gr->dL_dmean2D || !gr->dL_dconic || !gr->dL_dopacity || !gr->dL_dcolor || !gr->dL_dendpoints ||
-        !gr->dL_dwidth || !gr->dL_dopacity_logit || !gr->dL_dmask_logit || !gr->dL_dfeatures) { set_error("missing gradient output pointer"); return HGS_ERR_INVALID; }
+    if (!gr || !gr->dL_dmean2D || !gr->dL_dendpoints || !gr->dL_dwidth || !gr->dL_dopacity_logit || !gr->dL_dmask_logit ||
+        !gr->dL_dfeatures || (!gr->acc16 && (!gr->dL_dconic || !gr->dL_dopacity || !gr->dL_dcolor))) { set_error("missing gradient output pointer"); return HGS_ERR_INVALID; }
+    if (gr->acc16 && ((uintptr_t)gr->acc16 & 15)) { set_error("acc16 must be 16-byte aligned"); return HGS_ERR_INVALID; }
     if (!geom_ws || !image_ws || !dL_dpix || (R > 0 && !binning_ws)) { set_error("null workspace"); return HGS_ERR_INVALID; }
     const int P = prm->P;
     if (!gr->accumulate)
@@ -309,7 +310,9 @@ int hgs_strands_backward(const hgs_raster_params* prm, const hgs_strand_inputs* 
     BinningLayout b = carve_binning((void*)binning_ws, R, prm->channels);
     const int res = 0;  // the sorted pairs always end in ping-pong buffer 0 (stage_b_impl)
     const size_t Pz = (size_t)P;
-    if (gr->dL_dconic == gr->dL_dmean2D + 3 * Pz && gr->dL_dopacity == gr->dL_dconic + 4 * Pz &&
+    if (gr->acc16) {
+        if (int e = check_cuda(cudaMemsetAsync(gr->acc16, 0, Pz * 16 * 4, s), "memset acc16")) return e;
+    } else if (gr->dL_dconic == gr->dL_dmean2D + 3 * Pz && gr->dL_dopacity == gr->dL_dconic + 4 * Pz &&
         gr->dL_dcolor == gr->dL_dopacity + Pz) {
         if (int e = check_cuda(cudaMemsetAsync(gr->dL_dmean2D, 0, Pz * (8 + 7) * 4, s), "memset grads")) return e;
     } else {
@@ -322,7 +325,7 @@ int hgs_strands_backward(const hgs_raster_params* prm, const hgs_strand_inputs* 
         hgs_raster_grads rg;
         memset(&rg, 0, sizeof(rg));
         rg.dL_dmean2D = gr->dL_dmean2D; rg.dL_dconic = gr->dL_dconic; rg.dL_dopacity = gr->dL_dopacity; rg.dL_dcolor = gr->dL_dcolor;
-        if (int e = launch_composite_bwd(7, im, b, b.vals[res], prm->width, prm->height, in->background, dL_dpix, &rg, s)) return e;
+        if (int e = launch_composite_bwd(7, im, b, b.vals[res], prm->width, prm->height, in->background, dL_dpix, &rg, gr->acc16, s)) return e;
         if (int e = stage_check("composite_bwd", prm->debug, s)) return e;
     }
     if (int e = launch_strand_preprocess_bwd(prm, in, g, gr, s)) return e;
@@ -403,7 +406,7 @@ int hgs_rasterize_backward(const hgs_raster_params* prm, const hgs_raster_inputs
     }
     if (R > 0) {
         if (int e = launch_composite_bwd(prm->channels, im, b, b.vals[res], prm->width, prm->height, in->background,
-                                         dL_dpix, gr, s)) return e;
+                                         dL_dpix, gr, nullptr, s)) return e;
         if (int e = stage_check("composite_bwd", prm->debug, s)) return e;
     }
     if (int e = launch_preprocess_bwd(prm, in, g, radii, gr, s)) return e;

@@ -806,7 +806,14 @@ struct BwdHalfSmem {
     uint32_t vmask[GR];             // bits 0-15: pixels of half A that candidate g of half A reached; 16-31: half B
 };
 
-template <int C, int CS>
+// 16-byte vector reduction (sm_90+): one L2 atomic transaction for four floats of one record
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// kVec: gradients accumulate into ONE interleaved 64-byte record per Gaussian (hgs_strand_grads.acc16, passed in
+// dL_dmean2D) with four red.global.add.v4.f32 instead of 6 + C scalar atomics.
+template <int C, int CS, bool kVec>
 __global__ void __launch_bounds__(256, 3) composite_bwd_half_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
     const uint32_t* __restrict__ point_list, int W, int H,
@@ -969,7 +976,17 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_half_kernel(
         }
 #pragma unroll
         for (int k = 0; k < 6 + C; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
-        if (my_o == 0 && my_vm != 0) {
+        if (kVec && my_o == 0 && my_vm != 0) {
+            const uint32_t gid = __float_as_uint(my_hi[slot].w);
+            float* rec16 = dL_dmean2D + 16 * (size_t)gid;
+            float col[8];
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) col[ch] = ch < C ? acc[6 + ch] : 0.f;
+            red_add_v4(rec16, acc[0] * ddelx_dx, acc[1] * ddely_dy, acc[5], 0.f);
+            red_add_v4(rec16 + 4, -0.5f * acc[2], -0.5f * acc[3], 0.f, -0.5f * acc[4]);
+            red_add_v4(rec16 + 8, col[0], col[1], col[2], col[3]);
+            if (C > 4) red_add_v4(rec16 + 12, col[4], col[5], col[6], col[7]);
+        } else if (my_o == 0 && my_vm != 0) {
             const uint32_t gid = __float_as_uint(my_hi[slot].w);
             atomicAdd(dL_dmean2D + 3 * (size_t)gid, acc[0] * ddelx_dx);
             atomicAdd(dL_dmean2D + 3 * (size_t)gid + 1, acc[1] * ddely_dy);
@@ -1172,7 +1189,7 @@ int launch_composite_fwd(int channels, const ImageLayout& im, const BinningLayou
 
 template <int C>
 static int launch_bwd_c(const ImageLayout& im, const BinningLayout& b, const uint32_t* point_list, int W, int H,
-                        const float* bg, const float* dL_dpix, const hgs_raster_grads* gr, cudaStream_t s) {
+                        const float* bg, const float* dL_dpix, const hgs_raster_grads* gr, float* acc16, cudaStream_t s) {
     const unsigned grid = (unsigned)(((W + HGS_TILE - 1) / HGS_TILE) * ((H + HGS_TILE - 1) / HGS_TILE));
     constexpr int CS = (C <= 4) ? 4 : 8;
     const PackedView p = packed_view(b);
@@ -1182,14 +1199,21 @@ static int launch_bwd_c(const ImageLayout& im, const BinningLayout& b, const uin
     if (first_call_on_device(attr_done)) {
         if (int e = check_cuda(cudaFuncSetAttribute(composite_bwd_kernel<C, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)smem), "composite_bwd smem attr")) return e;
-        if (int e = check_cuda(cudaFuncSetAttribute(composite_bwd_half_kernel<C, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (int e = check_cuda(cudaFuncSetAttribute(composite_bwd_half_kernel<C, CS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)smem_half), "composite_bwd_half smem attr")) return e;
+        if (int e = check_cuda(cudaFuncSetAttribute(composite_bwd_half_kernel<C, CS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)smem_half), "composite_bwd_half smem attr")) return e;
     }
     StageScope prof(HGS_STAGE_COMPOSITE_BWD, s);
-    if (composite_blocks_4x4())
-        composite_bwd_half_kernel<C, CS><<<grid, 256, smem_half, s>>>(im.ranges, im.tile_order, point_list, W, H, bg, p.lo, p.hi,
-                                                                       p.col, im.final_T, im.n_contrib, dL_dpix, gr->dL_dmean2D,
-                                                                       gr->dL_dconic, gr->dL_dopacity, gr->dL_dcolor);
+    if (acc16 != nullptr)   // interleaved records + vector reductions (half-warp kernel only)
+        composite_bwd_half_kernel<C, CS, true><<<grid, 256, smem_half, s>>>(im.ranges, im.tile_order, point_list, W, H, bg, p.lo,
+                                                                             p.hi, p.col, im.final_T, im.n_contrib, dL_dpix, acc16,
+                                                                             nullptr, nullptr, nullptr);
+    else if (composite_blocks_4x4())
+        composite_bwd_half_kernel<C, CS, false><<<grid, 256, smem_half, s>>>(im.ranges, im.tile_order, point_list, W, H, bg, p.lo,
+                                                                              p.hi, p.col, im.final_T, im.n_contrib, dL_dpix,
+                                                                              gr->dL_dmean2D, gr->dL_dconic, gr->dL_dopacity,
+                                                                              gr->dL_dcolor);
     else
         composite_bwd_kernel<C, CS><<<grid, 256, smem, s>>>(im.ranges, im.tile_order, point_list, W, H, bg, p.lo, p.hi, p.col,
                                                              im.final_T, im.n_contrib, dL_dpix, gr->dL_dmean2D, gr->dL_dconic,
@@ -1198,16 +1222,16 @@ static int launch_bwd_c(const ImageLayout& im, const BinningLayout& b, const uin
 }
 
 int launch_composite_bwd(int channels, const ImageLayout& im, const BinningLayout& b, const uint32_t* point_list, int W,
-                         int H, const float* bg, const float* dL_dpix, const hgs_raster_grads* gr, cudaStream_t s) {
+                         int H, const float* bg, const float* dL_dpix, const hgs_raster_grads* gr, float* acc16, cudaStream_t s) {
     switch (channels) {
-        case 1: return launch_bwd_c<1>(im, b, point_list, W, H, bg, dL_dpix, gr, s);
-        case 2: return launch_bwd_c<2>(im, b, point_list, W, H, bg, dL_dpix, gr, s);
-        case 3: return launch_bwd_c<3>(im, b, point_list, W, H, bg, dL_dpix, gr, s);
-        case 4: return launch_bwd_c<4>(im, b, point_list, W, H, bg, dL_dpix, gr, s);
-        case 5: return launch_bwd_c<5>(im, b, point_list, W, H, bg, dL_dpix, gr, s);
-        case 6: return launch_bwd_c<6>(im, b, point_list, W, H, bg, dL_dpix, gr, s);
-        case 7: return launch_bwd_c<7>(im, b, point_list, W, H, bg, dL_dpix, gr, s);
-        case 8: return launch_bwd_c<8>(im, b, point_list, W, H, bg, dL_dpix, gr, s);
+        case 1: return launch_bwd_c<1>(im, b, point_list, W, H, bg, dL_dpix, gr, acc16, s);
+        case 2: return launch_bwd_c<2>(im, b, point_list, W, H, bg, dL_dpix, gr, acc16, s);
+        case 3: return launch_bwd_c<3>(im, b, point_list, W, H, bg, dL_dpix, gr, acc16, s);
+        case 4: return launch_bwd_c<4>(im, b, point_list, W, H, bg, dL_dpix, gr, acc16, s);
+        case 5: return launch_bwd_c<5>(im, b, point_list, W, H, bg, dL_dpix, gr, acc16, s);
+        case 6: return launch_bwd_c<6>(im, b, point_list, W, H, bg, dL_dpix, gr, acc16, s);
+        case 7: return launch_bwd_c<7>(im, b, point_list, W, H, bg, dL_dpix, gr, acc16, s);
+        case 8: return launch_bwd_c<8>(im, b, point_list, W, H, bg, dL_dpix, gr, acc16, s);
     }
     set_error("unsupported channel count %d", channels);
     return HGS_ERR_INVALID;

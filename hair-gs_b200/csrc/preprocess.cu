@@ -38,6 +38,7 @@ struct PreArgs {
     int32_t* radii;
     GeomLayout g;
     uint32_t nblocks;
+    int count_lists;             // HGS_SORT_TILE: count the instances per (tile, depth slice) list
     uint32_t slice_base;         // depth-slice hints of the tile-partitioned binning (hgs_raster_params.slice_base / _shift)
     int slice_shift;
     // strand-aligned entry (kStrand): Gaussians derived from segment end points (scene/hair_gaussian_model.py:134-206)
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(kPreprocThreads, 6) preprocess_fwd_kernel(cons
     // counters.  Warp-aggregated: neighbouring lanes hold neighbouring segments of a strand, which mostly share their tile -
     // one atomic per distinct list and trip instead of one per lane (a hot tile takes ~9 k instances at cfg3, and atomics on
     // one address serialise in L2).  The whole warp takes part in every trip (the loop bound is the warp's largest rect).
-    {
+    if (a.count_lists) {
         const uint32_t lane = threadIdx.x & 31;
         const uint32_t w = vis_rmax.x - vis_rmin.x;
         const uint32_t trips = __reduce_max_sync(0xffffffffu, touched);
@@ -578,6 +579,8 @@ struct PreBwdArgs {
     float* dL_dopacity_logit;     // [P]
     float* dL_dmask_logit;        // [P]
     int accumulate;               // strand entry: add to the gradient outputs instead of overwriting them
+    const float* acc16;           // strand entry, optional: interleaved [P,16] accumulation records (hgs_strand_grads.acc16)
+    float* dL_dmean2D_out;        // with acc16: [P,3] screen-space mean gradients written from the record
 };
 
 __device__ __forceinline__ float3 dnormvdv3(const float3 v, const float3 dv) {  // auxiliary.h:107-117
@@ -602,9 +605,14 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
     const bool has_sr = !kStrand && (a.scales != nullptr);
 
     // start every input stream before the visibility test
-    prefetch_l1(a.dL_dconic + 4 * (size_t)idx);
-    prefetch_l1(a.dL_dmean2D + 3 * (size_t)idx, 12);
-    prefetch_l1(a.dL_dcolor + (size_t)idx * a.channels, a.channels * 4);
+    const bool rec16 = kStrand && a.acc16 != nullptr;
+    if (rec16) {
+        prefetch_l1(a.acc16 + 16 * (size_t)idx, 64);
+    } else {
+        prefetch_l1(a.dL_dconic + 4 * (size_t)idx);
+        prefetch_l1(a.dL_dmean2D + 3 * (size_t)idx, 12);
+        prefetch_l1(a.dL_dcolor + (size_t)idx * a.channels, a.channels * 4);
+    }
     if (has_sh) {
         prefetch_l1(a.shs + (size_t)idx * a.M * 3, a.M * 12);
         prefetch_l1(a.clamped + idx);
@@ -614,7 +622,7 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
         prefetch_l1(a.width + idx);
         prefetch_l1(a.opacity_logit + idx);
         prefetch_l1(a.mask_logit + idx);
-        prefetch_l1(a.dL_dopacity + idx);
+        if (!rec16) prefetch_l1(a.dL_dopacity + idx);
     } else {
         prefetch_l1(a.means3D + 3 * (size_t)idx, 12);
         if (a.scales) prefetch_l1(a.scales + 3 * (size_t)idx, 12);
@@ -624,6 +632,7 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
 
     if (kStrand) {
         if (!(a.tiles_touched[idx] > 0)) {
+            if (rec16) { a.dL_dmean2D_out[3 * (size_t)idx] = 0.f; a.dL_dmean2D_out[3 * (size_t)idx + 1] = 0.f; a.dL_dmean2D_out[3 * (size_t)idx + 2] = 0.f; }
             if (!a.accumulate) {
                 a.dL_dwidth[idx] = 0.f;
                 a.dL_dopacity_logit[idx] = 0.f;
@@ -668,8 +677,16 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
     }
 
     // ---- conic -> cov2D -> cov3D and mean (backward_distwar.cu:145-275) -------------------------
-    const float3 dL_dconic = make_float3(a.dL_dconic[4 * (size_t)idx], a.dL_dconic[4 * (size_t)idx + 1],
-                                         a.dL_dconic[4 * (size_t)idx + 3]);
+    // accumulators of the backward compositor: four separate arrays, or one interleaved 64-byte record (strand entry)
+    float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;   // (m2d.x, m2d.y, opacity, -) (conic xx, xy, -, yy) colours
+    if (rec16) {
+        const float4* rp = reinterpret_cast<const float4*>(a.acc16 + 16 * (size_t)idx);
+        r0 = rp[0]; r1 = rp[1]; r2 = rp[2]; r3 = rp[3];
+        a.dL_dmean2D_out[3 * (size_t)idx] = r0.x; a.dL_dmean2D_out[3 * (size_t)idx + 1] = r0.y; a.dL_dmean2D_out[3 * (size_t)idx + 2] = 0.f;
+    }
+    const float3 dL_dconic = rec16 ? make_float3(r1.x, r1.y, r1.w)
+                                   : make_float3(a.dL_dconic[4 * (size_t)idx], a.dL_dconic[4 * (size_t)idx + 1],
+                                                 a.dL_dconic[4 * (size_t)idx + 3]);
     M3 T;
     float3 t;
     float txtz, tytz;
@@ -752,7 +769,7 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
     const float* proj = a.projmatrix;
     const float4 m_hom = xform_point_4x4(mean, proj);
     const float m_w = 1.0f / (m_hom.w + 0.0000001f);
-    const float g2x = a.dL_dmean2D[3 * (size_t)idx], g2y = a.dL_dmean2D[3 * (size_t)idx + 1];
+    const float g2x = rec16 ? r0.x : a.dL_dmean2D[3 * (size_t)idx], g2y = rec16 ? r0.y : a.dL_dmean2D[3 * (size_t)idx + 1];
     const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
     const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
     float3 dproj;
@@ -775,7 +792,7 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
         float dRGB[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            dRGB[c] = a.dL_dcolor[(size_t)idx * a.channels + c];
+            dRGB[c] = rec16 ? (c == 0 ? r2.x : (c == 1 ? r2.y : r2.z)) : a.dL_dcolor[(size_t)idx * a.channels + c];
             dRGB[c] *= ((cbits >> c) & 1u) ? 0.f : 1.f;
         }
         float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
@@ -886,10 +903,12 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
         // colour channels 4..6 carry diff/dist whenever dist >= 1e-7 (the reference's two getters differ at equality)
         float3 dL_dd = sg.collapsed ? make_float3(0.f, 0.f, 0.f)
                                     : make_float3(2.f * (av - bv) * Gd.x, 2.f * (av - bv) * Gd.y, 2.f * (av - bv) * Gd.z);
-        const float* dcol = a.dL_dcolor + (size_t)idx * a.channels;
+        const float* dcol = rec16 ? nullptr : a.dL_dcolor + (size_t)idx * a.channels;
+        const float dcol3 = rec16 ? r2.w : dcol[3];
+        const float3 dcol456 = rec16 ? make_float3(r3.x, r3.y, r3.z) : make_float3(dcol[4], dcol[5], dcol[6]);
         float3 dL_ddiff = make_float3(0.f, 0.f, 0.f);
         if (sg.dist >= kMinVal) {
-            dL_dd.x += dcol[4]; dL_dd.y += dcol[5]; dL_dd.z += dcol[6];
+            dL_dd.x += dcol456.x; dL_dd.y += dcol456.y; dL_dd.z += dcol456.z;
             const float3 o = sg.ohat;
             const float dd = o.x * dL_dd.x + o.y * dL_dd.y + o.z * dL_dd.z;
             const float inv = 1.f / sg.dist;
@@ -904,8 +923,8 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
         atomicAdd(a.dL_dendpoints + 3 * i1 + 1, 0.5f * dmean.y + dL_ddiff.y);
         atomicAdd(a.dL_dendpoints + 3 * i1 + 2, 0.5f * dmean.z + dL_ddiff.z);
         const float o = sigmoidf_(a.opacity_logit[idx]), m = sigmoidf_(a.mask_logit[idx]);
-        put(a.dL_dopacity_logit + idx, a.dL_dopacity[idx] * o * (1.f - o));
-        put(a.dL_dmask_logit + idx, dcol[3] * m * (1.f - m));
+        put(a.dL_dopacity_logit + idx, (rec16 ? r0.z : a.dL_dopacity[idx]) * o * (1.f - o));
+        put(a.dL_dmask_logit + idx, dcol3 * m * (1.f - m));
         return;
     }
     a.dL_dmean3D[3 * idx] = dmean.x;
@@ -1046,6 +1065,7 @@ int launch_preprocess_fwd(const hgs_raster_params* prm, const hgs_raster_inputs*
     a.radii = radii; a.g = g;
     a.nblocks = (prm->P + kPreprocThreads - 1) / kPreprocThreads;
     a.slice_base = (uint32_t)prm->slice_base; a.slice_shift = prm->slice_shift <= 0 ? 32 : prm->slice_shift;
+    a.count_lists = prm->sort_mode == HGS_SORT_TILE;
     a.endpoints = nullptr; a.pairs = nullptr; a.width = nullptr; a.opacity_logit = nullptr; a.mask_logit = nullptr;
     if (int e = check_cuda(cudaMemsetAsync(g.hdr, 0, g.clear_bytes, s), "memset geom header")) return e;
     {
@@ -1073,6 +1093,7 @@ int launch_strand_preprocess_fwd(const hgs_raster_params* prm, const hgs_strand_
     a.radii = radii; a.g = g;
     a.nblocks = (prm->P + kPreprocThreads - 1) / kPreprocThreads;
     a.slice_base = (uint32_t)prm->slice_base; a.slice_shift = prm->slice_shift <= 0 ? 32 : prm->slice_shift;
+    a.count_lists = prm->sort_mode == HGS_SORT_TILE;
     a.endpoints = in->endpoints; a.pairs = (const long long*)in->endpoint_pairs; a.width = in->width;
     a.opacity_logit = in->opacity_logit; a.mask_logit = in->mask_logit;
     if (int e = check_cuda(cudaMemsetAsync(g.hdr, 0, g.clear_bytes, s), "memset geom header")) return e;
@@ -1102,6 +1123,7 @@ int launch_preprocess_bwd(const hgs_raster_params* prm, const hgs_raster_inputs*
     a.tiles_touched = g.tiles_touched; a.endpoints = nullptr; a.pairs = nullptr; a.width = nullptr;
     a.opacity_logit = nullptr; a.mask_logit = nullptr; a.dL_dopacity = nullptr; a.dL_dendpoints = nullptr;
     a.dL_dwidth = nullptr; a.dL_dopacity_logit = nullptr; a.dL_dmask_logit = nullptr;
+    a.acc16 = nullptr; a.dL_dmean2D_out = nullptr;
     StageScope prof(HGS_STAGE_PREPROCESS_BWD, s);
     preprocess_bwd_kernel<false><<<(prm->P + 255) / 256, 256, 0, s>>>(a);
     return check_cuda(cudaGetLastError(), "preprocess_bwd launch");
@@ -1125,6 +1147,7 @@ int launch_strand_preprocess_bwd(const hgs_raster_params* prm, const hgs_strand_
     a.dL_dopacity = gr->dL_dopacity; a.dL_dendpoints = gr->dL_dendpoints; a.dL_dwidth = gr->dL_dwidth;
     a.dL_dopacity_logit = gr->dL_dopacity_logit; a.dL_dmask_logit = gr->dL_dmask_logit;
     a.accumulate = gr->accumulate ? 1 : 0;
+    a.acc16 = gr->acc16; a.dL_dmean2D_out = gr->dL_dmean2D;
     StageScope prof(HGS_STAGE_PREPROCESS_BWD, s);
     preprocess_bwd_kernel<true><<<(prm->P + 255) / 256, 256, 0, s>>>(a);
     return check_cuda(cudaGetLastError(), "strand preprocess_bwd launch");

@@ -125,6 +125,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                                 image_width, sh, degree, campos, prefiltered, debug)
     P, H, W, C = prm.P, prm.height, prm.width, prm.channels
     prm.slice_base, prm.slice_shift = slice_params((dev.index, P, H, W))
+    prm.sort_mode = sort_mode_for((dev.index, P, H, W))     # stage A counts the lists of the tile-partitioned formulation
     with torch.cuda.device(dev):
         stream = L.stream_ptr(dev)
         u8 = dict(dtype=torch.uint8, device=dev)
@@ -150,7 +151,6 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         key = (dev.index, P, H, W)
         cap = _capacity_hint.get(key) if SYNC_FREE else None
         prm.sort_depth_bits = _depth_bits_hint.get(key, 0) if SYNC_FREE else 0
-        prm.sort_mode = sort_mode_for(key)
         binning = None
         if cap is not None:
             binning = torch.empty((lib.hgs_binning_bytes(cap, C),), **u8)
@@ -177,7 +177,8 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                 cap_b = N
             else:
                 cap_b = cap
-            prm.sort_mode = L.SORT_GLOBAL if (overflow & 4) else sort_mode_for(key)
+            if overflow & 4:
+                prm.sort_mode = L.SORT_GLOBAL
             prm.sort_depth_bits = _next_depth_bits(H, W, need) if SYNC_FREE else 0
             L.check(lib.hgs_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
                                             binning.data_ptr() if cap_b > 0 else None, img.data_ptr(), cap_b,

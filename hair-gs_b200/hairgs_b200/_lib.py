@@ -49,7 +49,7 @@ class StrandInputs(ctypes.Structure):
 class StrandGrads(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("dL_dmean2D", "dL_dconic", "dL_dopacity", "dL_dcolor", "dL_dendpoints",
                                         "dL_dwidth", "dL_dopacity_logit", "dL_dmask_logit", "dL_dfeatures")] + \
-               [("accumulate", c_int32)]
+               [("accumulate", c_int32), ("acc16", c_void_p)]
 
 
 ALLOC_FN = ctypes.CFUNCTYPE(c_void_p, c_void_p, c_size_t)

@@ -21,6 +21,11 @@ from . import _lib as L
 from diff_gaussian_rasterization import _C as _dgr  # capacity hints / pinned read-back ring are shared
 
 
+# HGS_BWD_RED=scalar: the round-1 accumulation (four arrays, scalar red.global.add.f32); default: interleaved records +
+# red.global.add.v4.f32 (A/B: profiles/r2_bwd_vector_red.md)
+BWD_VECTOR_RED = __import__("os").environ.get("HGS_BWD_RED", "vec") != "scalar"
+
+
 def _prep(endpoints, endpoint_pairs, width, opacity_logit, mask_logit, features, s):
     if not endpoints.is_cuda:
         raise L.HgsError("endpoints must be a CUDA tensor: this rasterizer has no CPU path")
@@ -52,9 +57,10 @@ def strands_forward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit,
     u8 = dict(dtype=torch.uint8, device=dev)
     plan = settings.get("plan")
     if plan is not None:
-        prm.slice_base, prm.slice_shift = plan.slice_base, plan.slice_shift
+        prm.slice_base, prm.slice_shift, prm.sort_mode = plan.slice_base, plan.slice_shift, int(plan.sort_mode)
     else:
         prm.slice_base, prm.slice_shift = _dgr.slice_params((dev.index, P, H, W, 7))
+        prm.sort_mode = _dgr.sort_mode_for((dev.index, P, H, W, 7))
     with torch.cuda.device(dev):
         stream = L.stream_ptr(dev)
         image = torch.empty((7, H, W), dtype=torch.float32, device=dev)
@@ -85,7 +91,6 @@ def strands_forward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit,
         key = (dev.index, P, H, W, 7)
         cap = _dgr._capacity_hint.get(key) if _dgr.SYNC_FREE else None
         prm.sort_depth_bits = _dgr._depth_bits_hint.get(key, 0) if _dgr.SYNC_FREE else 0
-        prm.sort_mode = _dgr.sort_mode_for(key)
         binning = None
         if cap is not None:
             binning = torch.empty((lib.hgs_binning_bytes(cap, 7),), **u8)
@@ -108,7 +113,8 @@ def strands_forward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit,
             if cap is None or N > cap:
                 cap = N
                 binning = torch.empty((lib.hgs_binning_bytes(N, 7),), **u8)
-            prm.sort_mode = L.SORT_GLOBAL if (overflow & 4) else _dgr.sort_mode_for(key)
+            if overflow & 4:
+                prm.sort_mode = L.SORT_GLOBAL
             prm.sort_depth_bits = _dgr._next_depth_bits(H, W, need) if _dgr.SYNC_FREE else 0
             L.check(lib.hgs_strands_forward_stage_b(ctypes.byref(prm), ctypes.byref(inp), geom.data_ptr(),
                                                     binning.data_ptr() if cap > 0 else None, img.data_ptr(), cap,
@@ -128,8 +134,16 @@ def strands_backward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit
     f32 = dict(dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         dpix = L.f32c(grad_image, "grad_image", dev)
-        acc = torch.empty((P * 15,), **f32)  # mean2D 3 | conic 4 | opacity 1 | colour 7 : one memset in the library
-        d_mean2D = acc[:3 * P].view(P, 3)
+        vec = BWD_VECTOR_RED
+        if vec:
+            # one interleaved 64-byte accumulation record per Gaussian (hgs_strand_grads.acc16: four red.global.add.v4.f32
+            # per instance and pixel block instead of 13 scalar atomics) + the [P,3] screen-space mean gradients written
+            # from it by the preprocess backward
+            acc = torch.empty((P * 19,), **f32)
+            d_mean2D = acc[16 * P:].view(P, 3)
+        else:
+            acc = torch.empty((P * 15,), **f32)  # mean2D 3 | conic 4 | opacity 1 | colour 7 : one memset in the library
+            d_mean2D = acc[:3 * P].view(P, 3)
         sink = settings.get("grad_sink")
         if sink is None:
             out = torch.empty((3 * E + 3 * P + 3 * M * P,), **f32)
@@ -150,11 +164,12 @@ def strands_backward(endpoints, endpoint_pairs, width, opacity_logit, mask_logit
                                      "the parameters")
             accumulate = 1 if sink.accumulate else 0
             sink.accumulate = True      # later views of the same optimiser step add to the first
-        grads = L.StrandGrads(dL_dmean2D=acc.data_ptr(), dL_dconic=acc[3 * P:].data_ptr(),
-                              dL_dopacity=acc[7 * P:].data_ptr(), dL_dcolor=acc[8 * P:].data_ptr(),
+        grads = L.StrandGrads(dL_dmean2D=d_mean2D.data_ptr(), dL_dconic=None if vec else acc[3 * P:].data_ptr(),
+                              dL_dopacity=None if vec else acc[7 * P:].data_ptr(),
+                              dL_dcolor=None if vec else acc[8 * P:].data_ptr(),
                               dL_dendpoints=d_end.data_ptr(), dL_dwidth=d_width.data_ptr(),
                               dL_dopacity_logit=d_opac.data_ptr(), dL_dmask_logit=d_mask.data_ptr(),
-                              dL_dfeatures=d_feat.data_ptr(), accumulate=accumulate)
+                              dL_dfeatures=d_feat.data_ptr(), accumulate=accumulate, acc16=acc.data_ptr() if vec else None)
         L.check(lib.hgs_strands_backward(ctypes.byref(prm), ctypes.byref(inp), int(capacity), geom.data_ptr(),
                                          L.ptr(binning), img.data_ptr(), dpix.data_ptr(), ctypes.byref(grads),
                                          L.stream_ptr(dev)), "strands backward")

@@ -295,8 +295,13 @@ class GraphedStrandBatch:
         self.binning = [torch.empty(lib.hgs_binning_bytes(int(capacity), 7), **u8) for _ in range(V)]
         self.image = [torch.empty(7, self.H, self.W, **f32) for _ in range(V)]
         self.radii = [torch.empty(P, dtype=torch.int32, device=dev) for _ in range(V)]
-        self.acc = [torch.empty(P * 15, **f32) for _ in range(V)]      # mean2D 3 | conic 4 | opacity 1 | colour 7
-        self.mean2d_grad = [a[:3 * P].view(P, 3) for a in self.acc]
+        self.vec = fused.BWD_VECTOR_RED
+        if self.vec:       # interleaved [P,16] accumulation records + [P,3] mean2D output (hgs_strand_grads.acc16)
+            self.acc = [torch.empty(P * 19, **f32) for _ in range(V)]
+            self.mean2d_grad = [a[16 * P:].view(P, 3) for a in self.acc]
+        else:              # mean2D 3 | conic 4 | opacity 1 | colour 7
+            self.acc = [torch.empty(P * 15, **f32) for _ in range(V)]
+            self.mean2d_grad = [a[:3 * P].view(P, 3) for a in self.acc]
         self.losses = torch.zeros(V, **f32)
         self.terms = torch.zeros(V, 8, **f32)
         self.bin_stream = torch.cuda.Stream(device=dev, priority=-1)
@@ -381,8 +386,10 @@ class GraphedStrandBatch:
                                                                lam.get("bg_orient", (0.0, 0.0, 0.0)))
                     self.terms[v].copy_(terms)
                 acc = self.acc[v]
-                grads = L.StrandGrads(dL_dmean2D=acc.data_ptr(), dL_dconic=acc[3 * self.P:].data_ptr(),
-                                      dL_dopacity=acc[7 * self.P:].data_ptr(), dL_dcolor=acc[8 * self.P:].data_ptr(),
+                vec = self.vec
+                grads = L.StrandGrads(dL_dmean2D=self.mean2d_grad[v].data_ptr(), dL_dconic=None if vec else acc[3 * self.P:].data_ptr(),
+                                      dL_dopacity=None if vec else acc[7 * self.P:].data_ptr(),
+                                      dL_dcolor=None if vec else acc[8 * self.P:].data_ptr(), acc16=acc.data_ptr() if vec else None,
                                       dL_dendpoints=s.tensors["endpoints"].data_ptr(), dL_dwidth=s.tensors["width"].data_ptr(),
                                       dL_dopacity_logit=s.tensors["opacity"].data_ptr(),
                                       dL_dmask_logit=s.tensors["mask"].data_ptr(), dL_dfeatures=s.tensors["features"].data_ptr(),

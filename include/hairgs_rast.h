@@ -90,6 +90,8 @@ typedef struct hgs_raster_params {
                              * by the preprocess, one scatter) and every list is sorted by (depth, id) inside shared memory by
                              * the kernel that also packs the sorted records - two passes over the instances.  A list longer
                              * than HGS_TILE_SORT_MAX raises bit 2 of the overflow word in stage A: run stage B with HGS_SORT_GLOBAL.
+                             * Read by stage A too (it takes the counts): pass the same value to both stages; a stage B in
+                             * HGS_SORT_TILE after a stage A in HGS_SORT_GLOBAL is invalid (the reverse is fine).
                              * HGS_SORT_GLOBAL (1): stable radix sort of the 64-bit (tile | depth) keys, the reference's
                              * formulation (rasterizer_impl.cu:300-308); sort_depth_bits applies to this mode only.  This is
                              * what the Python packages select by default (measured faster on B200, profiles/r2_tilesort.md).
@@ -168,6 +170,12 @@ typedef struct hgs_strand_grads {
     float* dL_dfeatures;      /* [P,M,3] */
     int32_t accumulate;       /* 0: the five parameter gradients above are overwritten (every element written once);
                                * 1: they are ADDED to (several views sunk into one gradient bucket) */
+    float* acc16;             /* ABI v4, may be NULL.  [P,16] scratch, 16-byte aligned: ONE interleaved accumulation record per
+                               * Gaussian (mean2D.xy, opacity, - | conic xx, xy, -, yy | colour 0-3 | colour 4-6, -) that the
+                               * backward compositor fills with four red.global.add.v4.f32 per (instance, pixel block) instead
+                               * of thirteen scalar atomics; dL_dconic / dL_dopacity / dL_dcolor are then unused (may be NULL)
+                               * and dL_dmean2D is written from the record by the preprocess backward.  Vector reductions
+                               * flush denormal addends to zero (REDG.F32x4.FTZ). */
 } hgs_strand_grads;
 
 int hgs_strands_forward_stage_a(const hgs_raster_params* prm, const hgs_strand_inputs* in, void* geom_ws,
