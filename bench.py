@@ -199,18 +199,28 @@ def build_workload(cfg, dev, n_cams=None):
 
 
 def make_targets(cfg, n, hair_loss):
-    """Synthetic per-view targets in pinned host memory.  Workloads that train on RGB + mask + orientation carry what
-    Hair-GS's cameras hold (scene/cameras.py:60-85): original_image[3], float_mask[1], orientation_field[1] in [0, pi),
-    orientation_confidence[1]; the others an RGB image (+ unused planes).  Same generator and seed in both arms."""
+    """Synthetic per-view targets in pinned host memory, same generator and seed in both arms.  Workloads that train on RGB
+    + mask + orientation carry what Hair-GS's cameras hold (scene/cameras.py:60-85): original_image[3], float_mask,
+    orientation_field in [0, pi), orientation_confidence.  They are generated in their STORAGE format — image bytes + mask as
+    uint8 [H,W,4], angle + confidence as float16 [H,W,2], 8 bytes per pixel — which is what our arm uploads and unpacks on
+    the device (hgs_unpack_targets); "float" holds the same values as six float32 planes (24 bytes per pixel), what the
+    reference's Camera keeps and what the reference arm uploads.  Other workloads: an RGB image (+ unused planes), float32."""
     import torch
     g = torch.Generator(device="cpu").manual_seed(1234)
-    out = []
+    pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
+    out = {"float": [], "rgbm": [], "tc": []}
     for _ in range(n):
         t = torch.rand(6 if hair_loss else 7, cfg["H"], cfg["W"], generator=g)
         if hair_loss:
             t[3] = (t[3] < 0.5).float()
             t[4] *= math.pi
-        out.append(t.pin_memory() if torch.cuda.is_available() else t)
+            rgbm = torch.cat([(t[0:3] * 255.0).round(), t[3:4] * 255.0], 0).to(torch.uint8).permute(1, 2, 0).contiguous()
+            tc = torch.stack([t[4], t[5]], -1).to(torch.float16).contiguous()
+            t = torch.cat([rgbm[..., 0:3].permute(2, 0, 1).float() / 255.0, rgbm[..., 3][None].float() / 255.0,
+                           tc[..., 0][None].float(), tc[..., 1][None].float()], 0).contiguous()
+            out["rgbm"].append(pin(rgbm))
+            out["tc"].append(pin(tc))
+        out["float"].append(pin(t))
     return out
 
 
@@ -257,12 +267,15 @@ class Harness:
         self.n_tgt = 6 if self.hair_loss else 7
         # targets are generated for ALL cameras (same stream of random numbers on every rank and in the reference arm);
         # a rank keeps only its own
-        all_t = make_targets(cfg, len(self.cams), self.hair_loss) if len(self.cams) <= 16 else None
-        if all_t is None:
-            all_t = make_targets(cfg, len(self.my_views), self.hair_loss)
-            self.targets_host = all_t
+        if len(self.cams) <= 16:
+            all_t = make_targets(cfg, len(self.cams), self.hair_loss)
+            all_t = {k: [v[i] for i in self.my_views] for k, v in all_t.items() if v}
         else:
-            self.targets_host = [all_t[v] for v in self.my_views]
+            all_t = make_targets(cfg, len(self.my_views), self.hair_loss)
+        self.targets_host = all_t["float"]
+        # hair workloads upload the storage format (8 bytes per pixel) and unpack it on the device
+        self.compact = self.hair_loss
+        self.rgbm_host, self.tc_host = all_t.get("rgbm", []), all_t.get("tc", [])
         # device-resident inputs of the `value` loop
         with torch.no_grad():
             m = self.model
@@ -472,7 +485,11 @@ class Harness:
         self.copy_done = [torch.cuda.Event() for _ in range(2)]
         self.slot_free = [torch.cuda.Event() for _ in range(2)]
         self.loss_host = torch.zeros(1).pin_memory()
-        self.h2d_bytes = self.vps * (self.n_tgt * H * W * 4 + 35 * 4)
+        if self.compact:
+            self.rgbm_dev = [torch.empty(H, W, 4, dtype=torch.uint8, device=self.dev) for _ in range(2)]
+            self.tc_dev = [torch.empty(H, W, 2, dtype=torch.float16, device=self.dev) for _ in range(2)]
+            self.unpack_targets = losses.unpack_targets
+        self.h2d_bytes = self.vps * ((8 if self.compact else self.n_tgt * 4) * H * W + 35 * 4)
         self.d2h_bytes = self.vps * 4
         self._prefetched = -1
         self._setup_graph(graph)
@@ -494,6 +511,8 @@ class Harness:
                 V, H, W = self.vps, self.cfg["H"], self.cfg["W"]
                 if not hasattr(self, "tgt_sets"):
                     self.tgt_sets = [torch.empty(V, 6, H, W, device=self.dev) for _ in range(2)]
+                    self.rgbm_sets = [torch.empty(V, H, W, 4, dtype=torch.uint8, device=self.dev) for _ in range(2)]
+                    self.tc_sets = [torch.empty(V, H, W, 2, dtype=torch.float16, device=self.dev) for _ in range(2)]
                     self.cam_sets = [torch.empty(V, 35, device=self.dev) for _ in range(2)]
                     self.set_ready = [torch.cuda.Event() for _ in range(2)]
                     self.set_free = [torch.cuda.Event() for _ in range(2)]
@@ -538,7 +557,8 @@ class Harness:
             self.copy_stream.wait_event(self.set_free[k])
             for v in range(V):
                 idx = (it * V + v) % len(self.my_views)
-                self.tgt_sets[k][v].copy_(self.targets_host[idx], non_blocking=True)
+                self.rgbm_sets[k][v].copy_(self.rgbm_host[idx], non_blocking=True)
+                self.tc_sets[k][v].copy_(self.tc_host[idx], non_blocking=True)
                 self.cam_sets[k][v].copy_(self.cam_host[idx], non_blocking=True)
             self.set_ready[k].record(self.copy_stream)
         self._batch_prefetched = it
@@ -553,6 +573,7 @@ class Harness:
         cur.wait_event(self.set_ready[k])
         if self._batch_prefetched < it + 1:
             self._prefetch_batch(it + 1)     # the next step's copies overlap this step's kernels
+        self.unpack_targets(self.rgbm_sets[k], self.tc_sets[k], out=self.tgt_sets[k])   # storage format -> float planes, one launch
         losses = self.ebatch[k].replay(accumulate=False)
         self.set_free[k].record(cur)
         self.losses_host.copy_(losses, non_blocking=True)
@@ -563,7 +584,11 @@ class Harness:
         slot, k = it % 2, it % len(self.my_views)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.slot_free[slot])
-            self.tgt_dev[slot].copy_(self.targets_host[k], non_blocking=True)
+            if self.compact:
+                self.rgbm_dev[slot].copy_(self.rgbm_host[k], non_blocking=True)
+                self.tc_dev[slot].copy_(self.tc_host[k], non_blocking=True)
+            else:
+                self.tgt_dev[slot].copy_(self.targets_host[k], non_blocking=True)
             self.cam_dev[slot].copy_(self.cam_host[k], non_blocking=True)
             self.copy_done[slot].record(self.copy_stream)
         self._prefetched = it
@@ -604,6 +629,8 @@ class Harness:
         cam = Camera(base.image_width, base.image_height, base.FoVx, base.FoVy, cd[0:16].view(4, 4), cd[16:32].view(4, 4),
                      cd[32:35])
         tgt = self.tgt_dev[slot]
+        if self.compact:
+            self.unpack_targets(self.rgbm_dev[slot], self.tc_dev[slot], out=tgt)   # storage format -> float planes
         if first:
             if self.esink is not None:
                 self.esink.begin_step()      # the first view of the step overwrites the gradients, the others add
@@ -683,9 +710,9 @@ class RefHarness:
         costs = view_costs(ns.dgr_C, g, cams, cfg, dev) if world > 1 else None
         self.my_views, _ = multiview.shard_views(len(cams), world, 0, costs=costs)
         self.scene_cams = cams
-        all_t = make_targets(cfg, len(cams), self.hair_loss) if len(cams) <= 16 else None
+        all_t = make_targets(cfg, len(cams), self.hair_loss)["float"] if len(cams) <= 16 else None
         self.targets_host = ([all_t[v] for v in self.my_views] if all_t is not None
-                             else make_targets(cfg, len(self.my_views), self.hair_loss))
+                             else make_targets(cfg, len(self.my_views), self.hair_loss)["float"])
         H, W = cfg["H"], cfg["W"]
         # two reference Camera objects = the double-buffered input slots; their tensors are refilled every view
         self.cam_slots = []
@@ -1369,9 +1396,10 @@ def run():
             line["e2e"]["graph"] = graph_note
         if ms_e2e_eager is not None:
             line["e2e"]["api"] = ("hairgs_b200.graphs.GraphedStrandStep.replay(): render_strands() + hair_image_loss() + "
-                                  "backward captured as one CUDA graph per input slot; targets/camera copied from pinned "
-                                  "host memory into the slot every step, loss copied back; all-reduce / optimiser outside "
-                                  "the graph")
+                                  "backward captured as CUDA graph(s); the views' cameras and targets are copied from pinned host "
+                                  "memory every step in their storage format (uint8 image + mask, float16 angle + confidence: 8 "
+                                  "bytes per pixel) and unpacked on the device (hgs_unpack_targets), losses copied back; "
+                                  "all-reduce / optimiser outside the graph")
             line["e2e"]["value_eager"] = round(views / (ms_e2e_eager / 1000.0), 2)
     line["roofline"] = roofline
     line["stages"] = stages

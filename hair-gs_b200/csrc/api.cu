@@ -81,6 +81,7 @@ int set_fwd_stats(void* dev_ptr);
 int set_composite_blocks(int mode);
 int launch_weighted_l1(int, long long, const float*, const float*, const float*, float*, float*, cudaStream_t);
 int launch_hair_image_loss(const hgs_hair_loss&, cudaStream_t);
+int launch_unpack_targets(int, long long, const void*, const void*, float*, cudaStream_t);
 int launch_adam_flat(long long, float*, float*, float*, float*, int, const int64_t*, const float*, int, float, float, float,
                      float, int, cudaStream_t);
 int launch_densify_stats(int, const int*, const float*, int, int*, float*, float*, float*, cudaStream_t);
@@ -431,6 +432,11 @@ int hgs_hair_image_loss(const hgs_hair_loss* a, void* stream) {
     if (!a || a->height <= 0 || a->width <= 0 || !a->image7 || !a->gt_rgb || !a->gt_mask || !a->gt_theta || !a->confidence ||
         !a->terms || !a->scratch || !a->dL_dimage) { set_error("bad hair_image_loss args"); return HGS_ERR_INVALID; }
     return launch_hair_image_loss(*a, (cudaStream_t)stream);
+}
+
+int hgs_unpack_targets(int32_t views, int64_t HW, const void* rgbm, const void* theta_conf, float* out, void* stream) {
+    if (views < 0 || HW < 0 || (views > 0 && HW > 0 && (!rgbm || !theta_conf || !out))) { set_error("bad unpack_targets args"); return HGS_ERR_INVALID; }
+    return launch_unpack_targets(views, HW, rgbm, theta_conf, out, (cudaStream_t)stream);
 }
 
 int hgs_adam_step(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, int32_t n_groups,

@@ -5,6 +5,8 @@
 // autograd mirrors, the slice-backward zero fills); here: read image + target once, write dL/dimage once.
 #include "hgs_common.cuh"
 
+#include <cuda_fp16.h>
+
 namespace hgs {
 
 // loss += sum_c w[c] * sum_i |img[c][i] - tgt[c][i]| ;  dL[c][i] = w[c] * sign(img - tgt)   (sign(0) = 0 as torch)
@@ -359,6 +361,36 @@ __global__ void hair_loss_finish_kernel(const HairLossArgs a) {
     const float ori = cnt > 0.f ? a.terms[4] / cnt : 0.f;
     a.terms[1] = l1; a.terms[2] = dssim; a.terms[3] = mask; a.terms[4] = ori;
     a.terms[0] = a.l_l1 * l1 + a.l_dssim * dssim + a.l_mask * mask + a.l_orient * ori;
+}
+
+// ------------------------------------------------------------------------------------------------
+// target stacks: storage format (8 B / pixel) -> float planes (24 B / pixel)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) unpack_targets_kernel(long long HW, long long total, const uchar4* __restrict__ rgbm,
+                                                             const __half2* __restrict__ tc, float* __restrict__ out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long v = i / HW, px = i - v * HW;
+        const uchar4 c = rgbm[i];
+        const float2 t = __half22float2(tc[i]);
+        float* o = out + v * 6 * HW + px;
+        o[0] = (float)c.x / 255.0f;
+        o[HW] = (float)c.y / 255.0f;
+        o[2 * HW] = (float)c.z / 255.0f;
+        o[3 * HW] = (float)c.w / 255.0f;
+        o[4 * HW] = t.x;
+        o[5 * HW] = t.y;
+    }
+}
+
+int launch_unpack_targets(int views, long long HW, const void* rgbm, const void* tc, float* out, cudaStream_t s) {
+    const long long total = (long long)views * HW;
+    if (total <= 0) return HGS_OK;
+    long long nb = (total + 255) / 256;
+    if (nb > 148 * 16) nb = 148 * 16;
+    StageScope prof(HGS_STAGE_OTHER, s);
+    unpack_targets_kernel<<<(unsigned)nb, 256, 0, s>>>(HW, total, (const uchar4*)rgbm, (const __half2*)tc, out);
+    return check_cuda(cudaGetLastError(), "unpack_targets launch");
 }
 
 int launch_hair_image_loss(const HairLossArgs& a, cudaStream_t s) {

@@ -127,6 +127,8 @@ def load():
     lib.hgs_weighted_l1.argtypes = [c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.hgs_hair_image_loss.restype = c_int
     lib.hgs_hair_image_loss.argtypes = [P(HairLoss), c_void_p]
+    lib.hgs_unpack_targets.restype = c_int
+    lib.hgs_unpack_targets.argtypes = [c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.hgs_adam_step.restype = c_int
     lib.hgs_adam_step.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, P(c_int64), P(c_float), c_int32,
                                   c_float, c_float, c_float, c_float, c_int32, c_void_p]

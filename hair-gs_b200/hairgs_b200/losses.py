@@ -52,6 +52,40 @@ def l1_groups(groups, H, W, device):
     return w.to(device)
 
 
+def pack_targets(gt_rgb, gt_mask, gt_theta, confidence):
+    """Host-side storage format of one view's targets (what a data loader keeps in pinned memory): rgbm uint8 [H,W,4]
+    (image bytes + mask 0/255) and theta_conf float16 [H,W,2] — 8 bytes per pixel instead of the 24 of six float planes."""
+    rgb = (gt_rgb.clamp(0, 1) * 255.0).round().to(torch.uint8)
+    m = (gt_mask > 0.5).to(torch.uint8) * 255
+    rgbm = torch.cat([rgb, m[None]], 0).permute(1, 2, 0).contiguous()
+    tc = torch.stack([gt_theta, confidence], -1).to(torch.float16).contiguous()
+    return rgbm, tc
+
+
+def unpack_targets(rgbm, theta_conf, out=None):
+    """Device side of pack_targets (hgs_unpack_targets): rgbm [V,H,W,4] / [H,W,4] uint8 and theta_conf [V,H,W,2] / [H,W,2]
+    float16 CUDA tensors -> float32 [V,6,H,W] / [6,H,W] = (r, g, b, mask, theta, confidence) planes, one launch."""
+    lib = L.load()
+    if not rgbm.is_cuda or not theta_conf.is_cuda:
+        raise L.HgsError("unpack_targets: CUDA tensors only (no CPU path)")
+    dev = rgbm.device
+    batched = rgbm.dim() == 4
+    V = rgbm.shape[0] if batched else 1
+    H, W = rgbm.shape[-3], rgbm.shape[-2]
+    if rgbm.dtype != torch.uint8 or rgbm.shape[-1] != 4 or theta_conf.dtype != torch.float16 or \
+            tuple(theta_conf.shape) != tuple(rgbm.shape[:-1]) + (2,) or not rgbm.is_contiguous() or not theta_conf.is_contiguous():
+        raise L.HgsError("unpack_targets: expected contiguous rgbm uint8 [...,H,W,4] and theta_conf float16 [...,H,W,2]")
+    shape = (V, 6, H, W) if batched else (6, H, W)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
+        raise L.HgsError("unpack_targets: out must be a contiguous float32 tensor of shape " + str(shape))
+    with torch.cuda.device(dev):
+        L.check(lib.hgs_unpack_targets(V, H * W, rgbm.data_ptr(), theta_conf.data_ptr(), out.data_ptr(), L.stream_ptr(dev)),
+                "unpack_targets")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Hair-GS image-space loss of one view (loss/losses.py:319-346, image terms), fused: hgs_hair_image_loss
 # ---------------------------------------------------------------------------------------------------------------------

@@ -295,6 +295,13 @@ typedef struct hgs_hair_loss {
 } hgs_hair_loss;
 int hgs_hair_image_loss(const hgs_hair_loss* args, void* stream);
 
+/* Target stacks in their storage format -> the float planes hgs_hair_image_loss reads (ABI v4).  What Hair-GS's cameras hold
+ * per view (scene/cameras.py:60-85: original_image[3], float_mask, orientation_field, orientation_confidence) arrives from the
+ * host as 8 bytes per pixel instead of 24: rgbm = [views, H*W] uchar4 (r, g, b in 0..255 as the image files store them, mask
+ * 0 / 255), theta_conf = [views, H*W] half2 (orientation angle in [0, pi), confidence); out = [views, 6, H*W] float
+ * (r/255, g/255, b/255, mask/255, theta, confidence).  One launch for all views of a step. */
+int hgs_unpack_targets(int32_t views, int64_t HW, const void* rgbm, const void* theta_conf, float* out, void* stream);
+
 /* Optimiser step over the flat parameter bucket: torch.optim.Adam as Hair-GS configures it
  * (scene/gaussian_model.py:250: per-group lr, betas (0.9, 0.999), eps 1e-15, no weight decay, no amsgrad) for every
  * parameter group in ONE launch.  Group g covers flat elements [group_end[g-1], group_end[g]) and steps with lr[g];

@@ -1225,3 +1225,24 @@ def test_tile_sort_equals_global_sort_at_size():
     finally:
         ours_C.DEFAULT_SORT_MODE = saved
         ours_C._sort_mode_hint.clear()
+
+
+def test_unpack_targets_matches_torch():
+    """hgs_unpack_targets: the storage format of a view's targets (uint8 image bytes + mask, float16 angle + confidence;
+    losses.pack_targets) -> the six float planes the image loss reads, single view and batched."""
+    from hairgs_b200 import losses
+    g = torch.Generator().manual_seed(9)
+    V, H, W = 3, 37, 53
+    rgb, m = torch.rand(V, 3, H, W, generator=g), (torch.rand(V, H, W, generator=g) < 0.5).float()
+    th, cf = torch.rand(V, H, W, generator=g) * math.pi, torch.rand(V, H, W, generator=g)
+    packed = [losses.pack_targets(rgb[v], m[v], th[v], cf[v]) for v in range(V)]
+    rgbm = torch.stack([p[0] for p in packed]).to(dev())
+    tc = torch.stack([p[1] for p in packed]).to(dev())
+    assert rgbm.shape == (V, H, W, 4) and rgbm.dtype == torch.uint8 and tc.shape == (V, H, W, 2) and tc.dtype == torch.float16
+    out = losses.unpack_targets(rgbm, tc)
+    ref = torch.cat([(rgb * 255).round() / 255, m[:, None], th.half().float()[:, None], cf.half().float()[:, None]], 1).to(dev())
+    assert out.shape == (V, 6, H, W) and torch.equal(out, ref)
+    one = losses.unpack_targets(rgbm[1].contiguous(), tc[1].contiguous())
+    assert torch.equal(one, ref[1])
+    with pytest.raises(Exception):
+        losses.unpack_targets(rgbm.cpu(), tc.cpu())
