@@ -296,6 +296,12 @@ int hgs_strands_forward_stage_b(const hgs_raster_params* prm, const hgs_strand_i
 int hgs_strands_backward(const hgs_raster_params* prm, const hgs_strand_inputs* in, int64_t R, const void* geom_ws,
                          const void* binning_ws, const void* image_ws, const float* dL_dpix, const hgs_strand_grads* gr,
                          void* stream) {
+    return hgs_strands_backward_parts(prm, in, R, geom_ws, binning_ws, image_ws, dL_dpix, gr, 3, stream);
+}
+
+int hgs_strands_backward_parts(const hgs_raster_params* prm, const hgs_strand_inputs* in, int64_t R, const void* geom_ws,
+                               const void* binning_ws, const void* image_ws, const float* dL_dpix, const hgs_strand_grads* gr,
+                               int32_t parts, void* stream) {
     if (int e = validate_strands(prm, in)) return e;
     cudaStream_t s = (cudaStream_t)stream;
     if (!gr || !gr->dL_dmean2D || !gr->dL_dendpoints || !gr->dL_dwidth || !gr->dL_dopacity_logit || !gr->dL_dmask_logit ||
@@ -303,7 +309,7 @@ int hgs_strands_backward(const hgs_raster_params* prm, const hgs_strand_inputs* 
     if (gr->acc16 && ((uintptr_t)gr->acc16 & 15)) { set_error("acc16 must be 16-byte aligned"); return HGS_ERR_INVALID; }
     if (!geom_ws || !image_ws || !dL_dpix || (R > 0 && !binning_ws)) { set_error("null workspace"); return HGS_ERR_INVALID; }
     const int P = prm->P;
-    if (!gr->accumulate)
+    if ((parts & 2) && !gr->accumulate)
         if (int e = check_cuda(cudaMemsetAsync(gr->dL_dendpoints, 0, (size_t)in->num_endpoints * 3 * 4, s), "memset dL_dendpoints")) return e;
     if (P == 0) return HGS_OK;
     GeomLayout g = carve_geom((void*)geom_ws, P, prm->channels, tile_count_of(prm->width, prm->height));
@@ -311,7 +317,9 @@ int hgs_strands_backward(const hgs_raster_params* prm, const hgs_strand_inputs* 
     BinningLayout b = carve_binning((void*)binning_ws, R, prm->channels);
     const int res = 0;  // the sorted pairs always end in ping-pong buffer 0 (stage_b_impl)
     const size_t Pz = (size_t)P;
-    if (gr->acc16) {
+    if (!(parts & 1)) {
+        // part 2 only: the compositor's accumulators are already filled
+    } else if (gr->acc16) {
         if (int e = check_cuda(cudaMemsetAsync(gr->acc16, 0, Pz * 16 * 4, s), "memset acc16")) return e;
     } else if (gr->dL_dconic == gr->dL_dmean2D + 3 * Pz && gr->dL_dopacity == gr->dL_dconic + 4 * Pz &&
         gr->dL_dcolor == gr->dL_dopacity + Pz) {
@@ -322,13 +330,14 @@ int hgs_strands_backward(const hgs_raster_params* prm, const hgs_strand_inputs* 
         if (int e = check_cuda(cudaMemsetAsync(gr->dL_dopacity, 0, Pz * 4, s), "memset dL_dopacity")) return e;
         if (int e = check_cuda(cudaMemsetAsync(gr->dL_dcolor, 0, Pz * 7 * 4, s), "memset dL_dcolor")) return e;
     }
-    if (R > 0) {
+    if ((parts & 1) && R > 0) {
         hgs_raster_grads rg;
         memset(&rg, 0, sizeof(rg));
         rg.dL_dmean2D = gr->dL_dmean2D; rg.dL_dconic = gr->dL_dconic; rg.dL_dopacity = gr->dL_dopacity; rg.dL_dcolor = gr->dL_dcolor;
         if (int e = launch_composite_bwd(7, im, b, b.vals[res], prm->width, prm->height, in->background, dL_dpix, &rg, gr->acc16, s)) return e;
         if (int e = stage_check("composite_bwd", prm->debug, s)) return e;
     }
+    if (!(parts & 2)) return HGS_OK;
     if (int e = launch_strand_preprocess_bwd(prm, in, g, gr, s)) return e;
     return stage_check("strand preprocess_bwd", prm->debug, s);
 }

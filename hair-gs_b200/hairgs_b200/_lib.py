@@ -123,6 +123,9 @@ def load():
     lib.hgs_strands_backward.restype = c_int
     lib.hgs_strands_backward.argtypes = [P(RasterParams), P(StrandInputs), c_int64, c_void_p, c_void_p, c_void_p,
                                          c_void_p, P(StrandGrads), c_void_p]
+    lib.hgs_strands_backward_parts.restype = c_int
+    lib.hgs_strands_backward_parts.argtypes = [P(RasterParams), P(StrandInputs), c_int64, c_void_p, c_void_p, c_void_p,
+                                               c_void_p, P(StrandGrads), c_int32, c_void_p]
     lib.hgs_weighted_l1.restype = c_int
     lib.hgs_weighted_l1.argtypes = [c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.hgs_hair_image_loss.restype = c_int

@@ -305,6 +305,11 @@ class GraphedStrandBatch:
         self.losses = torch.zeros(V, **f32)
         self.terms = torch.zeros(V, 8, **f32)
         self.bin_stream = torch.cuda.Stream(device=dev, priority=-1)
+        # HGS_BATCH_COMP_BRANCHES: streams the views' compositing is dealt over (see _batch); 1 = one compositing branch
+        import os
+        self.comp_branches = max(1, min(4, int(os.environ.get("HGS_BATCH_COMP_BRANCHES", "2")), self.V))
+        self.comp_streams = [torch.cuda.Stream(device=dev) for _ in range(self.comp_branches - 1)]
+        self._keep = []
         self.graphs, self.execs, self.use_priority = {}, {}, True
         self.done = None
         self.replays = 0
@@ -345,6 +350,7 @@ class GraphedStrandBatch:
             want = {"endpoints": 3 * E, "width": self.P, "opacity": self.P, "mask": self.P, "features": 3 * Mf * self.P}.get(k)
             if want is not None and (t.numel() != want or t.dtype != torch.float32 or t.device != dev or not t.is_contiguous()):
                 raise L.HgsError("grad_sink: tensors must be contiguous float32 on the render device, shaped like the parameters")
+        self._keep = []
         with torch.no_grad(), torch.cuda.device(dev):
             features = m.get_features.contiguous()      # cat(dc, rest): once per batch, shared by the views
             self._features = features
@@ -367,36 +373,59 @@ class GraphedStrandBatch:
                     ev = torch.cuda.Event()
                     ev.record(side)
                     bin_done.append(ev)
+            # compositing branches: view v composites, takes its loss and back-propagates on stream v % B.  With B > 1 the
+            # forward side of view v+1 runs next to the backward of view v and fills the tail of its grid (a compositor
+            # launch is ~80 % busy: heavy tiles first, the last ones trail); the backwards themselves are chained - each adds
+            # to the gradients the previous one wrote.
+            B = self.comp_branches
+            comp_streams = [main] + self.comp_streams[:B - 1]
+            for cs in comp_streams[1:]:
+                cs.wait_stream(main)
+            bwd_done = []
             for v in range(V):
                 if parts == "bin":
                     break
                 prm, inp = self._prm_inp(v, features)
-                if parts != "comp":
-                    main.wait_event(bin_done[v])
-                st = main.cuda_stream
-                L.check(lib.hgs_forward_stage_b_composite(ctypes.byref(prm), self.bg7.data_ptr(), self.geom[v].data_ptr(),
-                                                          self.binning[v].data_ptr(), self.img_ws[v].data_ptr(), cap,
-                                                          self.image[v].data_ptr(), st), "composite")
-                if self.dimage is not None:
-                    dimage = self.dimage
-                else:
-                    tgt = self.tgt_buf[v]
-                    terms, dimage = losses.hair_image_loss_raw(self.image[v], tgt[0:3], tgt[3], tgt[4], tgt[5], tgt[3] > 0.5,
-                                                               self.cam_buf[v][0:16].view(4, 4), weights,
-                                                               lam.get("bg_orient", (0.0, 0.0, 0.0)))
-                    self.terms[v].copy_(terms)
-                acc = self.acc[v]
-                vec = self.vec
-                grads = L.StrandGrads(dL_dmean2D=self.mean2d_grad[v].data_ptr(), dL_dconic=None if vec else acc[3 * self.P:].data_ptr(),
-                                      dL_dopacity=None if vec else acc[7 * self.P:].data_ptr(),
-                                      dL_dcolor=None if vec else acc[8 * self.P:].data_ptr(), acc16=acc.data_ptr() if vec else None,
-                                      dL_dendpoints=s.tensors["endpoints"].data_ptr(), dL_dwidth=s.tensors["width"].data_ptr(),
-                                      dL_dopacity_logit=s.tensors["opacity"].data_ptr(),
-                                      dL_dmask_logit=s.tensors["mask"].data_ptr(), dL_dfeatures=s.tensors["features"].data_ptr(),
-                                      accumulate=1 if (accumulate_first or v > 0) else 0)
-                L.check(lib.hgs_strands_backward(ctypes.byref(prm), ctypes.byref(inp), cap, self.geom[v].data_ptr(),
-                                                 self.binning[v].data_ptr(), self.img_ws[v].data_ptr(), dimage.data_ptr(),
-                                                 ctypes.byref(grads), st), "strands backward")
+                cs = comp_streams[v % B]
+                with torch.cuda.stream(cs):
+                    if parts != "comp":
+                        cs.wait_event(bin_done[v])
+                    st = cs.cuda_stream
+                    L.check(lib.hgs_forward_stage_b_composite(ctypes.byref(prm), self.bg7.data_ptr(), self.geom[v].data_ptr(),
+                                                              self.binning[v].data_ptr(), self.img_ws[v].data_ptr(), cap,
+                                                              self.image[v].data_ptr(), st), "composite")
+                    if self.dimage is not None:
+                        dimage = self.dimage
+                    else:
+                        tgt = self.tgt_buf[v]
+                        terms, dimage = losses.hair_image_loss_raw(self.image[v], tgt[0:3], tgt[3], tgt[4], tgt[5], tgt[3] > 0.5,
+                                                                   self.cam_buf[v][0:16].view(4, 4), weights,
+                                                                   lam.get("bg_orient", (0.0, 0.0, 0.0)))
+                        self.terms[v].copy_(terms)
+                        self._keep.append((terms, dimage))     # alive until the join: other branches must not reuse them
+                    acc = self.acc[v]
+                    vec = self.vec
+                    grads = L.StrandGrads(dL_dmean2D=self.mean2d_grad[v].data_ptr(), dL_dconic=None if vec else acc[3 * self.P:].data_ptr(),
+                                          dL_dopacity=None if vec else acc[7 * self.P:].data_ptr(),
+                                          dL_dcolor=None if vec else acc[8 * self.P:].data_ptr(), acc16=acc.data_ptr() if vec else None,
+                                          dL_dendpoints=s.tensors["endpoints"].data_ptr(), dL_dwidth=s.tensors["width"].data_ptr(),
+                                          dL_dopacity_logit=s.tensors["opacity"].data_ptr(),
+                                          dL_dmask_logit=s.tensors["mask"].data_ptr(), dL_dfeatures=s.tensors["features"].data_ptr(),
+                                          accumulate=1 if (accumulate_first or v > 0) else 0)
+                    # part 1 (backward compositor: this view's scratch only) may overlap other views' backwards; part 2
+                    # (preprocess backward: adds to the shared parameter gradients) is chained over the views
+                    bargs = (ctypes.byref(prm), ctypes.byref(inp), cap, self.geom[v].data_ptr(), self.binning[v].data_ptr(),
+                             self.img_ws[v].data_ptr(), dimage.data_ptr(), ctypes.byref(grads))
+                    L.check(lib.hgs_strands_backward_parts(*bargs, 1, st), "strands backward (compositor)")
+                    if B > 1 and v > 0:
+                        cs.wait_event(bwd_done[v - 1])
+                    L.check(lib.hgs_strands_backward_parts(*bargs, 2, st), "strands backward (preprocess)")
+                    if B > 1:
+                        ev = torch.cuda.Event()
+                        ev.record(cs)
+                        bwd_done.append(ev)
+            for cs in comp_streams[1:]:
+                main.wait_stream(cs)
             if self.dimage is None:
                 self.losses.copy_(self.terms[:, 0])
             main.wait_stream(side)                      # join

@@ -186,6 +186,14 @@ int hgs_strands_backward(const hgs_raster_params* prm, const hgs_strand_inputs* 
                          const void* geom_ws, const void* binning_ws, const void* image_ws, const float* dL_dpix,
                          const hgs_strand_grads* grads, void* stream);
 
+/* The backward in its two halves (ABI v4): parts & 1 = clear the per-Gaussian accumulators + backward compositor (touches
+ * only this view's scratch), parts & 2 = preprocess backward (writes / adds the PARAMETER gradients).  Views of one
+ * optimiser step that run on different streams may overlap their part 1; their part 2 must be ordered (it read-modify-
+ * writes the shared gradient tensors).  hgs_strands_backward == parts 3. */
+int hgs_strands_backward_parts(const hgs_raster_params* prm, const hgs_strand_inputs* in, int64_t capacity,
+                               const void* geom_ws, const void* binning_ws, const void* image_ws, const float* dL_dpix,
+                               const hgs_strand_grads* grads, int32_t parts, void* stream);
+
 int hgs_abi_version(void);
 const char* hgs_last_error(void);
 
