@@ -1273,7 +1273,7 @@ def run():
     can_fuse = cfg["kind"] == "strands" and tuple(cfg["sets"]) == ("sh", "mask", "orientation")
     ms_res_3pass, ms_e2e_3pass = ms_res, None
     ms_e2e_eager, graph_note = None, None
-    ms_res_eager, res_graph_note = None, None
+    ms_res_eager, res_graph_note, graph_setup_s = None, None, None
     h.setup_e2e(fused=False)
     ms_e2e, st_e2e = timed_loop(torch, h.step_e2e, args.steps, args.warmup, world, dev, flush, h.finish)
     if can_fuse:
@@ -1283,7 +1283,10 @@ def run():
         ms_res, st_res = timed_loop(torch, h.step_resident_fused, args.steps, args.warmup, world, dev, flush, h.finish)
         launches_per_step = count_launches(h.step_resident_fused)
         if not args.no_graph:
+            t0 = time.perf_counter()
             h.setup_fused_graph()
+            torch.cuda.synchronize(dev)
+            graph_setup_s = time.perf_counter() - t0     # measure_plan (one eager view per camera) + warm-up + capture
             if h.fgraph is not None:
                 ms_res_eager = ms_res
                 ms_res, st_res = timed_loop(torch, h.step_resident_fused_graph, args.steps, args.warmup, world, dev, flush,
@@ -1388,6 +1391,10 @@ def run():
         line["value_dropin_3pass"] = line["dropin"]["value"]
         if ms_res_eager is not None:
             line["value_eager"] = round(views / (ms_res_eager / 1000.0), 2)
+        if graph_setup_s is not None:
+            # what a topology edit costs before the replays resume (Hair-GS edits the strands every 100 iterations,
+            # train.py:196-200): re-measuring the plan on this rank's cameras + warm-up batches + two captures
+            line["graph_replan_and_capture_s"] = round(graph_setup_s, 3)
         line["e2e"]["value_dropin_3pass"] = line["dropin"]["e2e"]
         line["e2e"]["api"] = ("hairgs_b200.fused.render_strands() + hairgs_b200.losses."
                               + ("hair_image_loss()" if h.hair_loss else "weighted_l1()") +

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 #include "hgs_common.cuh"
 
@@ -37,20 +38,23 @@ int stage_check(const char* stage, int debug, cudaStream_t s) {
 }
 
 // ---- stage profiler -------------------------------------------------------------------------------
-static bool g_prof_on = false;
-static int64_t g_launches[HGS_STAGE_COUNT] = {0};
+// process-wide (a profiler is), guarded: launches may come from several host threads (one per device / stream)
+static std::atomic<bool> g_prof_on{false};
+static std::atomic<long long> g_launches[HGS_STAGE_COUNT];
 struct ProfRec { int stage; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mutex;
 
 StageScope::StageScope(int stage_id, cudaStream_t s) : stage(stage_id), stream(s), stop(nullptr) {
-    g_launches[stage]++;
-    if (g_prof_on) {
+    g_launches[stage].fetch_add(1, std::memory_order_relaxed);
+    if (g_prof_on.load(std::memory_order_relaxed)) {
         ProfRec r;
         r.stage = stage;
         cudaEventCreate(&r.a);
         cudaEventCreate(&r.b);
         cudaEventRecord(r.a, stream);
         stop = r.b;
+        std::lock_guard<std::mutex> lock(g_prof_mutex);
         g_prof.push_back(r);
     }
 }
@@ -130,12 +134,13 @@ int hgs_debug_set_stats(void* dev_ptr) { return set_fwd_stats(dev_ptr); }
 int hgs_debug_set_composite_blocks(int mode) { return set_composite_blocks(mode); }
 
 int hgs_profile_enable(int on) {
-    g_prof_on = on != 0;
+    g_prof_on.store(on != 0);
     return HGS_OK;
 }
 
 int hgs_profile_collect(double* ms, int64_t* launches) {
     if (int e = check_cuda(cudaDeviceSynchronize(), "profile sync")) return e;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     for (auto& r : g_prof) {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && ms) ms[r.stage] += (double)t;
@@ -144,8 +149,8 @@ int hgs_profile_collect(double* ms, int64_t* launches) {
     }
     g_prof.clear();
     for (int i = 0; i < HGS_STAGE_COUNT; ++i) {
-        if (launches) launches[i] += g_launches[i];
-        g_launches[i] = 0;
+        const long long n = g_launches[i].exchange(0);
+        if (launches) launches[i] += n;
     }
     return HGS_OK;
 }

@@ -11,6 +11,8 @@
 // reference build's bit for bit.
 #include "hgs_common.cuh"
 
+#include <cstdlib>
+
 namespace hgs {
 
 __device__ __constant__ float kSH_C0 = 0.28209479177387814f;
@@ -38,6 +40,8 @@ struct PreArgs {
     int32_t* radii;
     GeomLayout g;
     uint32_t nblocks;
+    int vec_sh;                  // SH rows through 128-bit loads (rows 16-byte aligned and M >= 4)
+    int vec_rows;                // [P,3] attribute rows through 128-bit loads + a per-warp shared-memory transpose
     int count_lists;             // HGS_SORT_TILE: count the instances per (tile, depth slice) list
     uint32_t slice_base;         // depth-slice hints of the tile-partitioned binning (hgs_raster_params.slice_base / _shift)
     int slice_shift;
@@ -67,7 +71,13 @@ struct StrandGeom {
 __device__ __forceinline__ StrandGeom strand_geom(const float* __restrict__ endpoints, const long long* __restrict__ pairs,
                                                   const float* __restrict__ width, int idx, float mod) {
     StrandGeom sg;
-    const long long i0 = pairs[2 * (size_t)idx], i1 = pairs[2 * (size_t)idx + 1];
+    long long i0, i1;
+    if ((reinterpret_cast<uintptr_t>(pairs) & 15) == 0) {   // one 128-bit load for the index pair
+        const longlong2 pr = reinterpret_cast<const longlong2*>(pairs)[idx];
+        i0 = pr.x; i1 = pr.y;
+    } else {
+        i0 = pairs[2 * (size_t)idx]; i1 = pairs[2 * (size_t)idx + 1];
+    }
     const float3 e0 = make_float3(endpoints[3 * i0], endpoints[3 * i0 + 1], endpoints[3 * i0 + 2]);
     const float3 e1 = make_float3(endpoints[3 * i1], endpoints[3 * i1 + 1], endpoints[3 * i1 + 2]);
     sg.mean = make_float3((e0.x + e1.x) * 0.5f, (e0.y + e1.y) * 0.5f, (e0.z + e1.z) * 0.5f);
@@ -176,7 +186,10 @@ __device__ __forceinline__ float3 cov2d_ewa(const float3 mean, float focal_x, fl
 }
 
 // SH basis evaluation (forward.cu:20-71), one colour channel at a time; sh points at coefficient 0
-// of this Gaussian, layout [k][3].
+// of this Gaussian, layout [k][3].  kVec: the row is read with 128-bit loads, one batch per degree (coefficients 0-3 =
+// floats 0-11, degree 2 = floats 12-27, degree 3 = floats 28-47) so that at most 20 coefficients are live - 12 LDG.128
+// instead of 48 LDG.32 for a degree-3 row (needs a 16-byte aligned row: M * 3 floats a multiple of 4 and an aligned base).
+template <bool kVec>
 __device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ sh, const float3 pos,
                                             const float3 campos, uint32_t& clamp_bits) {
     float3 dir = make_float3(pos.x - campos.x, pos.y - campos.y, pos.z - campos.z);
@@ -185,31 +198,52 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ s
     dir.y = dir.y / len;
     dir.z = dir.z / len;
     float res[3];
+    float a[12], b[16], cc[20];
+    const float4* s4 = reinterpret_cast<const float4*>(sh);
+    auto load4 = [&](float* dst, int first, int count) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) res[c] = kSH_C0 * sh[0 * 3 + c];
+        for (int q = 0; q < count; ++q) {
+            const float4 v = s4[first + q];
+            dst[4 * q] = v.x; dst[4 * q + 1] = v.y; dst[4 * q + 2] = v.z; dst[4 * q + 3] = v.w;
+        }
+    };
+    // coefficient k, channel c: from the batch that holds float k*3+c (vector path) or straight from memory
+    auto S = [&](int k, int c) -> float {
+        const int i = k * 3 + c;
+        if (!kVec) return sh[i];
+        return i < 12 ? a[i] : (i < 28 ? b[i - 12] : cc[i - 28]);
+    };
+    if (kVec) {
+        if (deg > 0) load4(a, 0, 3);
+        else { a[0] = sh[0]; a[1] = sh[1]; a[2] = sh[2]; }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) res[c] = kSH_C0 * S(0, c);
     if (deg > 0) {
         const float x = dir.x, y = dir.y, z = dir.z;
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-            res[c] = res[c] - kSH_C1 * y * sh[1 * 3 + c] + kSH_C1 * z * sh[2 * 3 + c] - kSH_C1 * x * sh[3 * 3 + c];
+            res[c] = res[c] - kSH_C1 * y * S(1, c) + kSH_C1 * z * S(2, c) - kSH_C1 * x * S(3, c);
         if (deg > 1) {
+            if (kVec) load4(b, 3, 4);
             const float xx = x * x, yy = y * y, zz = z * z;
             const float xy = x * y, yz = y * z, xz = x * z;
 #pragma unroll
             for (int c = 0; c < 3; ++c)
-                res[c] = res[c] + kSH_C2[0] * xy * sh[4 * 3 + c] + kSH_C2[1] * yz * sh[5 * 3 + c] +
-                         kSH_C2[2] * (2.0f * zz - xx - yy) * sh[6 * 3 + c] + kSH_C2[3] * xz * sh[7 * 3 + c] +
-                         kSH_C2[4] * (xx - yy) * sh[8 * 3 + c];
+                res[c] = res[c] + kSH_C2[0] * xy * S(4, c) + kSH_C2[1] * yz * S(5, c) +
+                         kSH_C2[2] * (2.0f * zz - xx - yy) * S(6, c) + kSH_C2[3] * xz * S(7, c) +
+                         kSH_C2[4] * (xx - yy) * S(8, c);
             if (deg > 2) {
+                if (kVec) load4(cc, 7, 5);
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    res[c] = res[c] + kSH_C3[0] * y * (3.0f * xx - yy) * sh[9 * 3 + c] +
-                             kSH_C3[1] * xy * z * sh[10 * 3 + c] +
-                             kSH_C3[2] * y * (4.0f * zz - xx - yy) * sh[11 * 3 + c] +
-                             kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[12 * 3 + c] +
-                             kSH_C3[4] * x * (4.0f * zz - xx - yy) * sh[13 * 3 + c] +
-                             kSH_C3[5] * z * (xx - yy) * sh[14 * 3 + c] +
-                             kSH_C3[6] * x * (xx - 3.0f * yy) * sh[15 * 3 + c];
+                    res[c] = res[c] + kSH_C3[0] * y * (3.0f * xx - yy) * S(9, c) +
+                             kSH_C3[1] * xy * z * S(10, c) +
+                             kSH_C3[2] * y * (4.0f * zz - xx - yy) * S(11, c) +
+                             kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * S(12, c) +
+                             kSH_C3[4] * x * (4.0f * zz - xx - yy) * S(13, c) +
+                             kSH_C3[5] * z * (xx - yy) * S(14, c) +
+                             kSH_C3[6] * x * (xx - 3.0f * yy) * S(15, c);
             }
         }
     }
@@ -256,6 +290,13 @@ __device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long 
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
 
+// SH colour of Gaussian idx: vector row loads when the rows are 16-byte aligned (a.vec_sh, decided on the host)
+__device__ __forceinline__ float3 sh_row_to_rgb(const PreArgs& a, int idx, const float3 pos, uint32_t& clamp_bits) {
+    const float* row = a.shs + (size_t)idx * a.M * 3;
+    const float3 campos = make_float3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]);
+    return a.vec_sh ? sh_to_rgb<true>(a.D, row, pos, campos, clamp_bits) : sh_to_rgb<false>(a.D, row, pos, campos, clamp_bits);
+}
+
 template <bool kStrand>
 __global__ void __launch_bounds__(kPreprocThreads, 6) preprocess_fwd_kernel(const PreArgs a) {
     const int idx = (int)(blockIdx.x * kPreprocThreads + threadIdx.x);
@@ -264,6 +305,24 @@ __global__ void __launch_bounds__(kPreprocThreads, 6) preprocess_fwd_kernel(cons
     int radius_i = 0;
     uint2 vis_rmin = make_uint2(0, 0), vis_rmax = make_uint2(0, 0);
     uint32_t vis_slice = 0;
+    // [P,3] float rows (means3D, scales): a warp's 32 rows are 384 contiguous bytes = 24 x 128-bit loads instead of 3 x 32
+    // scalar ones at a 12-byte stride (north_star item 1); a per-warp shared-memory transpose (no block barrier) hands every
+    // lane its row.  Only for full warps and 16-byte aligned arrays; otherwise the scalar loads below.
+    __shared__ float s_rows[kStrand ? 1 : kPreprocThreads / 32][2][kStrand ? 1 : 96];
+    bool rows_ready = false;
+    if (!kStrand && a.vec_rows) {
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int wbase = (int)(blockIdx.x * kPreprocThreads + warp * 32);
+        rows_ready = wbase + 32 <= a.P && ((reinterpret_cast<uintptr_t>(a.means3D) | reinterpret_cast<uintptr_t>(a.scales)) & 15) == 0;
+        if (rows_ready) {
+            if (lane < 24) {
+                reinterpret_cast<float4*>(s_rows[warp][0])[lane] = ldg_stream4(reinterpret_cast<const float4*>(a.means3D + 3 * (size_t)wbase) + lane);
+                if (a.scales)
+                    reinterpret_cast<float4*>(s_rows[warp][1])[lane] = ldg_stream4(reinterpret_cast<const float4*>(a.scales + 3 * (size_t)wbase) + lane);
+            }
+            __syncwarp();
+        }
+    }
     if (idx < a.P) {
         // start every input stream now: the cull / degenerate early-outs below would otherwise serialise them
         if (kStrand) {
@@ -285,6 +344,9 @@ __global__ void __launch_bounds__(kPreprocThreads, 6) preprocess_fwd_kernel(cons
             if (kStrand) {
                 sg = strand_geom(a.endpoints, a.pairs, a.width, idx, a.scale_modifier);
                 p_orig = sg.mean;
+            } else if (rows_ready) {
+                const float* r = s_rows[threadIdx.x >> 5][0] + 3 * (threadIdx.x & 31);
+                p_orig = make_float3(r[0], r[1], r[2]);
             } else {
                 p_orig = make_float3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
             }
@@ -303,7 +365,9 @@ __global__ void __launch_bounds__(kPreprocThreads, 6) preprocess_fwd_kernel(cons
             } else if (a.cov3D_precomp != nullptr) {
                 cov3D = a.cov3D_precomp + (size_t)idx * 6;
             } else {
-                const float3 sc = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
+                const float* sr = s_rows[kStrand ? 0 : (threadIdx.x >> 5)][kStrand ? 0 : 1] + (kStrand ? 0 : 3 * (threadIdx.x & 31));
+                const float3 sc = rows_ready ? make_float3(sr[0], sr[1], sr[2])
+                                             : make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
                 const float4 rq = load_quat(a.rotations, idx);
                 cov3d_from_scale_rot(sc, a.scale_modifier, rq, cov3D_local);
                 cov3D = cov3D_local;
@@ -331,15 +395,13 @@ __global__ void __launch_bounds__(kPreprocThreads, 6) preprocess_fwd_kernel(cons
             if (kStrand) {
                 // 7 channels in one pass: SH colour, mask, world-space strand direction (loss/losses.py:246-249,311-312)
                 uint32_t cb;
-                const float3 c = sh_to_rgb(a.D, a.shs + (size_t)idx * a.M * 3, p_orig,
-                                           make_float3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]), cb);
+                const float3 c = sh_row_to_rgb(a, idx, p_orig, cb);
                 reinterpret_cast<float4*>(rgb_out)[0] = make_float4(c.x, c.y, c.z, sigmoidf_(a.mask_logit[idx]));
                 reinterpret_cast<float4*>(rgb_out)[1] = make_float4(sg.ohat.x, sg.ohat.y, sg.ohat.z, 0.f);
                 a.g.clamped[idx] = (uint8_t)cb;
             } else if (a.colors_precomp == nullptr) {
                 uint32_t cb;
-                const float3 c = sh_to_rgb(a.D, a.shs + (size_t)idx * a.M * 3, p_orig,
-                                           make_float3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]), cb);
+                const float3 c = sh_row_to_rgb(a, idx, p_orig, cb);
                 *reinterpret_cast<float4*>(rgb_out) = make_float4(c.x, c.y, c.z, 0.f);
                 a.g.clamped[idx] = (uint8_t)cb;
             } else {
@@ -1066,6 +1128,10 @@ int launch_preprocess_fwd(const hgs_raster_params* prm, const hgs_raster_inputs*
     a.nblocks = (prm->P + kPreprocThreads - 1) / kPreprocThreads;
     a.slice_base = (uint32_t)prm->slice_base; a.slice_shift = prm->slice_shift <= 0 ? 32 : prm->slice_shift;
     a.count_lists = prm->sort_mode == HGS_SORT_TILE;
+    // HGS_PRE_VEC=0: scalar row loads (A/B, profiles/r2_preprocess_vec.md)
+    static const int vec_rows = [] { const char* e = getenv("HGS_PRE_VEC"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+    a.vec_rows = vec_rows;
+    a.vec_sh = vec_rows && in->shs != nullptr && (prm->M * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(in->shs) & 15) == 0;
     a.endpoints = nullptr; a.pairs = nullptr; a.width = nullptr; a.opacity_logit = nullptr; a.mask_logit = nullptr;
     if (int e = check_cuda(cudaMemsetAsync(g.hdr, 0, g.clear_bytes, s), "memset geom header")) return e;
     {
@@ -1094,6 +1160,8 @@ int launch_strand_preprocess_fwd(const hgs_raster_params* prm, const hgs_strand_
     a.nblocks = (prm->P + kPreprocThreads - 1) / kPreprocThreads;
     a.slice_base = (uint32_t)prm->slice_base; a.slice_shift = prm->slice_shift <= 0 ? 32 : prm->slice_shift;
     a.count_lists = prm->sort_mode == HGS_SORT_TILE;
+    a.vec_rows = 0;
+    a.vec_sh = in->features != nullptr && (prm->M * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(in->features) & 15) == 0;
     a.endpoints = in->endpoints; a.pairs = (const long long*)in->endpoint_pairs; a.width = in->width;
     a.opacity_logit = in->opacity_logit; a.mask_logit = in->mask_logit;
     if (int e = check_cuda(cudaMemsetAsync(g.hdr, 0, g.clear_bytes, s), "memset geom header")) return e;

@@ -1246,3 +1246,14 @@ def test_unpack_targets_matches_torch():
     assert torch.equal(one, ref[1])
     with pytest.raises(Exception):
         losses.unpack_targets(rgbm.cpu(), tc.cpu())
+
+
+def test_prefiltered_is_accepted_and_changes_nothing():
+    """A5's `prefiltered` argument: the reference only uses it to TRAP when a Gaussian the caller claimed visible is culled
+    (auxiliary.h:156-160); Hair-GS always passes False (gaussian_renderer/__init__.py:67).  Here it is accepted and has no
+    effect on any output (the trap is not reproduced: documented in DESIGN.md)."""
+    import diff_gaussian_rasterization._C as ours_C
+    d = common.blob_inputs(5000, 128, 96, dev(), seed=61)
+    a = ours_C.rasterize_gaussians(*common.fwd_args(d))
+    b = ours_C.rasterize_gaussians(*common.fwd_args(dict(d, prefiltered=True)))
+    assert a[0] == b[0] and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
