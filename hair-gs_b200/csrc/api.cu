@@ -75,7 +75,7 @@ int launch_emit_keys(int, const GeomLayout&, const uint2*, uint64_t*, uint32_t*,
 int launch_sort_pairs(int64_t, const uint32_t*, int, uint64_t* [2], uint32_t* [2], void*, int*, cudaStream_t, GeomHeader*, int, int);
 int launch_finalize_sorted(int, int64_t, const uint32_t*, const uint64_t*, const uint32_t*, const GeomLayout&,
                            const BinningLayout&, uint2*,
-                           uint32_t*, size_t, cudaStream_t);
+                           uint32_t*, size_t, uint32_t, cudaStream_t);
 int launch_composite_fwd(int, const ImageLayout&, const BinningLayout&, int, int, const float*, float*, cudaStream_t);
 int launch_composite_bwd(int, const ImageLayout&, const BinningLayout&, const uint32_t*, int, int, const float*,
                          const float*, const hgs_raster_grads*, float*, cudaStream_t);
@@ -230,7 +230,7 @@ static int stage_b_impl(const hgs_raster_params* prm, const float* background, v
         if (int e = launch_sort_pairs(N, n_ptr, end_bit_for(prm), b.keys, b.vals, b.sort_ws, &res, s, g.hdr, depth_bits_for(prm),
                                       start)) return e;
         if (int e = stage_check("sort", prm->debug, s)) return e;
-        if (int e = launch_finalize_sorted(prm->channels, N, n_ptr, b.keys[res], b.vals[res], g, b, im.ranges, im.tile_order, (size_t)gx * gy, s)) return e;
+        if (int e = launch_finalize_sorted(prm->channels, N, n_ptr, b.keys[res], b.vals[res], g, b, im.ranges, im.tile_order, (size_t)gx * gy, gx, s)) return e;
         if (int e = stage_check("finalize_sorted", prm->debug, s)) return e;
     }
     if (parts & 2) {

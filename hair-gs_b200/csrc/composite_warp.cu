@@ -47,9 +47,10 @@ __global__ void __launch_bounds__(256) finalize_sorted_kernel(uint32_t cap, cons
                                                               const uint64_t* __restrict__ keys,
                                                               const uint32_t* __restrict__ point_list,
                                                               const float4* __restrict__ rec,
-                                                              const float* __restrict__ rgb, uint2* __restrict__ ranges,
+                                                              const float* __restrict__ rgb, uint32_t tiles_x,
+                                                              uint2* __restrict__ ranges,
                                                               float4* __restrict__ pk_lo, float4* __restrict__ pk_hi,
-                                                              float4* __restrict__ pk_col) {
+                                                              float4* __restrict__ pk_col, uint16_t* __restrict__ pk_mask) {
     const uint32_t L = n_ptr ? min(*n_ptr, cap) : cap;
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= L) return;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(256) finalize_sorted_kernel(uint32_t cap, cons
     if (CS > 4) pk_col[(size_t)idx * (CS / 4) + 1] = *reinterpret_cast<const float4*>(rgb + (size_t)id * CS + 4);
     // tile ranges (rasterizer_impl.cu:116-138)
     const uint32_t cur = (uint32_t)(keys[idx] >> 32);
+    pk_mask[idx] = (uint16_t)block_mask16(lo, hi, (cur % tiles_x) * HGS_TILE, (cur / tiles_x) * HGS_TILE);
     if (idx == 0) {
         ranges[cur].x = 0;
     } else {
@@ -288,12 +290,13 @@ struct __align__(128) FwdBulkSmem {
     uint64_t bar[kFwdStages];
 };
 
-template <int C, int CS, bool kStats, bool kBulk>
+template <int C, int CS, bool kStats, bool kBulk, bool kMask>
 __global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __restrict__ ranges,
                                                                  const uint32_t* __restrict__ tile_order, int W, int H,
                                                                  const float4* __restrict__ pk_lo,
                                                                  const float4* __restrict__ pk_hi,
                                                                  const float4* __restrict__ pk_col,
+                                                                 const uint16_t* __restrict__ pk_mask,
                                                                  const float* __restrict__ bg_color,
                                                                  float* __restrict__ final_T,
                                                                  uint32_t* __restrict__ n_contrib,
@@ -411,6 +414,9 @@ __global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __
     if (!__all_sync(0xffffffffu, done) && nchunks > 0) {
         float4 nlo = make_float4(0, 0, 0, 0), nhi = make_float4(0, 0, 0, 0), nc0 = make_float4(0, 0, 0, 0),
                nc1 = make_float4(0, 0, 0, 0);
+        uint32_t nmask = 0, nmask2 = 0;
+        // kMask: this warp's two blocks in the instance masks (block_mask16): block row = warp / 2, columns 2 (warp & 1) + half
+        const uint32_t bit_a = 1u << (4 * (warp >> 1) + 2 * (warp & 1)), bits_ab = 3u * bit_a;
         // kBulk: lane 0 asks the TMA engine for chunk c (three contiguous pieces) into stage c & 1
         auto issue = [&](int c) {
             if (lane == 0) {
@@ -430,6 +436,17 @@ __global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __
                 issue(k);
                 issued = k;
             }
+        } else if (kMask) {
+            // masks run two chunks ahead of the walk, the records of the lanes they select one chunk ahead
+            if ((int)lane < total) nmask = pk_mask[(size_t)range.x + lane];
+            if (32 + (int)lane < total) nmask2 = pk_mask[(size_t)range.x + 32 + lane];
+            if (nmask & bits_ab) {
+                const size_t i = (size_t)range.x + lane;
+                nlo = pk_lo[i];
+                nhi = pk_hi[i];
+                nc0 = pk_col[i * (CS / 4)];
+                if (CS > 4) nc1 = pk_col[i * (CS / 4) + 1];
+            }
         } else if ((int)lane < total) {
             const size_t i = (size_t)range.x + lane;
             nlo = pk_lo[i];
@@ -441,7 +458,28 @@ __global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __
         for (int c = 0; c < nchunks; ++c) {
             float4 lo, hi, c0, c1 = make_float4(0, 0, 0, 0);
             const bool have = c * 32 + (int)lane < total;
-            if (kBulk) {
+            bool cand_a, cand_b;
+            if (kMask) {
+                // the chunk's 32 block masks are 64 bytes; only the lanes whose instance reaches one of the warp's two blocks
+                // read its record (prefetched while the previous chunk was blended, like the masks of the chunk after)
+                const uint32_t m = nmask;
+                lo = nlo; hi = nhi; c0 = nc0; c1 = nc1;
+                nmask = nmask2;
+                nmask2 = 0;
+                if (c + 2 < nchunks) {
+                    const int p = (c + 2) * 32 + (int)lane;
+                    if (p < total) nmask2 = pk_mask[(size_t)range.x + p];
+                }
+                if (nmask & bits_ab) {
+                    const size_t i = (size_t)range.x + (size_t)((c + 1) * 32) + lane;
+                    nlo = pk_lo[i];
+                    nhi = pk_hi[i];
+                    nc0 = pk_col[i * (CS / 4)];
+                    if (CS > 4) nc1 = pk_col[i * (CS / 4) + 1];
+                }
+                cand_a = (m & bit_a) != 0;
+                cand_b = (m & (bit_a << 1)) != 0;
+            } else if (kBulk) {
                 // the stage of chunk c + kFwdStages - 1 held chunk c - 1, which every lane has copied out (the __syncwarp
                 // below orders those reads before the engine's writes)
                 if (c + kFwdStages - 1 < nchunks) {
@@ -468,11 +506,13 @@ __global__ void __launch_bounds__(256) composite_fwd_half_kernel(const uint2* __
                     }
                 }
             }
-            // culled only when a comparison is TRUE, so NaNs keep the instance (the reference would evaluate it)
-            const float xl = lo.x - hi.z, xr = lo.x + hi.z;
-            const bool in_rows = have && !(lo.y - hi.w > wy1 || lo.y + hi.w < wy0);
-            const bool cand_a = in_rows && !(xl > ax1 || xr < ax0);
-            const bool cand_b = in_rows && !(xl > bx1 || xr < bx0);
+            if (!kMask) {
+                // culled only when a comparison is TRUE, so NaNs keep the instance (the reference would evaluate it)
+                const float xl = lo.x - hi.z, xr = lo.x + hi.z;
+                const bool in_rows = have && !(lo.y - hi.w > wy1 || lo.y + hi.w < wy0);
+                cand_a = in_rows && !(xl > ax1 || xr < ax0);
+                cand_b = in_rows && !(xl > bx1 || xr < bx0);
+            }
             const uint32_t bits_a = __ballot_sync(0xffffffffu, cand_a);
             const uint32_t bits_b = __ballot_sync(0xffffffffu, cand_b);
             if (kStats) st_chunks++;
@@ -793,6 +833,12 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_kernel(
 //            candidate of either half) issue the red.global.adds.
 // cfg3, CPU model of the queue policy (tools/block_shape_study.py): 26 % fewer phase-1 trips than the 8x4 kernel; an
 // instance that reaches both halves is accumulated by both (1.3x the candidates, each over 16 instead of 32 pixels).
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 template <int CS>
 struct BwdHalfSmem {
     static constexpr int QN = 40;   // ring capacity per half: 32 new + <= 8 carried over
@@ -813,13 +859,13 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 
 // kVec: gradients accumulate into ONE interleaved 64-byte record per Gaussian (hgs_strand_grads.acc16, passed in
 // dL_dmean2D) with four red.global.add.v4.f32 instead of 6 + C scalar atomics.
-template <int C, int CS, bool kVec>
+template <int C, int CS, bool kVec, bool kMask>
 __global__ void __launch_bounds__(256, 3) composite_bwd_half_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
     const uint32_t* __restrict__ point_list, int W, int H,
     const float* __restrict__ bg_color, const float4* __restrict__ pk_lo, const float4* __restrict__ pk_hi,
-    const float4* __restrict__ pk_col, const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
-    const float* __restrict__ dL_dpixels, float* __restrict__ dL_dmean2D /*[P,3]*/,
+    const float4* __restrict__ pk_col, const uint16_t* __restrict__ pk_mask, const float* __restrict__ final_Ts,
+    const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels, float* __restrict__ dL_dmean2D /*[P,3]*/,
     float* __restrict__ dL_dconic /*[P,4]*/, float* __restrict__ dL_dopacity /*[P]*/,
     float* __restrict__ dL_dcolors /*[P,C]*/) {
     using WS = BwdHalfSmem<CS>;
@@ -902,7 +948,10 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_half_kernel(
         // composite_bwd_kernel for the scalar form of the colour recurrence
         auto recur = [&](uint32_t g, uint32_t slot, float G, float alpha) {
             const float om = 1.f - alpha;
-            const float rcp = 1.f / om;
+            // om lies in [0.01, 1]: MUFU.RCP (<= 1 ulp) instead of the IEEE division sequence (8 instructions with its range
+            // check and slow-path call); the reference divides T by om (backward_distwar.cu:963), either way T is a
+            // reconstruction good to ~1 ulp per step
+            const float rcp = rcp_approx(om);
             T = T * rcp;
             const float dchannel_dcolor = alpha * T;
             const float* col = reinterpret_cast<const float*>(&my_col[slot * (CS / 4)]);
@@ -1009,28 +1058,25 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_half_kernel(
     // back to front: lane l of chunk c holds list position total-1-(c*32+l)
     float4 nlo = make_float4(0, 0, 0, 0), nhi = make_float4(0, 0, 0, 0), nc0 = make_float4(0, 0, 0, 0),
            nc1 = make_float4(0, 0, 0, 0);
-    uint32_t nid = 0;
+    uint32_t nid = 0, nmask = 0, nmask2 = 0;
+    // kMask: this warp's two blocks in the instance masks (block_mask16): block row = warp / 2, columns 2 (warp & 1) + half.
+    // Masks run two chunks ahead of the walk, the records of the lanes they select one chunk ahead.
+    const uint32_t bit_a = 1u << (4 * (warp >> 1) + 2 * (warp & 1)), bits_ab = 3u * bit_a;
     {
         const int pos = total - 1 - (int)lane;
+        if (kMask && pos >= 32) nmask2 = pk_mask[(size_t)range.x + pos - 32];
         if (pos >= 0) {
             const size_t i = (size_t)range.x + pos;
-            nlo = pk_lo[i];
-            nhi = pk_hi[i];
-            nc0 = pk_col[i * (CS / 4)];
-            if (CS > 4) nc1 = pk_col[i * (CS / 4) + 1];
-            nid = point_list[i];
-        }
-    }
-    __syncwarp();
-    for (int c = 0; c < nchunks; ++c) {
-        const float4 lo = nlo, hi = nhi, c0 = nc0, c1 = nc1;
-        const uint32_t id = nid;
-        const int my_pos = total - 1 - c * 32 - (int)lane;
-        const bool have = my_pos >= 0;
-        if (c + 1 < nchunks) {
-            const int pos = my_pos - 32;
-            if (pos >= 0) {
-                const size_t i = (size_t)range.x + pos;
+            if (kMask) {
+                nmask = pk_mask[i];
+                if (nmask & bits_ab) {
+                    nlo = pk_lo[i];
+                    nhi = pk_hi[i];
+                    nc0 = pk_col[i * (CS / 4)];
+                    if (CS > 4) nc1 = pk_col[i * (CS / 4) + 1];
+                    nid = point_list[i];
+                }
+            } else {
                 nlo = pk_lo[i];
                 nhi = pk_hi[i];
                 nc0 = pk_col[i * (CS / 4)];
@@ -1038,13 +1084,53 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_half_kernel(
                 nid = point_list[i];
             }
         }
-        // extents relative to the warp's block origin, so the four block edges are immediates (the rounding of the
-        // extra subtraction, <= 2^-22 relative, is far inside the padding of the extents: preprocess.cu alpha_extent)
-        const float xl = (lo.x - hi.z) - ax0, xr = (lo.x + hi.z) - ax0;
-        const float yt = (lo.y - hi.w) - wy0, yb = (lo.y + hi.w) - wy0;
-        const bool in_rows = have && !(yt > 3.f || yb < 0.f);
-        const bool cand_a = in_rows && my_pos < total_a && !(xl > 3.f || xr < 0.f);
-        const bool cand_b = in_rows && my_pos < total_b && !(xl > 7.f || xr < 4.f);
+    }
+    __syncwarp();
+    for (int c = 0; c < nchunks; ++c) {
+        const float4 lo = nlo, hi = nhi, c0 = nc0, c1 = nc1;
+        const uint32_t id = nid;
+        const uint32_t m = nmask;
+        const int my_pos = total - 1 - c * 32 - (int)lane;
+        const bool have = my_pos >= 0;
+        nmask = nmask2;
+        nmask2 = 0;
+        if (kMask && my_pos >= 64) nmask2 = pk_mask[(size_t)range.x + my_pos - 64];
+        if (c + 1 < nchunks) {
+            const int pos = my_pos - 32;
+            if (pos >= 0) {
+                const size_t i = (size_t)range.x + pos;
+                if (kMask) {
+                    if (nmask & bits_ab) {
+                        nlo = pk_lo[i];
+                        nhi = pk_hi[i];
+                        nc0 = pk_col[i * (CS / 4)];
+                        if (CS > 4) nc1 = pk_col[i * (CS / 4) + 1];
+                        nid = point_list[i];
+                    }
+                } else {
+                    nlo = pk_lo[i];
+                    nhi = pk_hi[i];
+                    nc0 = pk_col[i * (CS / 4)];
+                    if (CS > 4) nc1 = pk_col[i * (CS / 4) + 1];
+                    nid = point_list[i];
+                }
+            }
+        }
+        bool cand_a, cand_b;
+        if (kMask) {
+            // (positions before the list start carry mask 0); only the lanes whose instance reaches one of the warp's two
+            // blocks go on to read its record
+            cand_a = (m & bit_a) != 0 && my_pos < total_a;
+            cand_b = (m & (bit_a << 1)) != 0 && my_pos < total_b;
+        } else {
+            // extents relative to the warp's block origin, so the four block edges are immediates (the rounding of the
+            // extra subtraction, <= 2^-22 relative, is far inside the padding of the extents: preprocess.cu alpha_extent)
+            const float xl = (lo.x - hi.z) - ax0, xr = (lo.x + hi.z) - ax0;
+            const float yt = (lo.y - hi.w) - wy0, yb = (lo.y + hi.w) - wy0;
+            const bool in_rows = have && !(yt > 3.f || yb < 0.f);
+            cand_a = in_rows && my_pos < total_a && !(xl > 3.f || xr < 0.f);
+            cand_b = in_rows && my_pos < total_b && !(xl > 7.f || xr < 4.f);
+        }
         const uint32_t bits_a = __ballot_sync(0xffffffffu, cand_a);
         const uint32_t bits_b = __ballot_sync(0xffffffffu, cand_b);
         if (!(bits_a | bits_b)) continue;
@@ -1081,9 +1167,20 @@ struct PackedView {
     float4* lo;
     float4* hi;
     float4* col;
+    uint16_t* mask;
 };
 
-static PackedView packed_view(const BinningLayout& b) { return PackedView{b.pk_lo, b.pk_hi, b.pk_col}; }
+static PackedView packed_view(const BinningLayout& b) { return PackedView{b.pk_lo, b.pk_hi, b.pk_col, b.pk_mask}; }
+
+// How the half-warp compositors find the instances that reach their two 4x4 blocks: by testing every instance's extent per
+// warp (default) or, HGS_WALK=mask, from the per-instance block masks written with the sorted records - only the lanes whose
+// instance reaches a block then read its 68-byte record.  Both select exactly the same instances.  Measured on cfg3
+// (profiles/r2_block_mask.md): the mask walk moves 3.5x fewer bytes through L1 but issues as many warp instructions (a chunk
+// nearly always has SOME candidate lane, so the predicated record loads are issued anyway): forward 5 % slower, backward equal.
+static bool walk_by_mask() {
+    static const bool v = [] { const char* e = getenv("HGS_WALK"); return e != nullptr && strcmp(e, "mask") == 0; }();
+    return v;
+}
 
 // Pixel-block shape of the compositors: two 4x4 blocks per warp (default) or one 8x4 block per warp (the round-1 kernels,
 // kept for A/B measurements: profiles/r1_*).  Both produce identical outputs.  Selected by the environment variable
@@ -1110,7 +1207,7 @@ static bool composite_blocks_4x4() {
 int launch_finalize_sorted(int channels, int64_t n, const uint32_t* n_ptr, const uint64_t* keys_sorted,
                            const uint32_t* point_list,
                            const GeomLayout& g, const BinningLayout& b, uint2* ranges, uint32_t* tile_order, size_t tiles,
-                           cudaStream_t s) {
+                           uint32_t tiles_x, cudaStream_t s) {
     if (int e = check_cuda(cudaMemsetAsync(ranges, 0, tiles * sizeof(uint2), s), "memset ranges")) return e;
     StageScope prof(HGS_STAGE_TILE_RANGES, s);
     if (n <= 0) {
@@ -1119,11 +1216,11 @@ int launch_finalize_sorted(int channels, int64_t n, const uint32_t* n_ptr, const
     }
     const unsigned nb = (unsigned)((n + 255) / 256);
     if (color_stride(channels) == 4)
-        finalize_sorted_kernel<4><<<nb, 256, 0, s>>>((uint32_t)n, n_ptr, keys_sorted, point_list, g.rec, g.rgb, ranges, b.pk_lo,
-                                                     b.pk_hi, b.pk_col);
+        finalize_sorted_kernel<4><<<nb, 256, 0, s>>>((uint32_t)n, n_ptr, keys_sorted, point_list, g.rec, g.rgb, tiles_x, ranges,
+                                                     b.pk_lo, b.pk_hi, b.pk_col, b.pk_mask);
     else
-        finalize_sorted_kernel<8><<<nb, 256, 0, s>>>((uint32_t)n, n_ptr, keys_sorted, point_list, g.rec, g.rgb, ranges, b.pk_lo,
-                                                     b.pk_hi, b.pk_col);
+        finalize_sorted_kernel<8><<<nb, 256, 0, s>>>((uint32_t)n, n_ptr, keys_sorted, point_list, g.rec, g.rgb, tiles_x, ranges,
+                                                     b.pk_lo, b.pk_hi, b.pk_col, b.pk_mask);
     tile_order_kernel<<<1, 1024, 0, s>>>((uint32_t)tiles, ranges, tile_order);
     return check_cuda(cudaGetLastError(), "finalize_sorted launch");
 }
@@ -1144,27 +1241,32 @@ static int launch_fwd_c(const ImageLayout& im, const BinningLayout& b, int W, in
         const int dyn = bulk ? (int)(8 * sizeof(FwdBulkSmem<CS>)) + pad : pad;
         static std::atomic<unsigned long long> pad_done{0};
         if (first_call_on_device(pad_done)) {
-            if (int e = check_cuda(cudaFuncSetAttribute(composite_fwd_half_kernel<C, CS, false, false>,
+            if (int e = check_cuda(cudaFuncSetAttribute(composite_fwd_half_kernel<C, CS, false, false, true>,
                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, dyn), "fwd pad attr")) return e;
-            if (int e = check_cuda(cudaFuncSetAttribute(composite_fwd_half_kernel<C, CS, false, true>,
+            if (int e = check_cuda(cudaFuncSetAttribute(composite_fwd_half_kernel<C, CS, false, true, false>,
                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, dyn), "fwd bulk attr")) return e;
         }
         StageScope prof(HGS_STAGE_COMPOSITE_FWD, s);
         if (bulk)
-            composite_fwd_half_kernel<C, CS, false, true><<<grid, 256, dyn, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col,
-                                                                                  bg, im.final_T, im.n_contrib, out_color);
+            composite_fwd_half_kernel<C, CS, false, true, false><<<grid, 256, dyn, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi,
+                                                                                         p.col, p.mask, bg, im.final_T, im.n_contrib,
+                                                                                         out_color);
         else
-            composite_fwd_half_kernel<C, CS, false, false><<<grid, 256, dyn, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col,
-                                                                                   bg, im.final_T, im.n_contrib, out_color);
+            composite_fwd_half_kernel<C, CS, false, false, true><<<grid, 256, dyn, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi,
+                                                                                         p.col, p.mask, bg, im.final_T, im.n_contrib,
+                                                                                         out_color);
         return check_cuda(cudaGetLastError(), "composite_fwd launch");
     }
     StageScope prof(HGS_STAGE_COMPOSITE_FWD, s);
     if (composite_blocks_4x4() && g_fwd_stats_on)
-        composite_fwd_half_kernel<C, CS, true, false><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col, bg,
-                                                                            im.final_T, im.n_contrib, out_color);
+        composite_fwd_half_kernel<C, CS, true, false, false><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col,
+                                                                                   p.mask, bg, im.final_T, im.n_contrib, out_color);
+    else if (composite_blocks_4x4() && walk_by_mask())
+        composite_fwd_half_kernel<C, CS, false, false, true><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col,
+                                                                                   p.mask, bg, im.final_T, im.n_contrib, out_color);
     else if (composite_blocks_4x4())
-        composite_fwd_half_kernel<C, CS, false, false><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col, bg,
-                                                                             im.final_T, im.n_contrib, out_color);
+        composite_fwd_half_kernel<C, CS, false, false, false><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col,
+                                                                                    p.mask, bg, im.final_T, im.n_contrib, out_color);
     else
         composite_fwd_kernel<C, CS><<<grid, 256, 0, s>>>(im.ranges, im.tile_order, W, H, p.lo, p.hi, p.col, bg, im.final_T,
                                                           im.n_contrib, out_color);
@@ -1199,21 +1301,30 @@ static int launch_bwd_c(const ImageLayout& im, const BinningLayout& b, const uin
     if (first_call_on_device(attr_done)) {
         if (int e = check_cuda(cudaFuncSetAttribute(composite_bwd_kernel<C, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)smem), "composite_bwd smem attr")) return e;
-        if (int e = check_cuda(cudaFuncSetAttribute(composite_bwd_half_kernel<C, CS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (int e = check_cuda(cudaFuncSetAttribute(composite_bwd_half_kernel<C, CS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)smem_half), "composite_bwd_half smem attr")) return e;
-        if (int e = check_cuda(cudaFuncSetAttribute(composite_bwd_half_kernel<C, CS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (int e = check_cuda(cudaFuncSetAttribute(composite_bwd_half_kernel<C, CS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)smem_half), "composite_bwd_half smem attr")) return e;
+        if (int e = check_cuda(cudaFuncSetAttribute(composite_bwd_half_kernel<C, CS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)smem_half), "composite_bwd_half smem attr")) return e;
+        if (int e = check_cuda(cudaFuncSetAttribute(composite_bwd_half_kernel<C, CS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)smem_half), "composite_bwd_half smem attr")) return e;
     }
     StageScope prof(HGS_STAGE_COMPOSITE_BWD, s);
-    if (acc16 != nullptr)   // interleaved records + vector reductions (half-warp kernel only)
-        composite_bwd_half_kernel<C, CS, true><<<grid, 256, smem_half, s>>>(im.ranges, im.tile_order, point_list, W, H, bg, p.lo,
-                                                                             p.hi, p.col, im.final_T, im.n_contrib, dL_dpix, acc16,
-                                                                             nullptr, nullptr, nullptr);
+    // half-warp kernel; kVec: interleaved [P,16] records + vector reductions (strand entry); kMask: see walk_by_mask()
+#define HGS_BWD_HALF(VEC, MASK, M2D, CONIC, OPAC, COL)                                                                          \
+    composite_bwd_half_kernel<C, CS, VEC, MASK><<<grid, 256, smem_half, s>>>(im.ranges, im.tile_order, point_list, W, H, bg, p.lo, \
+                                                                              p.hi, p.col, p.mask, im.final_T, im.n_contrib,       \
+                                                                              dL_dpix, M2D, CONIC, OPAC, COL)
+    if (acc16 != nullptr && walk_by_mask())
+        HGS_BWD_HALF(true, true, acc16, nullptr, nullptr, nullptr);
+    else if (acc16 != nullptr)
+        HGS_BWD_HALF(true, false, acc16, nullptr, nullptr, nullptr);
+    else if (composite_blocks_4x4() && walk_by_mask())
+        HGS_BWD_HALF(false, true, gr->dL_dmean2D, gr->dL_dconic, gr->dL_dopacity, gr->dL_dcolor);
     else if (composite_blocks_4x4())
-        composite_bwd_half_kernel<C, CS, false><<<grid, 256, smem_half, s>>>(im.ranges, im.tile_order, point_list, W, H, bg, p.lo,
-                                                                              p.hi, p.col, im.final_T, im.n_contrib, dL_dpix,
-                                                                              gr->dL_dmean2D, gr->dL_dconic, gr->dL_dopacity,
-                                                                              gr->dL_dcolor);
+        HGS_BWD_HALF(false, false, gr->dL_dmean2D, gr->dL_dconic, gr->dL_dopacity, gr->dL_dcolor);
+#undef HGS_BWD_HALF
     else
         composite_bwd_kernel<C, CS><<<grid, 256, smem, s>>>(im.ranges, im.tile_order, point_list, W, H, bg, p.lo, p.hi, p.col,
                                                              im.final_T, im.n_contrib, dL_dpix, gr->dL_dmean2D, gr->dL_dconic,

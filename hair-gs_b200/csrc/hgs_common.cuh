@@ -194,6 +194,7 @@ struct BinningLayout {
     float4* pk_lo;       // [N] sorted-order copies of the Gaussian records (x, y, conic.x, conic.y)
     float4* pk_hi;       // [N] (conic.z, opacity, hx, hy)
     float4* pk_col;      // [N * cstride/4] colours in sorted order
+    uint16_t* pk_mask;   // [N] which of the tile's sixteen 4x4 pixel blocks the instance's alpha extent reaches (block_mask16)
     void* sort_ws;
     size_t bytes;
 };
@@ -210,12 +211,32 @@ __host__ __device__ inline BinningLayout carve_binning(void* base, int64_t n, in
     b.pk_lo = (float4*)(p + off);     off = align_up(off + nz * 16);
     b.pk_hi = (float4*)(p + off);     off = align_up(off + nz * 16);
     b.pk_col = (float4*)(p + off);    off = align_up(off + nz * 4 * color_stride(channels));
+    b.pk_mask = (uint16_t*)(p + off); off = align_up(off + nz * 2);
     b.sort_ws = (void*)(p + off);
     SortLayout s = carve_sort(b.sort_ws, n);
     off = align_up(off + s.bytes);
     b.bytes = off;
     return b;
 }
+
+#ifdef __CUDACC__
+// Which of the sixteen 4x4 pixel blocks of the 16x16 tile at (X0, Y0) the instance's alpha >= 1/255 extent (preprocess.cu
+// alpha_extent, an axis-aligned box) reaches: bit 4 * block_row + block_column.  The same comparisons, on the same float
+// values, as the per-chunk test the compositors made on their own two blocks (a block is skipped only when a comparison
+// is TRUE, so NaNs keep the instance) - evaluated ONCE per instance here instead of once per warp and pass there, and
+// read back as 2 bytes instead of the 68-byte record by the 7 of 8 warps whose blocks the instance does not reach.
+__device__ __forceinline__ uint32_t block_mask16(const float4 lo, const float4 hi, uint32_t X0, uint32_t Y0) {
+    const float xl = lo.x - hi.z, xr = lo.x + hi.z;
+    const float yt = lo.y - hi.w, yb = lo.y + hi.w;
+    uint32_t cols = 0, rows = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {
+        if (!(xl > (float)(X0 + 4 * j + 3) || xr < (float)(X0 + 4 * j))) cols |= 1u << j;
+        if (!(yt > (float)(Y0 + 4 * j + 3) || yb < (float)(Y0 + 4 * j))) rows |= 1u << (4 * j);
+    }
+    return cols * rows;  // rows has one bit per nibble: the product copies cols into every reached block row
+}
+#endif
 
 // Number of 8-bit passes for keys whose significant bits are [0, end_bit), and which ping-pong
 // buffer ends up holding the sorted data.

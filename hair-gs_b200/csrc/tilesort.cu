@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(kThreads) tile_sort_pack_kernel(
     const uint32_t* __restrict__ work, const uint32_t* __restrict__ work_n, uint32_t* __restrict__ claim,
     const uint32_t* __restrict__ list_count, const uint32_t* __restrict__ list_start, const uint64_t* __restrict__ bucket,
     uint32_t capacity, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, const float4* __restrict__ rec,
-    const float* __restrict__ rgb, float4* __restrict__ pk_lo, float4* __restrict__ pk_hi, float4* __restrict__ pk_col) {
+    const float* __restrict__ rgb, uint32_t tiles_x, float4* __restrict__ pk_lo, float4* __restrict__ pk_hi,
+    float4* __restrict__ pk_col, uint16_t* __restrict__ pk_mask) {
     extern __shared__ __align__(16) unsigned char tsp_smem[];
     uint64_t* s = reinterpret_cast<uint64_t*>(tsp_smem);
     __shared__ uint32_t s_item;
@@ -237,7 +238,9 @@ __global__ void __launch_bounds__(kThreads) tile_sort_pack_kernel(
                 __syncthreads();
             }
         }
-        const uint64_t tile_hi = (uint64_t)(list / (uint32_t)HGS_TILE_SLICES) << 32;
+        const uint32_t tile = list / (uint32_t)HGS_TILE_SLICES;
+        const uint64_t tile_hi = (uint64_t)tile << 32;
+        const uint32_t X0 = (tile % tiles_x) * HGS_TILE, Y0 = (tile / tiles_x) * HGS_TILE;
         for (uint32_t i = tid; i < n; i += kThreads) {
             const uint64_t w = s[i];
             const uint32_t id = (uint32_t)w;
@@ -249,6 +252,7 @@ __global__ void __launch_bounds__(kThreads) tile_sort_pack_kernel(
             const float4 c0 = *reinterpret_cast<const float4*>(rgb + (size_t)id * CS);
             pk_lo[o] = lo;
             pk_hi[o] = hi;
+            pk_mask[o] = (uint16_t)block_mask16(lo, hi, X0, Y0);
             pk_col[o * (CS / 4)] = c0;
             if (CS > 4) pk_col[o * (CS / 4) + 1] = *reinterpret_cast<const float4*>(rgb + (size_t)id * CS + 4);
         }
@@ -260,7 +264,7 @@ __global__ void __launch_bounds__(kThreads) tile_sort_pack_kernel(
 // ------------------------------------------------------------------------------------------------
 template <int CS>
 static int launch_sort_pack_cs(const ImageLayout& im, const GeomLayout& g, const BinningLayout& b, uint64_t* bucket,
-                               uint32_t capacity, size_t lists, cudaStream_t s) {
+                               uint32_t capacity, size_t lists, uint32_t tiles_x, cudaStream_t s) {
     static std::atomic<unsigned long long> attr_done{0};
     if (first_call_on_device(attr_done)) {
         if (int e = check_cuda(cudaFuncSetAttribute(tile_sort_pack_kernel<1024, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -271,19 +275,19 @@ static int launch_sort_pack_cs(const ImageLayout& im, const GeomLayout& g, const
         StageScope prof(HGS_STAGE_TILE_SORT_PACK, s);
         tile_sort_pack_kernel<1024, CS><<<148, 1024, HGS_TILE_SORT_MAX * 8, s>>>(
             im.work, im.work_count, im.work_count + 4, g.tile_count, im.list_start, bucket, capacity, b.keys[0], b.vals[0], g.rec,
-            g.rgb, b.pk_lo, b.pk_hi, b.pk_col);
+            g.rgb, tiles_x, b.pk_lo, b.pk_hi, b.pk_col, b.pk_mask);
     }
     {
         StageScope prof(HGS_STAGE_TILE_SORT_PACK, s);
         tile_sort_pack_kernel<512, CS><<<148 * 4, 512, kMediumMax * 8, s>>>(
             im.work + lists, im.work_count + 1, im.work_count + 5, g.tile_count, im.list_start, bucket, capacity, b.keys[0],
-            b.vals[0], g.rec, g.rgb, b.pk_lo, b.pk_hi, b.pk_col);
+            b.vals[0], g.rec, g.rgb, tiles_x, b.pk_lo, b.pk_hi, b.pk_col, b.pk_mask);
     }
     {
         StageScope prof(HGS_STAGE_TILE_SORT_PACK, s);
         tile_sort_pack_kernel<128, CS><<<148 * 16, 128, kSmallMax * 8, s>>>(
             im.work + 2 * lists, im.work_count + 2, im.work_count + 6, g.tile_count, im.list_start, bucket, capacity, b.keys[0],
-            b.vals[0], g.rec, g.rgb, b.pk_lo, b.pk_hi, b.pk_col);
+            b.vals[0], g.rec, g.rgb, tiles_x, b.pk_lo, b.pk_hi, b.pk_col, b.pk_mask);
     }
     return check_cuda(cudaGetLastError(), "tile_sort_pack launch");
 }
@@ -308,8 +312,8 @@ int launch_tile_binning(int P, int channels, int64_t N, const GeomLayout& g, con
                                                             im.list_cursor, b.keys[1], grid_x, (uint32_t)N, slice_base, slice_shift);
         if (int e = check_cuda(cudaGetLastError(), "tile_scatter launch")) return e;
     }
-    if (color_stride(channels) == 4) return launch_sort_pack_cs<4>(im, g, b, b.keys[1], (uint32_t)N, lists, s);
-    return launch_sort_pack_cs<8>(im, g, b, b.keys[1], (uint32_t)N, lists, s);
+    if (color_stride(channels) == 4) return launch_sort_pack_cs<4>(im, g, b, b.keys[1], (uint32_t)N, lists, grid_x, s);
+    return launch_sort_pack_cs<8>(im, g, b, b.keys[1], (uint32_t)N, lists, grid_x, s);
 }
 
 }  // namespace hgs

@@ -1175,6 +1175,17 @@ def test_tile_sort_falls_back_to_the_global_sort_for_very_long_tile_lists():
     C = need_ref()
     ours_C._sort_mode_hint.clear()
     ours_C._slice_hint.clear()
+    saved = ours_C.DEFAULT_SORT_MODE
+    ours_C.DEFAULT_SORT_MODE = L.SORT_TILE          # the library default is the global sort (HGS_SORT_MODE)
+    try:
+        _tile_sort_fallback_body(ours_C, L)
+    finally:
+        ours_C.DEFAULT_SORT_MODE = saved
+        ours_C._sort_mode_hint.clear()
+        ours_C._slice_hint.clear()
+
+
+def _tile_sort_fallback_body(ours_C, L):
     P = 20000
     d = common.blob_inputs(P, 64, 64, dev(), seed=77, scale_mul=0.2)
     # every Gaussian in front of the camera, projected into the image centre: one tile list of ~P entries

@@ -1,5 +1,6 @@
 #!/bin/bash
-# ncu launch list (gpu__time_duration.sum) of the headline command, all launches; summarised by tools/launchlist_summary.py
+# ncu launch list (gpu__time_duration.sum) of the end-to-end batch-graph step bench.py's headline e2e times; summarised by
+# tools/launchlist_summary.py.  The capture/warm-up launches come first; the last step is what the summary's --tail takes.
 mkdir -p gpurun_out
-timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 40000 --csv --log-file gpurun_out/r2_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_ncu_bench.log 2>&1
-wc -l gpurun_out/r2_launches_bench.csv; gzip -f -9 gpurun_out/r2_launches_bench.csv; ls -la gpurun_out/r2_launches_bench.csv.gz
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/r2_launches_batch.csv python tools/prof_pass.py cfg3 2 batch > gpurun_out/r2_ncu_batch.log 2>&1
+wc -l gpurun_out/r2_launches_batch.csv; tail -3 gpurun_out/r2_ncu_batch.log; gzip -f -9 gpurun_out/r2_launches_batch.csv

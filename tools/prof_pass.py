@@ -1,5 +1,7 @@
 """Minimal driver for ncu captures: a few forward+backward rasterization passes of one workload through the
-drop-in `_C` entry points (no e2e glue, no CPU baseline).  Usage: python tools/prof_pass.py cfg3 3 [ref]"""
+drop-in `_C` entry points (no e2e glue, no CPU baseline).  Usage: python tools/prof_pass.py cfg3 3 [ref|fused|batch]
+`batch`: the end-to-end step bench.py's headline `e2e` times (H2D of 8 views' targets, unpack, ONE batch-graph replay with the
+image loss, D2H of the losses) — 2 untimed steps to page everything in, then `iters` steps."""
 import os
 import sys
 
@@ -20,11 +22,20 @@ if use_ref:
 else:
     import diff_gaussian_rasterization._C as backend
 import types  # noqa: E402
-args = types.SimpleNamespace(views_per_step=1, gpus=1, graph_mode="view")
+batch = len(sys.argv) > 3 and sys.argv[3] == "batch"
+args = types.SimpleNamespace(views_per_step=8 if batch else 1, gpus=1, graph_mode="batch" if batch else "view")
 h = bench.Harness(bench.WORKLOADS[name], args, dev, backend, 1, 0)
 fused = len(sys.argv) > 3 and sys.argv[3] == "fused"
 if fused:
     h.setup_fused()
+if batch:
+    h.setup_e2e(fused=True, graph=True)
+    assert h.ebatch is not None, h.graph_note
+    for it in range(iters + 2):
+        h.step_e2e(it)
+        torch.cuda.synchronize()
+    print("done batch", name, "P", h.P)
+    sys.exit(0)
 for it in range(iters):
     (h.step_resident_fused if fused else h.step_resident)(it)
 torch.cuda.synchronize()
