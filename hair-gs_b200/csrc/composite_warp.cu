@@ -833,12 +833,6 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_kernel(
 //            candidate of either half) issue the red.global.adds.
 // cfg3, CPU model of the queue policy (tools/block_shape_study.py): 26 % fewer phase-1 trips than the 8x4 kernel; an
 // instance that reaches both halves is accumulated by both (1.3x the candidates, each over 16 instead of 32 pixels).
-__device__ __forceinline__ float rcp_approx(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
 template <int CS>
 struct BwdHalfSmem {
     static constexpr int QN = 40;   // ring capacity per half: 32 new + <= 8 carried over
@@ -986,6 +980,10 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_half_kernel(
         }
         __syncwarp();
         // ---- phase 2: lanes = (half, candidate my_g, column parity my_o) ---------------------------------------
+        // With s = G * dL/dalpha of a contributing pixel and d = mean2D - pixel, every geometric gradient of the candidate
+        // is a combination of six moments of s over its pixels - sum s, s dx, s dy, s dx dx, s dx dy, s dy dy - with
+        // coefficients that depend on the candidate only (backward_distwar.cu:993-1006 expanded: dL/dG = opacity * dL/dalpha,
+        // dG/ddelx = -G (conic.x dx + conic.y dy), ...): 9 FP operations per pixel instead of 16, the coefficients once per group.
         float acc[6 + C];
 #pragma unroll
         for (int k = 0; k < 6 + C; ++k) acc[k] = 0.f;
@@ -999,8 +997,8 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_half_kernel(
             // group with 7 lanes active, profiles/r1_composite_half.md)
             uint32_t m = my_vm & (0x5555u << my_o);
             if (m) {
-                const float4 glo = my_lo[slot];
-                const float4 ghi = my_hi[slot];
+                const float2 gxy = *reinterpret_cast<const float2*>(&my_lo[slot]);
+                const float4 glo = make_float4(gxy.x, gxy.y, 0.f, 0.f);
                 const float hx0 = ax0 + (float)(half * 4);
                 while (m) {
                     const uint32_t p = (uint32_t)__ffs(m) - 1u;  // pixel of this half, row-major 4x4
@@ -1009,14 +1007,14 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_half_kernel(
                     const float2 r = ws.slab_gd[si];  // (G, dL_dalpha)
                     const float rw = ws.slab_w[si];   // alpha * T
                     const float dx = glo.x - (hx0 + (float)(p & 3)), dy = glo.y - (wy0 + (float)(p >> 2));
-                    const float dL_dG = ghi.y * r.y;
-                    const float gdx = r.x * dx, gdy = r.x * dy;
-                    acc[0] += dL_dG * (-gdx * glo.z - gdy * glo.w);
-                    acc[1] += dL_dG * (-gdy * ghi.x - gdx * glo.w);
-                    acc[2] += gdx * dx * dL_dG;
-                    acc[3] += gdx * dy * dL_dG;
-                    acc[4] += gdy * dy * dL_dG;
-                    acc[5] += r.x * r.y;
+                    const float sv = r.x * r.y;
+                    const float sx = sv * dx, sy = sv * dy;
+                    acc[0] += sv;
+                    acc[1] += sx;
+                    acc[2] += sy;
+                    acc[3] += sx * dx;
+                    acc[4] += sx * dy;
+                    acc[5] += sy * dy;
                     const float* dp = reinterpret_cast<const float*>(&ws.dpix[(half * 16 + p) * (CS / 4)]);
 #pragma unroll
                     for (int ch = 0; ch < C; ++ch) acc[6 + ch] += rw * dp[ch];
@@ -1025,26 +1023,33 @@ __global__ void __launch_bounds__(256, 3) composite_bwd_half_kernel(
         }
 #pragma unroll
         for (int k = 0; k < 6 + C; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
-        if (kVec && my_o == 0 && my_vm != 0) {
-            const uint32_t gid = __float_as_uint(my_hi[slot].w);
-            float* rec16 = dL_dmean2D + 16 * (size_t)gid;
-            float col[8];
+        if (my_o == 0 && my_vm != 0) {
+            const float4 glo = my_lo[slot], ghi = my_hi[slot];   // re-read here: not kept live across the pixel loop
+            const uint32_t gid = __float_as_uint(ghi.w);
+            const float op = ghi.y;
+            // glo = (x, y, conic.x, conic.y), ghi = (conic.z, opacity, position, id)
+            const float g_mx = -op * (glo.z * acc[1] + glo.w * acc[2]) * ddelx_dx;
+            const float g_my = -op * (ghi.x * acc[2] + glo.w * acc[1]) * ddely_dy;
+            const float g_cxx = -0.5f * op * acc[3], g_cxy = -0.5f * op * acc[4], g_cyy = -0.5f * op * acc[5];
+            if (kVec) {
+                float* rec16 = dL_dmean2D + 16 * (size_t)gid;
+                float col[8];
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) col[ch] = ch < C ? acc[6 + ch] : 0.f;
-            red_add_v4(rec16, acc[0] * ddelx_dx, acc[1] * ddely_dy, acc[5], 0.f);
-            red_add_v4(rec16 + 4, -0.5f * acc[2], -0.5f * acc[3], 0.f, -0.5f * acc[4]);
-            red_add_v4(rec16 + 8, col[0], col[1], col[2], col[3]);
-            if (C > 4) red_add_v4(rec16 + 12, col[4], col[5], col[6], col[7]);
-        } else if (my_o == 0 && my_vm != 0) {
-            const uint32_t gid = __float_as_uint(my_hi[slot].w);
-            atomicAdd(dL_dmean2D + 3 * (size_t)gid, acc[0] * ddelx_dx);
-            atomicAdd(dL_dmean2D + 3 * (size_t)gid + 1, acc[1] * ddely_dy);
-            atomicAdd(dL_dconic + 4 * (size_t)gid, -0.5f * acc[2]);
-            atomicAdd(dL_dconic + 4 * (size_t)gid + 1, -0.5f * acc[3]);
-            atomicAdd(dL_dconic + 4 * (size_t)gid + 3, -0.5f * acc[4]);
-            atomicAdd(dL_dopacity + gid, acc[5]);
+                for (int ch = 0; ch < 8; ++ch) col[ch] = ch < C ? acc[6 + ch] : 0.f;
+                red_add_v4(rec16, g_mx, g_my, acc[0], 0.f);
+                red_add_v4(rec16 + 4, g_cxx, g_cxy, 0.f, g_cyy);
+                red_add_v4(rec16 + 8, col[0], col[1], col[2], col[3]);
+                if (C > 4) red_add_v4(rec16 + 12, col[4], col[5], col[6], col[7]);
+            } else {
+                atomicAdd(dL_dmean2D + 3 * (size_t)gid, g_mx);
+                atomicAdd(dL_dmean2D + 3 * (size_t)gid + 1, g_my);
+                atomicAdd(dL_dconic + 4 * (size_t)gid, g_cxx);
+                atomicAdd(dL_dconic + 4 * (size_t)gid + 1, g_cxy);
+                atomicAdd(dL_dconic + 4 * (size_t)gid + 3, g_cyy);
+                atomicAdd(dL_dopacity + gid, acc[0]);
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) atomicAdd(dL_dcolors + (size_t)gid * C + ch, acc[6 + ch]);
+                for (int ch = 0; ch < C; ++ch) atomicAdd(dL_dcolors + (size_t)gid * C + ch, acc[6 + ch]);
+            }
         }
         head_a += na;
         head_a = head_a >= QN ? head_a - QN : head_a;

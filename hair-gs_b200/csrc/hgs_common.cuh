@@ -220,6 +220,14 @@ __host__ __device__ inline BinningLayout carve_binning(void* base, int64_t n, in
 }
 
 #ifdef __CUDACC__
+// MUFU.RCP (<= 1 ulp, flush-to-zero) for gradient-side reciprocals of well-scaled arguments, where the IEEE division sequence
+// (8 instructions with its range check and slow-path call) buys nothing; never used where bits are compared with the reference.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // Which of the sixteen 4x4 pixel blocks of the 16x16 tile at (X0, Y0) the instance's alpha >= 1/255 extent (preprocess.cu
 // alpha_extent, an axis-aligned box) reaches: bit 4 * block_row + block_column.  The same comparisons, on the same float
 // values, as the per-chunk test the compositors made on their own two blocks (a block is skipped only when a comparison

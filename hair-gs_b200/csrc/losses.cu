@@ -73,10 +73,11 @@ int launch_weighted_l1(int C, long long HW, const float* img, const float* tgt, 
 //     + l_mask   * BCEWithLogits(mask_plane, gt_mask)                                   loss/losses.py:292-316
 //     + l_orient * mean_{mask}( bidirectional_angle_diff(theta(orientation), gt_theta) * confidence )   :224-289
 // In torch this is ~70 kernels over 1-12 MB tensors per view (five grouped 11x11 conv2d + their autograd, the
-// permute/matmul/norm/atan2/where chain of the orientation term, BCE); here it is four launches:
-//   hair_loss_count      : number of pixels in the orientation mask (the mean's denominator is data dependent)
-//   ssim_fwd_kernel      : 16x16 output tile per CTA, 26x26 halo of render + target staged in shared memory, separable
-//                          11-tap Gaussian for the five moments, SSIM map -> loss sum and three derivative maps
+// permute/matmul/norm/atan2/where chain of the orientation term, BCE); here it is four launches (three kernels over the image + the one-thread finish):
+//   ssim_fwd_kernel      : 32x32 output tile per CTA, 42x42 halo of render + target staged in shared memory, separable
+//                          11-tap Gaussian for the five moments, SSIM map -> loss sum and three derivative maps; its
+//                          channel-0 blocks also count the pixels of the orientation mask (the mean's denominator is
+//                          data dependent)
 //   ssim_bwd_kernel      : convolves the three derivative maps back (same tiling) and adds the L1 term's sign()
 //   hair_pointwise_kernel: BCE-with-logits and the orientation chain, forward value and analytic gradient per pixel
 // =====================================================================================================================
@@ -114,19 +115,6 @@ __device__ __forceinline__ float block_sum_256(float v, float* s_part) {
 __device__ __forceinline__ bool orient_in_mask(const HairLossArgs& a, long long i, float ox, float oy, float oz) {
     if (a.orient_mask) return a.orient_mask[i] != 0;
     return ox != a.bg_orient[0] || oy != a.bg_orient[1] || oz != a.bg_orient[2];
-}
-
-__global__ void __launch_bounds__(256) hair_loss_count_kernel(const HairLossArgs a) {
-    __shared__ float s_part[8];
-    const long long HW = (long long)a.height * a.width;
-    float cnt = 0.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
-        float ox = 0.f, oy = 0.f, oz = 0.f;
-        if (!a.orient_mask) { ox = a.image7[4 * HW + i]; oy = a.image7[5 * HW + i]; oz = a.image7[6 * HW + i]; }
-        cnt += orient_in_mask(a, i, ox, oy, oz) ? 1.f : 0.f;
-    }
-    const float r = block_sum_256(cnt, s_part);
-    if (threadIdx.x == 0 && r != 0.f) atomicAdd(a.terms + 5, r);
 }
 
 // Separable 11-tap filter with register sliding windows: every thread produces kSsimStrip consecutive outputs from
@@ -202,20 +190,30 @@ __global__ void __launch_bounds__(256, 2) ssim_fwd_kernel(const HairLossArgs a) 
     float mom[5][kSsimStrip];
     ssim_vertical<5>(s_h, col, strip, mom);
     const int px = blockIdx.x * kSsimTile + col;
-    float ssim_sum = 0.f, l1_sum = 0.f;
+    float ssim_sum = 0.f, l1_sum = 0.f, cnt = 0.f;
 #pragma unroll
     for (int j = 0; j < kSsimStrip; ++j) {
         const int ly = strip * kSsimStrip + j, py = blockIdx.y * kSsimTile + ly;
         if (px < W && py < H) {
+            if (c == 0) {
+                // the channel-0 blocks also count the pixels of the orientation mask (the denominator of the orientation
+                // term's mean is data dependent, and hair_pointwise needs it before it can write gradients)
+                const long long q = (long long)py * W + px;
+                float ox = 0.f, oy = 0.f, oz = 0.f;
+                if (!a.orient_mask) { ox = a.image7[4 * HW + q]; oy = a.image7[5 * HW + q]; oz = a.image7[6 * HW + q]; }
+                cnt += orient_in_mask(a, q, ox, oy, oz) ? 1.f : 0.f;
+            }
             const float mu1 = mom[0][j], mu2 = mom[1][j], e11 = mom[2][j], e22 = mom[3][j], e12 = mom[4][j];
             const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
             const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
             const float s11 = e11 - mu1_sq, s22 = e22 - mu2_sq, s12 = e12 - mu12;
             const float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2, B1 = mu1_sq + mu2_sq + C1, B2 = s11 + s22 + C2;
-            const float inv = 1.f / (B1 * B2);
+            // B1, B2 >= C1, C2 > 0: two MUFU.RCP instead of three IEEE divisions
+            const float inv_B1 = rcp_approx(B1), inv_B2 = rcp_approx(B2);
+            const float inv = inv_B1 * inv_B2;
             const float ssim_val = A1 * A2 * inv;
             // d ssim / d(mu1, E[x^2], E[xy]) with s11 = E[x^2]-mu1^2, s12 = E[xy]-mu1 mu2
-            const float d_A1 = A2 * inv, d_A2 = A1 * inv, d_B1 = -ssim_val / B1, d_B2 = -ssim_val / B2;
+            const float d_A1 = A2 * inv, d_A2 = A1 * inv, d_B1 = -ssim_val * inv_B1, d_B2 = -ssim_val * inv_B2;
             const float d_mu1 = d_A1 * 2.f * mu2 + d_B1 * 2.f * mu1 + d_B2 * (-2.f * mu1) + d_A2 * 2.f * (-mu2);
             const long long p = (long long)py * W + px;
             a.scratch[(0 * 3 + c) * HW + p] = d_mu1;
@@ -227,9 +225,11 @@ __global__ void __launch_bounds__(256, 2) ssim_fwd_kernel(const HairLossArgs a) 
     }
     const float rs = block_sum_256(ssim_sum, s_part);
     const float rl = block_sum_256(l1_sum, s_part);
+    const float rc = c == 0 ? block_sum_256(cnt, s_part) : 0.f;
     if (threadIdx.x == 0) {
         atomicAdd(a.terms + 2, rs);
         atomicAdd(a.terms + 1, rl);
+        if (rc != 0.f) atomicAdd(a.terms + 5, rc);
     }
 }
 
@@ -302,8 +302,10 @@ __global__ void __launch_bounds__(256) hair_pointwise_kernel(const HairLossArgs 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
         // ---- mask: BCEWithLogits(x, z) = max(x,0) - x z + log(1 + exp(-|x|)), mean over pixels ----------------
         const float x = a.image7[3 * HW + i], z = a.gt_mask[i];
-        bce_sum += fmaxf(x, 0.f) - x * z + log1pf(expf(-fabsf(x)));
-        const float sig = 1.f / (1.f + expf(-x));
+        const float e = expf(-fabsf(x));            // shared by the value and the sigmoid: sigmoid(x) = 1/(1+e) or e/(1+e)
+        bce_sum += fmaxf(x, 0.f) - x * z + log1pf(e);
+        const float inv_1pe = rcp_approx(1.f + e);
+        const float sig = x >= 0.f ? inv_1pe : e * inv_1pe;
         a.dL_dimage[3 * HW + i] = a.l_mask * (sig - z) / (float)HW;
         // ---- orientation (loss/losses.py:244-288) ---------------------------------------------------------------
         const float ox = a.image7[4 * HW + i], oy = a.image7[5 * HW + i], oz = a.image7[6 * HW + i];
@@ -314,8 +316,9 @@ __global__ void __launch_bounds__(256) hair_pointwise_kernel(const HairLossArgs 
             const float vy = ox * r1 + oy * r4 + oz * r7;
             const float nrm = sqrtf(vx * vx + vy * vy);
             const float den = nrm + eps;
-            const float pxn = vx / den;
-            float pyn = vy / den;
+            const float inv_den = rcp_approx(den);      // den >= 1e-7
+            const float pxn = vx * inv_den;
+            float pyn = vy * inv_den;
             if (pyn < eps) pyn += eps;
             float theta = atan2f(pxn, pyn);
             if (theta < 0.f) theta += kPi;
@@ -329,12 +332,13 @@ __global__ void __launch_bounds__(256) hair_pointwise_kernel(const HairLossArgs 
             const float sgn_in = inner > 0.f ? 1.f : (inner < 0.f ? -1.f : 0.f);
             const float g_theta = a.l_orient * inv_count * cf * (-sgn_in * sgn_dt);
             const float r2 = pxn * pxn + pyn * pyn;
-            const float g_px = r2 > 0.f ? g_theta * (pyn / r2) : 0.f;   // d atan2(x, y)/dx =  y/(x^2+y^2)
-            const float g_py = r2 > 0.f ? g_theta * (-pxn / r2) : 0.f;  //              /dy = -x/(x^2+y^2)
+            const float inv_r2 = r2 > 1e-30f ? rcp_approx(r2) : (r2 > 0.f ? 1.f / r2 : 0.f);
+            const float g_px = g_theta * (pyn * inv_r2);    // d atan2(x, y)/dx =  y/(x^2+y^2)
+            const float g_py = g_theta * (-pxn * inv_r2);   //              /dy = -x/(x^2+y^2)
             // p = v / (|v| + eps); d|v|/dv = v/|v| (0 at the origin, as torch.norm)
             const float gdotv = g_px * vx + g_py * vy;
-            const float k = nrm > 0.f ? gdotv / (den * den * nrm) : 0.f;
-            const float g_vx = g_px / den - k * vx, g_vy = g_py / den - k * vy;
+            const float k = nrm > 0.f ? gdotv / (den * den * nrm) : 0.f;   // IEEE: the divisor can be denormal
+            const float g_vx = g_px * inv_den - k * vx, g_vy = g_py * inv_den - k * vy;
             gox = g_vx * r0 + g_vy * r1;
             goy = g_vx * r3 + g_vy * r4;
             goz = g_vx * r6 + g_vy * r7;
@@ -399,7 +403,6 @@ int launch_hair_image_loss(const HairLossArgs& a, cudaStream_t s) {
     long long nb = (HW + 255) / 256;
     if (nb > 148 * 8) nb = 148 * 8;
     StageScope prof(HGS_STAGE_OTHER, s);
-    hair_loss_count_kernel<<<(unsigned)nb, 256, 0, s>>>(a);
     dim3 grid((a.width + kSsimTile - 1) / kSsimTile, (a.height + kSsimTile - 1) / kSsimTile, 3);
     ssim_fwd_kernel<<<grid, 256, 0, s>>>(a);
     ssim_bwd_kernel<<<grid, 256, 0, s>>>(a);

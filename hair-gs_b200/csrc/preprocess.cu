@@ -846,10 +846,15 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
     if (has_sh) {
         const float* sh = a.shs + (size_t)idx * a.M * 3;
         float* dsh = a.dL_dsh + (size_t)idx * a.M * 3;
-        const float3 campos = make_float3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]);
-        const float3 dir_orig = make_float3(mean.x - campos.x, mean.y - campos.y, mean.z - campos.z);
-        const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
-        const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
+        // the view direction matters from degree 1 on (Hair-GS trains its strands at degree 0: none of this is needed)
+        float3 dir_orig = make_float3(0.f, 0.f, 0.f);
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (a.D > 0) {
+            const float3 campos = make_float3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]);
+            dir_orig = make_float3(mean.x - campos.x, mean.y - campos.y, mean.z - campos.z);
+            const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+            x = dir_orig.x / len; y = dir_orig.y / len; z = dir_orig.z / len;
+        }
         const uint32_t cbits = a.clamped[idx];
         float dRGB[3];
 #pragma unroll
@@ -930,13 +935,15 @@ __global__ void __launch_bounds__(256, 4) preprocess_bwd_kernel(const PreBwdArgs
         for (int k = written; k < a.M; ++k) {
             put(dsh + (k * 3 + 0), 0.f); put(dsh + (k * 3 + 1), 0.f); put(dsh + (k * 3 + 2), 0.f);
         }
-        const float3 dL_ddir = make_float3(dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2],
-                                           dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2],
-                                           dRGBdz[0] * dRGB[0] + dRGBdz[1] * dRGB[1] + dRGBdz[2] * dRGB[2]);
-        const float3 dsm = dnormvdv3(dir_orig, dL_ddir);
-        dmean.x += dsm.x;
-        dmean.y += dsm.y;
-        dmean.z += dsm.z;
+        if (a.D > 0) {   // at degree 0 the colour does not depend on the direction: dL/ddir is exactly zero
+            const float3 dL_ddir = make_float3(dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2],
+                                               dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2],
+                                               dRGBdz[0] * dRGB[0] + dRGBdz[1] * dRGB[1] + dRGBdz[2] * dRGB[2]);
+            const float3 dsm = dnormvdv3(dir_orig, dL_ddir);
+            dmean.x += dsm.x;
+            dmean.y += dsm.y;
+            dmean.z += dsm.z;
+        }
     } else if (a.dL_dsh && !a.accumulate) {
         for (int i = 0; i < a.M * 3; ++i) a.dL_dsh[(size_t)idx * a.M * 3 + i] = 0.f;
     }
