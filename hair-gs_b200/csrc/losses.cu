@@ -75,10 +75,10 @@ int launch_weighted_l1(int C, long long HW, const float* img, const float* tgt, 
 // In torch this is ~70 kernels over 1-12 MB tensors per view (five grouped 11x11 conv2d + their autograd, the
 // permute/matmul/norm/atan2/where chain of the orientation term, BCE); here it is four launches (three kernels over the image + the one-thread finish):
 //   ssim_fwd_kernel      : 32x32 output tile per CTA, 42x42 halo of render + target staged in shared memory, separable
-//                          11-tap Gaussian for the five moments, SSIM map -> loss sum and three derivative maps; its
+//                          11-tap Gaussian for the five moments, SSIM map -> loss sum and three derivative maps
+//   ssim_bwd_kernel      : convolves the three derivative maps back (same tiling) and adds the L1 term's sign(); its
 //                          channel-0 blocks also count the pixels of the orientation mask (the mean's denominator is
 //                          data dependent)
-//   ssim_bwd_kernel      : convolves the three derivative maps back (same tiling) and adds the L1 term's sign()
 //   hair_pointwise_kernel: BCE-with-logits and the orientation chain, forward value and analytic gradient per pixel
 // =====================================================================================================================
 static constexpr int kSsimTile = 32;                        // output tile edge
@@ -117,6 +117,40 @@ __device__ __forceinline__ bool orient_in_mask(const HairLossArgs& a, long long 
     return ox != a.bg_orient[0] || oy != a.bg_orient[1] || oz != a.bg_orient[2];
 }
 
+// Stages the 42 x 42 halo tile of one plane (zero outside the image, F.conv2d padding=5) into shared memory: rows
+// [y0, y0+42), columns [tx-5, tx+37) with tx = 32 * blockIdx.x.  When rows are 16-byte aligned (W % 4 == 0, aligned plane)
+// the 48-column window [tx-8, tx+40) is read as 12 float4 per row - 504 128-bit loads per plane instead of 1764 scalar ones
+// with their index arithmetic (the halo loads were the kernels' top stall, profiles/r2_loss_ncu.md).
+__device__ __forceinline__ void ssim_stage_tile(float (*dst)[kSsimInStride], const float* __restrict__ src, int W, int H,
+                                                int tx, int y0) {
+    if (((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        for (int i = threadIdx.x; i < kSsimIn * 12; i += 256) {
+            const int r = i / 12, v = i - r * 12;
+            const int yy = y0 + r, c0 = tx - 8 + 4 * v;
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (yy >= 0 && yy < H && c0 >= 0 && c0 < W) t = __ldg(reinterpret_cast<const float4*>(src + (long long)yy * W + c0));
+            const int q = 4 * v - 3;   // tile column of t.x: the window's first three and last three columns are not the tile's
+            if (v == 0) {
+                dst[r][0] = t.w;
+            } else if (v == 11) {
+                dst[r][41] = t.x;
+            } else {
+                dst[r][q] = t.x;
+                dst[r][q + 1] = t.y;
+                dst[r][q + 2] = t.z;
+                dst[r][q + 3] = t.w;
+            }
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < kSsimIn * kSsimIn; i += 256) {
+        const int r = i / kSsimIn, q = i - r * kSsimIn;
+        const int yy = y0 + r, xx = tx - kSsimHalo + q;
+        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        dst[r][q] = in ? __ldg(src + (long long)yy * W + xx) : 0.f;
+    }
+}
+
 // Separable 11-tap filter with register sliding windows: every thread produces kSsimStrip consecutive outputs from
 // kSsimWin inputs, so a tap costs one FMA and 1/4 of a shared-memory read instead of one read per FMA.
 //   pass 1 (rows):    item = (input row r, 4-column segment)  -> 42 x 8 items
@@ -140,7 +174,7 @@ __device__ __forceinline__ void ssim_vertical(const float (*s_h)[kSsimIn][kSsimH
 }
 
 // grid (ceil(W/32), ceil(H/32), 3 channels), 256 threads
-__global__ void __launch_bounds__(256, 2) ssim_fwd_kernel(const HairLossArgs a) {
+__global__ void __launch_bounds__(256, 5) ssim_fwd_kernel(const HairLossArgs a) {
     __shared__ float s_x[kSsimIn][kSsimInStride];
     __shared__ float s_y[kSsimIn][kSsimInStride];
     __shared__ float s_h[5][kSsimIn][kSsimHStride];  // row-filtered x, y, xx, yy, xy
@@ -149,14 +183,9 @@ __global__ void __launch_bounds__(256, 2) ssim_fwd_kernel(const HairLossArgs a) 
     const long long HW = (long long)H * W;
     const float* X = a.image7 + c * HW;
     const float* Y = a.gt_rgb + c * HW;
-    const int x0 = blockIdx.x * kSsimTile - kSsimHalo, y0 = blockIdx.y * kSsimTile - kSsimHalo;
-    for (int i = threadIdx.x; i < kSsimIn * kSsimIn; i += 256) {
-        const int r = i / kSsimIn, q = i - r * kSsimIn;
-        const int yy = y0 + r, xx = x0 + q;
-        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;  // zero padding (F.conv2d padding=5)
-        s_x[r][q] = in ? __ldg(X + (long long)yy * W + xx) : 0.f;
-        s_y[r][q] = in ? __ldg(Y + (long long)yy * W + xx) : 0.f;
-    }
+    const int y0 = blockIdx.y * kSsimTile - kSsimHalo;
+    ssim_stage_tile(s_x, X, W, H, blockIdx.x * kSsimTile, y0);
+    ssim_stage_tile(s_y, Y, W, H, blockIdx.x * kSsimTile, y0);
     __syncthreads();
     for (int i = threadIdx.x; i < kSsimIn * (kSsimTile / kSsimStrip); i += 256) {
         const int r = i >> 3, c0 = (i & 7) * kSsimStrip;
@@ -190,19 +219,12 @@ __global__ void __launch_bounds__(256, 2) ssim_fwd_kernel(const HairLossArgs a) 
     float mom[5][kSsimStrip];
     ssim_vertical<5>(s_h, col, strip, mom);
     const int px = blockIdx.x * kSsimTile + col;
-    float ssim_sum = 0.f, l1_sum = 0.f, cnt = 0.f;
+    float ssim_sum = 0.f, l1_sum = 0.f;
 #pragma unroll
     for (int j = 0; j < kSsimStrip; ++j) {
         const int ly = strip * kSsimStrip + j, py = blockIdx.y * kSsimTile + ly;
         if (px < W && py < H) {
-            if (c == 0) {
-                // the channel-0 blocks also count the pixels of the orientation mask (the denominator of the orientation
-                // term's mean is data dependent, and hair_pointwise needs it before it can write gradients)
-                const long long q = (long long)py * W + px;
-                float ox = 0.f, oy = 0.f, oz = 0.f;
-                if (!a.orient_mask) { ox = a.image7[4 * HW + q]; oy = a.image7[5 * HW + q]; oz = a.image7[6 * HW + q]; }
-                cnt += orient_in_mask(a, q, ox, oy, oz) ? 1.f : 0.f;
-            }
+
             const float mu1 = mom[0][j], mu2 = mom[1][j], e11 = mom[2][j], e22 = mom[3][j], e12 = mom[4][j];
             const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
             const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
@@ -225,29 +247,22 @@ __global__ void __launch_bounds__(256, 2) ssim_fwd_kernel(const HairLossArgs a) 
     }
     const float rs = block_sum_256(ssim_sum, s_part);
     const float rl = block_sum_256(l1_sum, s_part);
-    const float rc = c == 0 ? block_sum_256(cnt, s_part) : 0.f;
     if (threadIdx.x == 0) {
         atomicAdd(a.terms + 2, rs);
         atomicAdd(a.terms + 1, rl);
-        if (rc != 0.f) atomicAdd(a.terms + 5, rc);
     }
 }
 
 // dL/dx = -(l_dssim / n) * [ conv(d_mu1) + 2 x conv(d_e11) + y conv(d_e12) ] + (l_l1 / n) * sign(x - y)
-__global__ void __launch_bounds__(256, 2) ssim_bwd_kernel(const HairLossArgs a) {
+__global__ void __launch_bounds__(256, 5) ssim_bwd_kernel(const HairLossArgs a) {
     __shared__ float s_m[3][kSsimIn][kSsimInStride];
     __shared__ float s_h[3][kSsimIn][kSsimHStride];
+    __shared__ float s_part[8];
     const int H = a.height, W = a.width, c = blockIdx.z;
     const long long HW = (long long)H * W;
-    const int x0 = blockIdx.x * kSsimTile - kSsimHalo, y0 = blockIdx.y * kSsimTile - kSsimHalo;
-    for (int i = threadIdx.x; i < kSsimIn * kSsimIn; i += 256) {
-        const int r = i / kSsimIn, q = i - r * kSsimIn;
-        const int yy = y0 + r, xx = x0 + q;
-        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
-        const long long p = (long long)yy * W + xx;
+    const int y0 = blockIdx.y * kSsimTile - kSsimHalo;
 #pragma unroll
-        for (int m = 0; m < 3; ++m) s_m[m][r][q] = in ? __ldg(a.scratch + (m * 3 + c) * HW + p) : 0.f;
-    }
+    for (int m = 0; m < 3; ++m) ssim_stage_tile(s_m[m], a.scratch + (m * 3 + c) * HW, W, H, blockIdx.x * kSsimTile, y0);
     __syncthreads();
     for (int i = threadIdx.x; i < kSsimIn * (kSsimTile / kSsimStrip); i += 256) {
         const int r = i >> 3, c0 = (i & 7) * kSsimStrip;
@@ -271,17 +286,29 @@ __global__ void __launch_bounds__(256, 2) ssim_bwd_kernel(const HairLossArgs a) 
     ssim_vertical<3>(s_h, col, strip, cv);
     const int px = blockIdx.x * kSsimTile + col;
     const float n = 3.f * (float)HW;
+    float cnt = 0.f;
 #pragma unroll
     for (int j = 0; j < kSsimStrip; ++j) {
         const int py = blockIdx.y * kSsimTile + strip * kSsimStrip + j;
         if (px < W && py < H) {
             const long long p = (long long)py * W + px;
+            if (c == 0) {
+                // the channel-0 blocks also count the pixels of the orientation mask (the denominator of the orientation
+                // term's mean is data dependent; hair_pointwise, launched next, needs it before it can write gradients)
+                float ox = 0.f, oy = 0.f, oz = 0.f;
+                if (!a.orient_mask) { ox = a.image7[4 * HW + p]; oy = a.image7[5 * HW + p]; oz = a.image7[6 * HW + p]; }
+                cnt += orient_in_mask(a, p, ox, oy, oz) ? 1.f : 0.f;
+            }
             const float x = a.image7[c * HW + p], y = a.gt_rgb[c * HW + p];
             const float dssim = cv[0][j] + 2.f * x * cv[1][j] + y * cv[2][j];
             const float d = x - y;
             const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
             a.dL_dimage[c * HW + p] = -(a.l_dssim / n) * dssim + (a.l_l1 / n) * sgn;
         }
+    }
+    if (c == 0) {   // block-uniform
+        const float rc = block_sum_256(cnt, s_part);
+        if (threadIdx.x == 0 && rc != 0.f) atomicAdd(a.terms + 5, rc);
     }
 }
 
@@ -309,6 +336,8 @@ __global__ void __launch_bounds__(256) hair_pointwise_kernel(const HairLossArgs 
         a.dL_dimage[3 * HW + i] = a.l_mask * (sig - z) / (float)HW;
         // ---- orientation (loss/losses.py:244-288) ---------------------------------------------------------------
         const float ox = a.image7[4 * HW + i], oy = a.image7[5 * HW + i], oz = a.image7[6 * HW + i];
+        // loaded before the branch so that all of the pixel's reads are in flight together (the kernel waits on memory)
+        const float gt_theta = a.gt_theta[i], cf = a.confidence[i];
         float gox = 0.f, goy = 0.f, goz = 0.f;
         if (orient_in_mask(a, i, ox, oy, oz)) {
             // view-space xy: o_world @ wvt[:3,:3]
@@ -322,10 +351,9 @@ __global__ void __launch_bounds__(256) hair_pointwise_kernel(const HairLossArgs 
             if (pyn < eps) pyn += eps;
             float theta = atan2f(pxn, pyn);
             if (theta < 0.f) theta += kPi;
-            const float dt = theta - a.gt_theta[i];
+            const float dt = theta - gt_theta;
             const float inner = fabsf(dt) - kPi2;
             const float diff = kPi2 - fabsf(inner);
-            const float cf = a.confidence[i];
             ori_sum += diff * cf;
             // backward
             const float sgn_dt = dt > 0.f ? 1.f : (dt < 0.f ? -1.f : 0.f);
