@@ -117,7 +117,7 @@ def make_config(args, cfg):
         "colour_sets": list(cfg["sets"]), "resolution": [cfg["W"], cfg["H"]],
         "views_per_step": f"{args.views_per_step} per rank: gradients of the step's views accumulate in the flat bucket, ONE "
                           f"all-reduce (N>1) and ONE optimiser step (incl_optimizer loop) per step",
-        "sharding": "views ordered by tile-instance count and dealt round-robin over the ranks; one process per GPU",
+        "sharding": "views ordered by tile-instance count and dealt over the ranks in snake order (balanced per-rank sums); one process per GPU",
         "e2e_loss": ("Hair-GS image loss: (1-0.2) l1 + 0.2 d-ssim + 0.01 BCE mask + 100 orientation (loss/losses.py:319-346, "
                      "arguments/__init__.py:84-86; strand regularisers lambda_smooth / lambda_magnet = 0: out of scope)"
                      if hair else "l1 (loss/losses.py:16-17)"),

@@ -17,8 +17,9 @@ def shard_views(n_views, world_size, rank, costs=None):
     collectives stay matched when n_views < world_size (the extra ranks repeat a view with zero weight).
 
     costs (optional, one number per view, identical on every rank — e.g. the view's tile-instance count N): the views
-    are first ordered by decreasing cost and then dealt round-robin, so the world_size views that meet in one lock-step
-    iteration cost about the same and the per-step max over ranks stays close to the mean."""
+    are first ordered by decreasing cost and then dealt in groups of world_size, so the views that meet in one lock-step
+    iteration cost about the same; every other group is dealt in reverse rank order (snake), so the SUM over a rank's views
+    — what a multi-view step costs — is balanced too (plain round-robin hands rank 0 the dearest view of every group)."""
     if not (0 <= rank < world_size):
         raise ValueError(f"rank {rank} outside world of {world_size}")
     order = list(range(n_views))
@@ -26,7 +27,13 @@ def shard_views(n_views, world_size, rank, costs=None):
         if len(costs) != n_views:
             raise ValueError("one cost per view")
         order.sort(key=lambda v: (-float(costs[v]), v))
-    mine = order[rank::world_size]
+        mine = []
+        for g in range(0, n_views, world_size):
+            i = g + (rank if (g // world_size) % 2 == 0 else world_size - 1 - rank)
+            if i < n_views:
+                mine.append(order[i])
+    else:
+        mine = order[rank::world_size]
     weights = [1.0] * len(mine)
     if not mine:
         mine, weights = [rank % max(n_views, 1)], [0.0]

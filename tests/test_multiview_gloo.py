@@ -104,6 +104,13 @@ def test_shard_views_cost_sorted():
     step0 = sorted(costs[d[0]] for d in dealt)
     step1 = sorted(costs[d[1]] for d in dealt)
     assert step0 == [5, 7, 8, 9] and step1 == [1, 2, 3, 4]
+    # the second group is dealt in reverse rank order: the per-rank sums (the cost of a multi-view step) are balanced
+    sums = [sum(costs[v] for v in d) for d in dealt]
+    assert sums == [10, 10, 10, 9]
+    for n, w in ((64, 8), (10, 4), (3, 8)):
+        c = [((7 * i) % 11) + 1 for i in range(n)]
+        parts = [multiview.shard_views(n, w, r, costs=c)[0] for r in range(w)]
+        assert sorted(set(v for d in parts for v in d)) == list(range(n))
     with pytest.raises(ValueError):
         multiview.shard_views(3, 2, 0, costs=[1, 2])
 
