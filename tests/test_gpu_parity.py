@@ -1268,3 +1268,23 @@ def test_prefiltered_is_accepted_and_changes_nothing():
     a = ours_C.rasterize_gaussians(*common.fwd_args(d))
     b = ours_C.rasterize_gaussians(*common.fwd_args(dict(d, prefiltered=True)))
     assert a[0] == b[0] and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["HGS_WALK=mask", "HGS_FWD_STAGING=bulk", "HGS_SORT_RANK=ballot", "HGS_BWD_RED=scalar",
+                                     "HGS_SORT_MODE=tile"])
+def test_optional_kernel_variants_keep_parity(variant):
+    """The alternatives this round built, measured and did not adopt stay selectable by environment variable (read once
+    per process): each must pass the reference-parity cases like the default path.  Runs the forward / backward parity
+    cases (small scenes, odd shapes, all channel counts, the fused strand entry) in a child process under the variable."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    key, val = variant.split("=")
+    env = dict(os.environ, **{key: val})
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
+                        "-p", "no:cacheprovider", "-k",
+                        "forward_and_backward_vs_reference or tiny_and_odd or multichannel or fused_strands_equals"],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-1500:]
