@@ -894,14 +894,19 @@ def timed_loop(torch, step_fn, steps, warmup, world, dev, flush=None, finish=Non
         torch.cuda.synchronize(dev)
         per_step = [a.elapsed_time(b) for a, b in evs]
         ms = sum(per_step)
+    per_rank = None
     if world > 1:
         torch.distributed.barrier()
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms = float(t.item())
+        all_t = [torch.zeros_like(t) for _ in range(world)]
+        torch.distributed.all_gather(all_t, t)
+        per_rank = [round(float(x.item()) / steps, 4) for x in all_t]
+        ms = max(float(x.item()) for x in all_t)
     s = sorted(per_step)
     q = lambda f: s[min(len(s) - 1, max(0, int(round(f * (len(s) - 1)))))]  # noqa: E731
     stats = {"median": round(q(0.5), 4), "p10": round(q(0.1), 4), "p90": round(q(0.9), 4), "n": len(s)}
+    if per_rank is not None:
+        stats["per_rank_ms_per_step"] = per_rank     # the timed region of every rank (value uses the max)
     return ms, stats
 
 
@@ -1274,6 +1279,7 @@ def run():
     ms_res_3pass, ms_e2e_3pass = ms_res, None
     ms_e2e_eager, graph_note = None, None
     ms_res_eager, res_graph_note, graph_setup_s = None, None, None
+    allreduce_ms = None
     h.setup_e2e(fused=False)
     ms_e2e, st_e2e = timed_loop(torch, h.step_e2e, args.steps, args.warmup, world, dev, flush, h.finish)
     if can_fuse:
@@ -1289,8 +1295,19 @@ def run():
             graph_setup_s = time.perf_counter() - t0     # measure_plan (one eager view per camera) + warm-up + capture
             if h.fgraph is not None:
                 ms_res_eager = ms_res
+                if h.freducer is not None:
+                    h.freducer.timing = True
                 ms_res, st_res = timed_loop(torch, h.step_resident_fused_graph, args.steps, args.warmup, world, dev, flush,
                                             h.finish)
+                if h.freducer is not None:
+                    # CUDA events around every collective of the loop just timed (side stream): the residual of the scaling curve
+                    # is either here (waiting for the slowest rank + the reduction itself) or in the step (SMs shared with it)
+                    ar = h.freducer.collective_ms()[args.warmup:]
+                    h.freducer.timing = False
+                    if ar:
+                        sa = sorted(ar)
+                        allreduce_ms = {"median": round(sa[len(sa) // 2], 4), "min": round(sa[0], 4), "max": round(sa[-1], 4),
+                                        "bytes": int(h.fbucket.flat.numel()) * 4}
                 h.fgraph.check()
             res_graph_note = h.fgraph_note
         h.setup_e2e(fused=True)
@@ -1399,6 +1416,9 @@ def run():
     line["value_path"] = "three-pass drop-in: `_C.rasterize_gaussians` + `_backward` per colour set, dL/dimage fixed, inputs resident"
     line["allreduce"] = ("snapshot of the flat bucket + ONE NCCL all-reduce per step on a side stream, overlapped with the next "
                          "step's views (multiview.AsyncReducer)" if world > 1 else "none (1 rank)")
+    if allreduce_ms is not None:
+        line["allreduce_ms"] = dict(allreduce_ms, what="device time of one collective of the timed resident loop on rank 0 (CUDA events "
+                                    "on the side stream; includes the wait for the last rank to arrive)")
     line["binning_chain_ms_per_pass"] = round(binning_ms, 5)
     if can_fuse:
         line["value_path"] = ("fused strand entry: strand parameterisation + RGB/mask/orientation in ONE rasterization pass "

@@ -104,6 +104,8 @@ class AsyncReducer:
         self.stream = torch.cuda.Stream(device=device) if self.cuda else None
         self.done = None
         self.launched = 0
+        self.timing = False      # record (begin, end) CUDA events around every collective on the side stream
+        self._timed = []
 
     def _active(self):
         return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
@@ -126,11 +128,27 @@ class AsyncReducer:
         ready.record(cur)
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
+            begin = None
+            if self.timing:
+                begin = torch.cuda.Event(enable_timing=True)
+                begin.record(self.stream)
             if self._active():
                 dist.all_reduce(self.staging, op=dist.ReduceOp.SUM, group=self.group)
-            self.done = torch.cuda.Event()
+            self.done = torch.cuda.Event(enable_timing=self.timing)
             self.done.record(self.stream)
+            if begin is not None:
+                self._timed.append((begin, self.done))
         return self
+
+    def collective_ms(self):
+        """Device time of the recorded collectives (timing=True), one number per launch; synchronises the side stream.
+        A collective starts when the LAST rank arrives, so this includes the wait for the slowest rank of the step."""
+        if not self._timed:
+            return []
+        self.stream.synchronize()
+        out = [a.elapsed_time(b) for a, b in self._timed]
+        self._timed = []
+        return out
 
     def wait(self):
         """The caller's stream waits for the last launched reduction; returns the staging buffer holding the sum."""
